@@ -1,0 +1,78 @@
+"""Run the reference's OWN alignment functions, unmodified, straight from /root/reference.
+
+TEST INFRASTRUCTURE ONLY (see oracle/ssak_oracle.c).  `ssak.utils.align_transcriptions` cannot
+be imported in this image (matplotlib, speechbrain, whisper ... are missing), so the module is
+parsed with `ast` and only the nodes that make up the path are executed:
+    USE_MAX, USE_CHAR_REPEATED (:24-25), get_trellis (:27-70), Point (:72-76),
+    backtrack (:79-123), Segment (:126-138), merge_repeats (:141-157), merge_words (:159-173)
+in a namespace holding just `torch` and `dataclass`.  No reference source is copied into the
+repository; /root/reference only exists in the build container, never on the GPU box, so
+callers must guard with `available()`.  Used by tests/golden/make_golden.py (fixture
+generation) and by tests/test_oracle.py (live pin of the C restatement).
+"""
+from __future__ import annotations
+
+import ast
+import os
+
+REFERENCE_ROOT = os.environ.get("SSAK_REFERENCE_ROOT", "/root/reference")
+_ALIGN_PY = os.path.join(REFERENCE_ROOT, "ssak", "utils", "align_transcriptions.py")
+_WANTED_DEFS = {"get_trellis", "backtrack", "merge_repeats", "merge_words", "Point", "Segment"}
+_WANTED_ASSIGNS = {"USE_MAX", "USE_CHAR_REPEATED"}
+_ns = None
+
+
+def available() -> bool:
+    return os.path.isfile(_ALIGN_PY)
+
+
+def namespace() -> dict:
+    """Namespace with the reference's get_trellis/backtrack/merge_repeats/merge_words/Point/Segment."""
+    global _ns
+    if _ns is None:
+        import torch
+        from dataclasses import dataclass
+        with open(_ALIGN_PY, "r", encoding="utf-8") as f:
+            tree = ast.parse(f.read(), filename=_ALIGN_PY)
+        keep = []
+        for node in tree.body:
+            if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in _WANTED_DEFS:
+                keep.append(node)
+            elif isinstance(node, ast.Assign) and any(
+                    isinstance(t, ast.Name) and t.id in _WANTED_ASSIGNS for t in node.targets):
+                keep.append(node)
+        mod = ast.Module(body=keep, type_ignores=[])
+        ns = {"torch": torch, "dataclass": dataclass}
+        exec(compile(mod, _ALIGN_PY, "exec"), ns)
+        missing = (_WANTED_DEFS | _WANTED_ASSIGNS) - set(ns)
+        if missing:
+            raise RuntimeError(f"reference extraction incomplete: {sorted(missing)}")
+        _ns = ns
+    return _ns
+
+
+def align(emission, tokens, blank_id=0, first_as_garbage=False, want_trellis=False):
+    """Reference get_trellis -> backtrack -> merge_repeats on a torch CPU tensor [T,V].
+
+    Returns dict(status, path=[(token_index, time_index, score)], segments=[(token, start, end,
+    score)], t_start, trellis?) with status -1 when the reference raises "Failed to align"."""
+    import torch
+    ns = namespace()
+    em = torch.as_tensor(emission, dtype=torch.float32)
+    toks = [int(x) for x in tokens]
+    trellis = ns["get_trellis"](em, toks, blank_id=blank_id, first_as_garbage=first_as_garbage)
+    out = {"status": 0, "path": [], "segments": [],
+           "t_start": int(torch.argmax(trellis[:, trellis.size(1) - 1]).item())}
+    if want_trellis:
+        out["trellis"] = trellis.numpy().copy()
+    try:
+        path = ns["backtrack"](trellis, em, toks, blank_id=blank_id)
+    except RuntimeError as e:
+        if "Failed to align" not in str(e):
+            raise
+        out["status"] = -1
+        return out
+    out["path"] = [(p.token_index, p.time_index, p.score) for p in path]
+    segs = ns["merge_repeats"](list(range(len(toks))), path)
+    out["segments"] = [(s.label, s.start, s.end, s.score) for s in segs]
+    return out

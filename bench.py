@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- lattice-cells/s of the CTC loss forward+backward hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path, rank 0)
+
+Workload (BASELINE.json configs[1], "C2"): synthetic CTC loss fwd+bwd, B=64 utterances per GPU,
+T=1500 frames, V=50, L in [200,400], T_b in [1200,1500], fp32, planted-alignment emissions
+(SURVEY.md section 8d).  A step = one forward + one backward of the loss over the batch.
+cells = sum_b T_b*(2L_b+1), counted once per fwd+bwd.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B, T, V, Lmin, Lmax, Tmin)
+    "c2": (64, 1500, 50, 200, 400, 1200),
+    "1k": (1024, 1500, 50, 200, 400, 1200),
+    "c5": (512, 750, 1024, 100, 200, 600),
+}
+METRIC = "ctc_lattice_cells_per_sec"
+UNIT = "cells/s"
+
+
+def make_batch(name, seed):
+    from ssak_b200.synth import ctc_batch
+    B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
+    lp, tg, il, tl = ctc_batch(B, T, V, Lmin, Lmax, seed, Tmin=Tmin, planted=True)
+    cells = int((il * (2 * tl + 1)).sum())
+    return lp, tg, il, tl, cells
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_time(lp, tg, il, tl, repeats=3):
+    """The reference's CPU path for the loss: torch CPU F.ctc_loss fwd + bwd, all host threads."""
+    import torch.nn.functional as F
+    best = float("inf")
+    for _ in range(repeats):
+        x = lp.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        F.ctc_loss(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    lp, tg, il, tl, cells = make_batch(args.workload, 1234 + 2)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_time(lp, tg, il, tl, 1)
+    times = [cpu_reference_time(lp, tg, il, tl, 1) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    B, T, V, _, Lmax, _ = WORKLOADS[args.workload]
+    val = cells / t
+    sample = f"full {args.workload} batch (B={B}) per step, torch {torch.__version__} CPU F.ctc_loss fwd+bwd"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: CTC loss fwd+bwd B={B} T={T} V={V} L<={Lmax} (rank-0 host only)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_kernels(lib, dev, lp_d, tg32, off, il32, tl32, Lmax, iters, flush):
+    """CUDA-event time of the forward launch pair and of the backward launch, separately."""
+    T, B, V = lp_d.shape
+    ws_bytes = lib.ssak_ctc_loss_workspace_bytes(T, B, Lmax, 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nll = torch.empty(B, dtype=torch.float32, device=dev)
+    go = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(lp_d)
+    s = torch.cuda.current_stream().cuda_stream
+    tf, tb = [], []
+    for i in range(iters + 2):
+        flush.add_(1)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        rc = lib.ssak_ctc_loss_forward(lp_d.data_ptr(), T, B, V, lp_d.stride(0), lp_d.stride(1), tg32.data_ptr(),
+                                       off.data_ptr(), il32.data_ptr(), tl32.data_ptr(), Lmax, 0, 1, nll.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, s)
+        assert rc == 0
+        e1.record()
+        rc = lib.ssak_ctc_loss_backward(go.data_ptr(), lp_d.data_ptr(), T, B, V, lp_d.stride(0), lp_d.stride(1),
+                                        tg32.data_ptr(), off.data_ptr(), il32.data_ptr(), tl32.data_ptr(), Lmax, 0, 1,
+                                        nll.data_ptr(), grad.data_ptr(), grad.stride(0), grad.stride(1),
+                                        ws.data_ptr(), ws_bytes, s)
+        assert rc == 0
+        e2.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            tf.append(e0.elapsed_time(e1))
+            tb.append(e1.elapsed_time(e2))
+    return statistics.mean(tf) * 1e-3, statistics.mean(tb) * 1e-3
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import ssak_b200
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ssak_b200.lib()
+    name = args.workload
+    B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
+    lp, tg, il, tl, cells = make_batch(name, 1234 + 2 + 1000 * rank)   # weak scaling: own batch per rank
+    lp_pin, grad_pin = lp.pin_memory(), torch.empty_like(lp).pin_memory()
+    lp_d = lp_pin.to(dev, non_blocking=True)
+    tg_d, il_d, tl_d = tg.to(dev), il.to(dev), tl.to(dev)
+    flush = torch.zeros(96 * 1024 * 1024, dtype=torch.float32, device=dev)      # 384 MB > 126 MB L2
+
+    def step():
+        x = lp_d.detach().requires_grad_(True)
+        loss = ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True)
+        loss.backward()
+        return loss, x.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident throughput: K steps, CUDA events on the launching stream, L2 flushed
+    #      (384 MB write) before each step, outside the per-step event pair
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.add_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    # ---- end to end through the host-buffer C ABI: pinned host log-probs in, nll + gradient out
+    ctx = C.c_void_p()
+    assert lib.ssak_context_create(local_rank, C.byref(ctx)) == 0
+    tg32 = tg.to(torch.int32).contiguous()
+    il32, tl32 = il.to(torch.int32), tl.to(torch.int32)
+    nll_h = torch.empty(B, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        rc = lib.ssak_ctc_loss_host(ctx, lp_pin.data_ptr(), T, B, V, tg32.data_ptr(), tg32.shape[1],
+                                    il32.data_ptr(), tl32.data_ptr(), 0, 1, None, nll_h.data_ptr(),
+                                    grad_pin.data_ptr())
+        assert rc == 0, rc
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if rank == 0:
+        sampler.stop_flag.set()
+    # parity gate on the timed configuration: the host-ABI result equals the torch-facing one
+    _, g = step()
+    torch.cuda.synchronize()
+    gscale = (1.0 / (B * tl.clamp_min(1).float())).view(1, B, 1)
+    assert (g.cpu() - grad_pin * gscale).abs().max().item() < 1e-6
+
+    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    tot_cells = torch.tensor([float(cells)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_cells, op=dist.ReduceOp.SUM)
+    t_dev, t_e2e = times.tolist()
+    total = tot_cells.item()
+
+    out = None
+    if rank == 0:
+        hbm, hbm_src = peaks()
+        off = (torch.arange(B, device=dev, dtype=torch.int64) * tg.shape[1])
+        t_fwd, t_bwd = time_kernels(lib, dev, lp_d, tg32.to(dev), off, il32.to(dev), tl32.to(dev), int(tl.max()),
+                                    max(args.steps, 5), flush)
+        sumTV = float(il.sum()) * V
+        bwd_bytes = 8.0 * sumTV            # read every emission row once + write the gradient row
+        achieved = bwd_bytes / t_bwd / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(name)
+        cpu_s = cpu_reference_time(lp, tg, il, tl, 3)
+        ncores = os.cpu_count() or 1
+        h2d = lp.numel() * 4 + tg32.numel() * 4 + 2 * B * 4 + B * 8 + B * 4
+        d2h = lp.numel() * 4 + B * 4
+        out = {
+            "metric": METRIC, "value": total * args.steps / t_dev, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: CTC loss fwd+bwd, B={B} per GPU, T={T}, V={V}, L in [{Lmin},{Lmax}], "
+                                   f"T_b in [{Tmin},{T}], planted-alignment emissions, reduction=mean, zero_infinity",
+                       "cells_per_step_per_gpu": cells, "l2": "flushed (384 MB write) before every timed step",
+                       "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
+            "e2e": {"value": total * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "path": "ssak_ctc_loss_host (C ABI): pinned host log-probs in, nll + full gradient out"},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "ctc_lattice_kernel<K,true> (backward: recursion + gradient)",
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": traffic, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_launch": bwd_bytes, "launch_ms": t_bwd * 1e3,
+                         "forward_launch_ms": t_fwd * 1e3,
+                         "forward_achieved_gbs": 4.0 * sumTV / t_fwd / 1e9,
+                         "note": "V=50: 0.75 B/cell of compulsory traffic, the kernel is bound by the serial "
+                                 "recursion and MUFU (DESIGN.md), not by HBM"},
+            "cpu_baseline": {"value": cells / cpu_s, "unit": UNIT, "cores": ncores, "kind": "reference",
+                             "sample": f"full {name} batch (B={B}) fwd+bwd, best of 3, torch {torch.__version__} "
+                                       f"CPU F.ctc_loss with {ncores} threads"},
+            "clocks": sampler.summary(),
+        }
+        if args.extra:
+            out["extra"] = extra_numbers(lib, dev, flush)
+    lib.ssak_context_destroy(ctx)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def extra_numbers(lib, dev, flush):
+    """Other configurations of BASELINE.json, device-resident, kernels only (informational)."""
+    import ssak_b200
+    from ssak_b200.synth import align_batch
+    res = {}
+    for name in ("1k", "c5"):
+        try:
+            B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
+            lp, tg, il, tl, cells = make_batch(name, 99)
+            lp_d = lp.to(dev)
+            off = torch.arange(B, device=dev, dtype=torch.int64) * tg.shape[1]
+            tf, tb = time_kernels(lib, dev, lp_d, tg.to(torch.int32).to(dev), off, il.to(torch.int32).to(dev),
+                                  tl.to(torch.int32).to(dev), int(tl.max()), 5, flush)
+            sumTV = float(il.sum()) * V
+            res[f"loss_{name}"] = {"cells_per_s": cells / (tf + tb), "fwd_ms": tf * 1e3, "bwd_ms": tb * 1e3,
+                                   "hbm_frac_canonical_12B": 12.0 * sumTV / (tf + tb) / 1e9 / peaks()[0]}
+            del lp_d
+        except Exception as e:  # keep the headline line even if an extra shape fails
+            res[f"loss_{name}"] = {"error": repr(e)}
+    for name, (B, T, V, Lmin, Lmax, Tmin) in {"align_c5": (512, 750, 1024, 100, 200, 600),
+                                               "align_c2shape": (64, 1500, 50, 200, 400, 1200)}.items():
+        try:
+            em, toks, el, tl = align_batch(B, T, V, Lmin, Lmax, 5, Tmin=Tmin)
+            em_d = em.to(dev)
+            ts = []
+            for i in range(5):
+                flush.add_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                r = ssak_b200.forced_align(em_d, toks, el, tl)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) * 1e-3)
+            cells = int((el.long() * (tl.long() + 1)).sum())
+            t = statistics.mean(ts[1:])
+            res[name] = {"cells_per_s": cells / t, "ms": t * 1e3, "aligned": int((r.status == 0).sum())}
+            del em_d
+        except Exception as e:
+            res[name] = {"error": repr(e)}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--extra", action="store_true", help="also time the other BASELINE configs (rank 0)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""ssak_b200 -- B200 (sm_100a) kernels for the CTC lattice path of linto-ai/ssak.
+
+Public API (same call signatures as the reference's call sites, see each module):
+    ctc_loss, sb_ctc_loss, install            -- torch.nn.functional.ctc_loss replacement
+    forced_align, get_trellis, backtrack,
+    merge_repeats, merge_words, Point, Segment -- ssak/utils/align_transcriptions.py
+    ctc_greedy_decode, argmax_ids             -- greedy CTC collapse
+The compute lives in libssak_b200.so (C ABI: include/ssak_b200.h); there is no CPU fallback.
+"""
+from ._lib import LIB_PATH, SsakB200Error, lib  # noqa: F401
+from .align import (AlignResult, Point, Segment, Trellis, backtrack, forced_align, get_trellis,  # noqa: F401
+                    merge_repeats, merge_words, segments_from_result)
+from .greedy import argmax_ids, ctc_greedy_decode, greedy_ids, hf_collapse  # noqa: F401
+from .loss import ctc_loss, ctc_neg_log_likelihood, install, sb_ctc_loss, uninstall  # noqa: F401
+
+__version__ = "0.1.0"

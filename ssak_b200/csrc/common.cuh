@@ -1,0 +1,145 @@
+// common.cuh -- device helpers shared by the sm_100a CTC lattice kernels.
+//
+// PTX wrappers for the pieces of the Blackwell execution model the kernels use:
+//   * mbarrier (init / arrive.expect_tx / try_wait.parity) as the completion mechanism of
+//   * cp.async.bulk (1-D TMA bulk copy, SASS UBLKCP) global -> shared, used to prefetch
+//     emission rows for the next frames into a shared-memory ring,
+//   * MUFU ex2 / lg2 for the log2-domain log-sum-exp,
+// plus the emission-ring bookkeeping (aligned super-range copies so that rows of any
+// element alignment can be moved by the 16-byte-granular bulk copy engine).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ssak {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+// Finite stand-in for log(0): keeps (-inf) - (-inf) NaNs out of the log-sum-exp without
+// branches.  ex2(kNeg - x) == 0 for every finite x that can occur, and kNeg absorbs the
+// O(T) additions it sees, so an unreachable state stays "minus infinity".
+constexpr float kNeg = -1.0e30f;
+constexpr float kNegTest = -1.0e29f;  // value < kNegTest  <=>  log(0)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log2(2^a + 2^b): one MUFU.EX2 + one MUFU.LG2.
+__device__ __forceinline__ float lse2(float a, float b) {
+    const float m = fmaxf(a, b);
+    const float d = fminf(a, b) - m;
+    return m + lg2_approx(1.0f + ex2_approx(d));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------- bulk copy (1-D TMA)
+// global -> shared::cta, completion counted in bytes on `bar`.  dst, src 16-byte aligned,
+// bytes a positive multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// --------------------------------------------------------------------------- row ring
+// A ring of `stages` chunks of `chunk` frame rows each.  A row of V floats that starts at an
+// arbitrary 4-byte-aligned global address is fetched as the enclosing 16-byte-aligned byte
+// range; its first element then sits (addr & 15) bytes into the slot.
+struct RowRing {
+    unsigned char *slots;  // stages * chunk * slot_bytes, 16-byte aligned
+    uint64_t *full;        // one mbarrier per stage
+    int chunk;             // frames per stage
+    int stages;
+    int slot_bytes;        // >= round16(4V) + 32
+    int row_bytes;         // 4V
+};
+
+__host__ __device__ __forceinline__ int ring_slot_bytes(int V) {
+    return ((4 * V + 15) & ~15) + 32;
+}
+
+// Issue the copies of one chunk (executed by ONE thread).  Frame f (0 <= f < n) of the chunk
+// is global row base + frame_index(f) * stride_t, with frame_index(f) = t0 + f * dt.
+__device__ __forceinline__ void ring_issue(const RowRing &r, int stage, const float *base,
+                                           int64_t stride_t, int t0, int dt, int n) {
+    uint32_t total = 0;
+    for (int f = 0; f < n; ++f) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base + (int64_t)(t0 + f * dt) * stride_t);
+        const uintptr_t a0 = a & ~(uintptr_t)15;
+        total += (uint32_t)(((a + r.row_bytes + 15) & ~(uintptr_t)15) - a0);
+    }
+    mbar_arrive_expect_tx(&r.full[stage], total);
+    for (int f = 0; f < n; ++f) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base + (int64_t)(t0 + f * dt) * stride_t);
+        const uintptr_t a0 = a & ~(uintptr_t)15;
+        const uint32_t bytes = (uint32_t)(((a + r.row_bytes + 15) & ~(uintptr_t)15) - a0);
+        bulk_g2s(r.slots + (size_t)(stage * r.chunk + f) * r.slot_bytes,
+                 reinterpret_cast<const void *>(a0), bytes, &r.full[stage]);
+    }
+}
+
+// Pointer to the V floats of frame f of `stage` (frame at global row index t).
+__device__ __forceinline__ const float *ring_row(const RowRing &r, int stage, int f,
+                                                 const float *base, int64_t stride_t, int t) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base + (int64_t)t * stride_t);
+    return reinterpret_cast<const float *>(r.slots + (size_t)(stage * r.chunk + f) * r.slot_bytes +
+                                           (a & 15));
+}
+
+}  // namespace ssak
+
+// --------------------------------------------------------------------- host-side helpers
+#include "../../include/ssak_b200.h"
+
+namespace ssak {
+void set_last_cuda_error(cudaError_t e);
+inline int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_cuda_error(e);
+        return SSAK_ERR_CUDA;
+    }
+    return SSAK_OK;
+}
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace ssak

@@ -1,0 +1,219 @@
+"""CTC loss with torch.nn.functional.ctc_loss's signature, on the sm_100a kernels.
+
+Reference call sites this drops into (paths relative to the reference repository):
+  * HF wav2vec2: site-packages/transformers/models/wav2vec2/modeling_wav2vec2.py:1727-1736,
+    configured at ssak/train/transformers/wav2vec_train.py:313-325 (reduction="mean",
+    zero_infinity=True, 1-D concatenated int64 targets, transposed [T,B,V] view)
+  * SpeechBrain: ssak/train/speechbrain/wav2vec_train.py:66 through the yaml key `ctc_cost`
+    (ssak/train/speechbrain/fr/hyperparameters_wav2vec_finetune_cv-fr.yaml:116-117) -> `sb_ctc_loss`
+  * NeMo: ssak/train/nemo/yamls/model.yaml:3 (`ctc_reduction: mean_volume`) -> `reduction="mean_volume"`
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_REDUCTIONS = ("none", "mean", "sum", "mean_volume")
+
+
+def _as_length_tensor(x, B: int, device, name: str):
+    """-> (int32 device tensor [B], host list or None)."""
+    host = None
+    if isinstance(x, torch.Tensor):
+        if x.dim() == 0:
+            x = x.reshape(1)
+        if x.numel() != B:
+            raise RuntimeError(f"{name} must be of size batch_size ({B}), got {x.numel()}")
+        if x.is_floating_point():
+            raise RuntimeError(f"{name} must be integral")
+        if not x.is_cuda:
+            host = [int(v) for v in x.tolist()]
+        dev = x.to(device=device, dtype=torch.int32, non_blocking=True)
+    else:
+        host = [int(v) for v in x]
+        if len(host) != B:
+            raise RuntimeError(f"{name} must be of size batch_size ({B}), got {len(host)}")
+        dev = torch.tensor(host, dtype=torch.int32, device=device)
+    return dev, host
+
+
+class _CTCLossFunction(torch.autograd.Function):
+    """aten::_ctc_loss / _ctc_loss_backward on libssak_b200.so: forward -> nll[B]."""
+
+    @staticmethod
+    def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity):
+        L = _lib.lib()
+        T, B, V = log_probs.shape
+        save = bool(ctx.needs_input_grad[0])
+        ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, max_target_len, int(save))
+        if ws_bytes == 0:
+            raise _lib.SsakB200Error(
+                f"ctc_loss: shape not supported (T={T}, B={B}, max target length={max_target_len})")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=log_probs.device)
+        nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
+        stream = torch.cuda.current_stream(log_probs.device).cuda_stream
+        rc = L.ssak_ctc_loss_forward(log_probs.data_ptr(), T, B, V, log_probs.stride(0), log_probs.stride(1),
+                                     targets.data_ptr(), tgt_off.data_ptr(), in_len.data_ptr(),
+                                     tgt_len.data_ptr(), max_target_len, blank, int(save), nll.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "ssak_ctc_loss_forward")
+        if save:
+            ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws)
+            ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes)
+        return nll
+
+    @staticmethod
+    def backward(ctx, grad_nll):
+        log_probs, targets, tgt_off, in_len, tgt_len, nll, ws = ctx.saved_tensors
+        max_target_len, blank, zero_infinity, ws_bytes = ctx.meta
+        L = _lib.lib()
+        T, B, V = log_probs.shape
+        g = grad_nll.to(torch.float32).contiguous()
+        # same (dense) layout as log_probs: HF hands in a transposed [B,T,V] buffer and its
+        # log_softmax backward reads the gradient in that layout
+        grad = torch.empty_like(log_probs)
+        if grad.stride(2) != 1:
+            grad = torch.empty((T, B, V), dtype=torch.float32, device=log_probs.device)
+        with torch.cuda.device(log_probs.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = L.ssak_ctc_loss_backward(g.data_ptr(), log_probs.data_ptr(), T, B, V, log_probs.stride(0),
+                                          log_probs.stride(1), targets.data_ptr(), tgt_off.data_ptr(),
+                                          in_len.data_ptr(), tgt_len.data_ptr(), max_target_len, blank,
+                                          int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
+                                          grad.stride(1), ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "ssak_ctc_loss_backward")
+        return grad, None, None, None, None, None, None, None
+
+
+def ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, blank=0, zero_infinity=False):
+    """Per-utterance negative log-likelihood [B] (+inf when infeasible), differentiable w.r.t.
+    `log_probs` with torch's gradient convention.  Arguments as torch.nn.functional.ctc_loss."""
+    _lib.require_cuda(log_probs, "log_probs")
+    unbatched = log_probs.dim() == 2
+    if unbatched:
+        log_probs = log_probs.unsqueeze(1)
+        if isinstance(targets, torch.Tensor) and targets.dim() == 1:
+            targets = targets.unsqueeze(0)
+    if log_probs.dim() != 3:
+        raise RuntimeError("log_probs must be [T, B, V] (or [T, V])")
+    if log_probs.dtype != torch.float32:
+        log_probs = log_probs.float()
+    if log_probs.stride(2) != 1 and log_probs.size(2) > 1:
+        log_probs = log_probs.contiguous()
+    T, B, V = log_probs.shape
+    if not (0 <= int(blank) < V):
+        raise RuntimeError("blank must be in label range")
+    dev = log_probs.device
+    in_len, in_host = _as_length_tensor(input_lengths, B, dev, "input_lengths")
+    tgt_len, tgt_host = _as_length_tensor(target_lengths, B, dev, "target_lengths")
+    if not isinstance(targets, torch.Tensor):
+        targets = torch.as_tensor(targets)
+    if targets.is_floating_point():
+        raise RuntimeError("targets must be integral")
+    tg = targets.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+    if tg.dim() == 2:
+        if tg.size(0) != B:
+            raise RuntimeError(f"targets must have batch size {B}")
+        smax = tg.size(1)
+        tgt_off = torch.arange(B, device=dev, dtype=torch.int64) * smax
+        max_target_len = smax
+        if tgt_host is not None:
+            if max(tgt_host, default=0) > smax:
+                raise RuntimeError("Expected tensor to have size at least max(target_lengths) along dimension 1")
+            max_target_len = max(tgt_host, default=0)
+    elif tg.dim() == 1:
+        tl64 = tgt_len.to(torch.int64)
+        tgt_off = torch.cumsum(tl64, 0) - tl64
+        if tgt_host is None:
+            # concatenated targets with device lengths (the HF call): one sync, as torch itself does
+            tgt_host = [int(v) for v in tgt_len.tolist()]
+        max_target_len = max(tgt_host, default=0)
+        if sum(tgt_host) > tg.numel():
+            raise RuntimeError("Expected targets to hold sum(target_lengths) elements")
+    else:
+        raise RuntimeError("targets must be 1-D (concatenated) or 2-D (padded)")
+    if in_host is not None and (max(in_host, default=0) > T or min(in_host, default=0) < 0):
+        raise RuntimeError(f"Expected input_lengths to have value at most {T}, but got value "
+                           f"{max(in_host)} (while checking arguments for ctc_loss)")
+    if tgt_host is not None and min(tgt_host, default=0) < 0:
+        raise RuntimeError("Expected target_lengths to have non-negative values")
+    if tg.numel() == 0:
+        tg = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        return _CTCLossFunction.apply(log_probs, tg, tgt_off, in_len, tgt_len, int(max_target_len),
+                                      int(blank), bool(zero_infinity)), tgt_len
+
+
+def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean",
+             zero_infinity=False):
+    """Drop-in for torch.nn.functional.ctc_loss (site-packages/torch/nn/functional.py:3042-3115).
+
+    Extra reduction "mean_volume" = sum(nll) / sum(target_lengths) (NeMo, model.yaml:3)."""
+    if reduction not in _REDUCTIONS:
+        raise ValueError(f"{reduction} is not a valid value for reduction")
+    nll, tgt_len = ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, blank,
+                                          zero_infinity)
+    if zero_infinity:
+        nll = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll)
+    if reduction == "none":
+        return nll[0] if log_probs.dim() == 2 else nll
+    if reduction == "sum":
+        return nll.sum()
+    if reduction == "mean_volume":
+        return nll.sum() / tgt_len.sum().clamp_min(1).to(nll.dtype)
+    return (nll / tgt_len.clamp_min(1).to(nll.dtype)).mean()
+
+
+def sb_ctc_loss(log_probs, targets, input_lens, target_lens, blank_index, reduction="mean"):
+    """SpeechBrain's `speechbrain.nnet.losses.ctc_loss` wrapper (the `ctc_cost` yaml hook,
+    ssak/train/speechbrain/fr/hyperparameters_wav2vec_finetune_cv-fr.yaml:116-117):
+    log_probs [B,T,V], relative lengths in (0,1], zero_infinity=True."""
+    input_lens = (input_lens * log_probs.shape[1]).round().int()
+    target_lens = (target_lens * targets.shape[1]).round().int()
+    lp = log_probs.transpose(0, 1)
+    if reduction == "batchmean":
+        red = "sum"
+    elif reduction == "batch":
+        red = "none"
+    else:
+        red = reduction
+    loss = ctc_loss(lp, targets, input_lens, target_lens, blank_index, reduction=red, zero_infinity=True)
+    if reduction == "batchmean":
+        return loss / targets.shape[0]
+    if reduction == "batch":
+        N = loss.size(0)
+        return loss.view(N, -1).sum(1) / target_lens.view(N, -1).sum(1)
+    return loss
+
+
+_torch_ctc_loss = None
+
+
+def install() -> None:
+    """Route torch.nn.functional.ctc_loss to the sm_100a kernels for CUDA inputs (HF, SpeechBrain
+    and NeMo all end up there).  CPU tensors keep going to torch's own CPU kernel."""
+    global _torch_ctc_loss
+    import torch.nn.functional as F
+    if _torch_ctc_loss is not None:
+        return
+    _lib.lib()  # fail now if the library is missing
+    _torch_ctc_loss = F.ctc_loss
+
+    def patched(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean",
+                zero_infinity=False):
+        if isinstance(log_probs, torch.Tensor) and log_probs.is_cuda:
+            return ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, reduction, zero_infinity)
+        return _torch_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, reduction,
+                               zero_infinity)
+
+    patched.__wrapped__ = _torch_ctc_loss
+    F.ctc_loss = patched
+
+
+def uninstall() -> None:
+    global _torch_ctc_loss
+    import torch.nn.functional as F
+    if _torch_ctc_loss is not None:
+        F.ctc_loss = _torch_ctc_loss
+        _torch_ctc_loss = None

@@ -1,0 +1,161 @@
+"""Parity of the CUDA aligner (through the C ABI) with the oracle / the reference-generated
+fixtures.  Bar: spans, t_start, status and the decision path bit-exact; per-token scores (they
+contain an exp) within 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_cases
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+SCORE_RTOL = 1e-6
+
+
+def _run(em, toks, el=None, tl=None, blank=0, fag=False, **kw):
+    import ssak_b200
+    res = ssak_b200.forced_align(em.cuda(), toks, el, tl, blank_id=blank, first_as_garbage=fag, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _check_batch(em, toks, el, tl, blank=0, fag=False, res=None, tag=""):
+    res = _run(em, toks, el, tl, blank, fag) if res is None else res
+    st, en, sc = res.starts.cpu().numpy(), res.ends.cpu().numpy(), res.scores.cpu().numpy()
+    status, ts = res.status.cpu().numpy(), res.t_start.cpu().numpy()
+    n_ok = 0
+    for b in range(em.shape[0]):
+        Tb, Lb = int(el[b]), int(tl[b])
+        rc, ss, se, ssc, t0 = O.align(em[b, :Tb].numpy(), toks[b, :Lb].tolist(), blank, fag)
+        assert (status[b] == 0) == (rc == 0), f"{tag} b={b} status {status[b]} vs oracle {rc}"
+        if rc != 0:
+            continue
+        n_ok += 1
+        assert ts[b] == t0, f"{tag} b={b} t_start {ts[b]} vs {t0}"
+        assert st[b, :Lb].tolist() == ss.tolist(), f"{tag} b={b} starts differ"
+        assert en[b, :Lb].tolist() == se.tolist(), f"{tag} b={b} ends differ"
+        np.testing.assert_allclose(sc[b, :Lb], ssc, rtol=SCORE_RTOL, atol=0, err_msg=f"{tag} b={b} scores")
+    return n_ok
+
+
+def test_align_golden_fixtures(golden_dir):
+    """Every reference-generated case: trellis bit-exact (debug dump), path, spans, scores."""
+    import ssak_b200
+    for i, c in enumerate(load_cases(os.path.join(golden_dir, "align_golden.npz"))):
+        e = torch.from_numpy(c["emission"])
+        toks = c["tokens"].tolist()
+        blank, fag = int(c["blank"]), bool(c["first_as_garbage"])
+        T, L = e.shape[0], len(toks)
+        tk = torch.tensor([toks], dtype=torch.int32).reshape(1, L)
+        res = _run(e.unsqueeze(0), tk, blank=blank, fag=fag, return_path=True, return_trellis=True)
+        tr = res.trellis[0].cpu().numpy()
+        assert np.array_equal(tr.view(np.int32), c["trellis"].view(np.int32)), f"case {i}: trellis bits"
+        assert int(res.status[0]) == (0 if int(c["status"]) == 0 else 1), f"case {i}: status"
+        assert int(res.t_start[0]) == int(c["t_start"]) or L == 0, f"case {i}: t_start"
+        if int(c["status"]) != 0:
+            continue
+        assert res.starts[0].cpu().tolist() == c["seg_start"].tolist(), f"case {i}: starts"
+        assert res.ends[0].cpu().tolist() == c["seg_end"].tolist(), f"case {i}: ends"
+        np.testing.assert_allclose(res.scores[0].cpu().numpy(), c["seg_score"], rtol=SCORE_RTOL)
+        ptok = res.path_token[0].cpu().numpy()
+        frames = np.nonzero(ptok >= 0)[0]
+        assert frames.tolist() == c["path_time"].tolist(), f"case {i}: path frames"
+        assert ptok[frames].tolist() == c["path_token"].tolist(), f"case {i}: path tokens"
+        np.testing.assert_allclose(res.path_prob[0].cpu().numpy()[frames], c["path_score"], rtol=SCORE_RTOL)
+        # reference-shaped API
+        trl = ssak_b200.get_trellis(e.cuda(), toks, blank_id=blank, first_as_garbage=fag)
+        assert trl.size(0) == T + 1
+        path = ssak_b200.backtrack(trl, e.cuda(), toks, blank_id=blank)
+        assert [(p.token_index, p.time_index) for p in path] == list(zip(c["path_token"].tolist(), c["path_time"].tolist()))
+        segs = ssak_b200.merge_repeats(list(range(L)), path)
+        assert [(s.start, s.end) for s in segs] == list(zip(c["seg_start"].tolist(), c["seg_end"].tolist()))
+
+
+@pytest.mark.parametrize("kind", ["random", "tie", "planted"])
+@pytest.mark.parametrize("fag", [False, True])
+def test_align_random_ragged_batches(kind, fag):
+    from ssak_b200.synth import align_batch
+    total = 0
+    for seed, (B, T, V, Lmin, Lmax) in enumerate([(9, 60, 7, 1, 20), (6, 200, 50, 10, 70), (5, 97, 33, 1, 96),
+                                                   (4, 300, 50, 100, 140)]):
+        em, toks, el, tl = align_batch(B, T, V, Lmin, Lmax, 100 + seed, Tmin=max(1, T // 2), kind=kind)
+        total += _check_batch(em, toks, el, tl, 0, fag, tag=f"{kind}/{fag}/{seed}")
+    assert total > 0
+
+
+def test_align_edge_cases():
+    from ssak_b200.synth import align_batch
+    # L > T, L == T, L == 1, L == 0 in one ragged batch; blank != 0
+    em, toks, el, tl = align_batch(6, 40, 9, 1, 45, 7, kind="planted", blank=4)
+    el = torch.tensor([40, 3, 40, 12, 40, 40], dtype=torch.int32)
+    tl = torch.tensor([45, 5, 40, 12, 1, 0], dtype=torch.int32)
+    res = _run(em, toks, el, tl, blank=4)
+    assert res.status.cpu().tolist()[:2] == [1, 1] and int(res.status[5]) == 1
+    _check_batch(em, toks, el, tl, blank=4, res=res, tag="edge")
+    # SpeechBrain-style padded frames (-700, blank 0.0)
+    em2, toks2, el2, tl2 = align_batch(3, 80, 12, 5, 20, 8, kind="planted")
+    em2[:, -16:, :] = -700.0
+    em2[:, -16:, 0] = 0.0
+    assert _check_batch(em2, toks2, el2, tl2, tag="sb_padded") == 3
+
+
+def test_align_non_contiguous_and_long_labels():
+    from ssak_b200.synth import align_batch
+    # emissions as a [T,B,V] -> [B,T,V] transposed view (strided batch/time axes)
+    em, toks, el, tl = align_batch(4, 150, 50, 20, 60, 21, Tmin=100)
+    em_tbv = em.transpose(0, 1).contiguous().cuda()
+    import ssak_b200
+    res = ssak_b200.forced_align(em_tbv.transpose(0, 1), toks, el, tl)
+    _check_batch(em, toks, el, tl, res=res, tag="strided")
+    # several states per lane and many warps (L+1 > 1024 -> K >= 4)
+    em, toks, el, tl = align_batch(2, 2600, 50, 1100, 1300, 22, Tmin=2500)
+    assert _check_batch(em, toks, el, tl, tag="longL") == 2
+    # V = 1024 (BPE-sized rows, chunked ring)
+    em, toks, el, tl = align_batch(3, 300, 1024, 40, 90, 23, Tmin=200)
+    assert _check_batch(em, toks, el, tl, tag="V1024") == 3
+
+
+def test_align_host_abi():
+    """The host-buffer C entry point (what a non-torch caller binds)."""
+    import ctypes as C
+    import ssak_b200
+    from ssak_b200.synth import align_batch
+    L = ssak_b200.lib()
+    em, toks, el, tl = align_batch(3, 90, 20, 5, 30, 31, Tmin=60)
+    ctx = C.c_void_p()
+    assert L.ssak_context_create(0, C.byref(ctx)) == 0
+    B, T, V = em.shape
+    Lm = toks.shape[1]
+    emn, tkn = np.ascontiguousarray(em.numpy()), np.ascontiguousarray(toks.numpy().astype(np.int32))
+    eln, tln = el.numpy().astype(np.int32), tl.numpy().astype(np.int32)
+    st, en = np.zeros((B, Lm), np.int32), np.zeros((B, Lm), np.int32)
+    sc, ts, status = np.zeros((B, Lm), np.float64), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    rc = L.ssak_forced_align_host(ctx, emn.ctypes.data, B, T, V, tkn.ctypes.data, Lm, eln.ctypes.data,
+                                  tln.ctypes.data, 0, 0, None, st.ctypes.data, en.ctypes.data, sc.ctypes.data,
+                                  ts.ctypes.data, status.ctypes.data)
+    assert rc == 0
+    L.ssak_context_destroy(ctx)
+    for b in range(B):
+        rcb, ss, se, ssc, t0 = O.align(emn[b, : eln[b]], tkn[b, : tln[b]].tolist())
+        assert rcb == 0 and status[b] == 0 and ts[b] == t0
+        assert st[b, : tln[b]].tolist() == ss.tolist() and en[b, : tln[b]].tolist() == se.tolist()
+
+
+def test_align_full_size_properties():
+    """C5-shaped batch (B=512 would take the oracle minutes): properties that hold at any size --
+    spans are sorted, contiguous, inside [0, t_start], scores in (0, 1]; plus an oracle spot-check."""
+    from ssak_b200.synth import align_batch
+    em, toks, el, tl = align_batch(64, 750, 1024, 100, 200, 41, Tmin=600)
+    res = _run(em, toks, el, tl)
+    st, en, sc = res.starts.cpu().numpy(), res.ends.cpu().numpy(), res.scores.cpu().numpy()
+    ts, status = res.t_start.cpu().numpy(), res.status.cpu().numpy()
+    assert (status == 0).all()
+    for b in range(em.shape[0]):
+        Lb = int(tl[b])
+        assert (st[b, :Lb] < en[b, :Lb]).all() and (en[b, : Lb - 1] == st[b, 1:Lb]).all()
+        assert en[b, Lb - 1] == ts[b] <= int(el[b]) and st[b, 0] >= 0
+        assert ((sc[b, :Lb] > 0) & (sc[b, :Lb] <= 1.0 + 1e-6)).all()
+    idx = [0, 17, 63]
+    _check_batch(em[idx], toks[idx], el[idx], tl[idx], res=None, tag="C5 spot")

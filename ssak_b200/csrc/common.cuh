@@ -98,32 +98,76 @@ __host__ __device__ __forceinline__ int ring_slot_bytes(int V) {
     return ((4 * V + 15) & ~15) + 32;
 }
 
-// Issue the copies of one chunk (executed by ONE thread).  Frame f (0 <= f < n) of the chunk
-// is global row base + frame_index(f) * stride_t, with frame_index(f) = t0 + f * dt.
-__device__ __forceinline__ void ring_issue(const RowRing &r, int stage, const float *base,
-                                           int64_t stride_t, int t0, int dt, int n) {
+// Producer-side cursor: the next chunk to fetch (kept by the one thread that issues copies).
+struct RingProducer {
+    const float *src;    // global address of the first frame row of the next chunk
+    int64_t step_elems;  // elements between consecutive frames (negative: time runs backwards)
+    int stage;           // stage the next chunk goes to
+    int remaining;       // frames not issued yet
+};
+
+// Issue the copies of the next chunk (executed by ONE thread).
+__device__ __forceinline__ void ring_issue_next(const RowRing &r, RingProducer &pr) {
+    const int n = pr.remaining < r.chunk ? pr.remaining : r.chunk;
+    if (n <= 0) return;
     uint32_t total = 0;
-    for (int f = 0; f < n; ++f) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(base + (int64_t)(t0 + f * dt) * stride_t);
-        const uintptr_t a0 = a & ~(uintptr_t)15;
-        total += (uint32_t)(((a + r.row_bytes + 15) & ~(uintptr_t)15) - a0);
+    const float *s = pr.src;
+    for (int f = 0; f < n; ++f, s += pr.step_elems) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        total += (uint32_t)(((a + r.row_bytes + 15) & ~(uintptr_t)15) - (a & ~(uintptr_t)15));
     }
-    mbar_arrive_expect_tx(&r.full[stage], total);
-    for (int f = 0; f < n; ++f) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(base + (int64_t)(t0 + f * dt) * stride_t);
+    mbar_arrive_expect_tx(&r.full[pr.stage], total);
+    unsigned char *dst = r.slots + (size_t)pr.stage * r.chunk * r.slot_bytes;
+    s = pr.src;
+    for (int f = 0; f < n; ++f, s += pr.step_elems, dst += r.slot_bytes) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
         const uintptr_t a0 = a & ~(uintptr_t)15;
-        const uint32_t bytes = (uint32_t)(((a + r.row_bytes + 15) & ~(uintptr_t)15) - a0);
-        bulk_g2s(r.slots + (size_t)(stage * r.chunk + f) * r.slot_bytes,
-                 reinterpret_cast<const void *>(a0), bytes, &r.full[stage]);
+        bulk_g2s(dst, reinterpret_cast<const void *>(a0),
+                 (uint32_t)(((a + r.row_bytes + 15) & ~(uintptr_t)15) - a0), &r.full[pr.stage]);
     }
+    pr.src = s;
+    pr.remaining -= n;
+    if (++pr.stage == r.stages) pr.stage = 0;
 }
 
-// Pointer to the V floats of frame f of `stage` (frame at global row index t).
-__device__ __forceinline__ const float *ring_row(const RowRing &r, int stage, int f,
-                                                 const float *base, int64_t stride_t, int t) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(base + (int64_t)t * stride_t);
-    return reinterpret_cast<const float *>(r.slots + (size_t)(stage * r.chunk + f) * r.slot_bytes +
-                                           (a & 15));
+// Consumer-side cursor over the frames of the ring: no divisions in the time loop.
+struct RingPos {
+    int f, stage, phase, slot;
+    uint32_t a15, a15_step;
+    __device__ __forceinline__ void init(const float *first_row, int64_t step_elems) {
+        f = stage = phase = slot = 0;
+        a15 = (uint32_t)(reinterpret_cast<uintptr_t>(first_row) & 15);
+        a15_step = (uint32_t)((step_elems * 4) & 15);
+    }
+    // wait for the chunk when entering it, return the V floats of the current frame
+    __device__ __forceinline__ const float *row(const RowRing &r) const {
+        if (f == 0) mbar_wait(&r.full[stage], (uint32_t)phase);
+        return reinterpret_cast<const float *>(r.slots + (size_t)slot * r.slot_bytes + a15);
+    }
+    __device__ __forceinline__ void advance(const RowRing &r) {
+        a15 = (a15 + a15_step) & 15u;
+        ++slot;
+        if (++f == r.chunk) {
+            f = 0;
+            if (++stage == r.stages) {
+                stage = 0;
+                phase ^= 1;
+                slot = 0;
+            }
+        }
+    }
+};
+
+// Order-preserving float <-> int map, so that a warp-wide float max is one integer REDUX.
+__device__ __forceinline__ int float_order_key(float x) {
+    const int b = __float_as_int(x);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float float_from_order_key(int k) {
+    return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
+}
+__device__ __forceinline__ float warp_max(float x) {
+    return float_from_order_key(__reduce_max_sync(0xffffffffu, float_order_key(x)));
 }
 
 }  // namespace ssak

@@ -81,6 +81,9 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const float INF = __int_as_float(0x7f800000);
+    const int W = c.W;
+    const bool compute = warp < W;
+    const int prod_warp = W < 32 ? W : 0;  // dedicated producer warp when the CTA has room
 
     int Tb = p.em_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.Tmax ? (int)p.Tmax : Tb);
@@ -88,6 +91,12 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     if (L == 0 || Tb == 0) {  // reference: empty back-track loop -> "Failed to align"
         if (tid == 0) p.t_start[b] = 0;
+        if (p.dump) {  // :41-42 with an empty token list / no frames: column 0 is all +inf
+            float *d = p.dump + (int64_t)b * (p.Tmax + 1) * (p.Lmax + 1);
+            for (int t = tid; t <= Tb; t += blockDim.x) d[(int64_t)t * (p.Lmax + 1)] = INF;
+            if (Tb == 0)
+                for (int j = 1 + tid; j <= L; j += blockDim.x) d[j] = -INF;
+        }
         return;
     }
     const int V = p.V;
@@ -125,93 +134,97 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
         v[k] = j == 0 ? (L >= Tb + 1 ? INF : 0.f) : -INF;
     }
     const int jL_rel = L - warp * 32 * K;  // state L inside this warp?
-    const bool ownsL = jL_rel >= 0 && jL_rel < 32 * K && (jL_rel & 31) == lane;
+    const bool ownsL = compute && jL_rel >= 0 && jL_rel < 32 * K && (jL_rel & 31) == lane;
     const int kL = jL_rel >> 5;
     float best = -INF;  // trellis[0, L] with L >= 1
     int best_t = 0;
-    if (p.dump) {
+    if (p.dump && compute) {
         float *d = p.dump + (int64_t)b * (p.Tmax + 1) * (p.Lmax + 1);
 #pragma unroll
         for (int k = 0; k < K; ++k)
             if (jbase + k * 32 <= L) d[jbase + k * 32] = v[k];
     }
-    if (lane == 31) xchg[warp] = v[K - 1];
+    if (compute && lane == 31) xchg[warp] = v[K - 1];
     __syncthreads();
 
     const int C = c.chunk, NST = c.stages, NW = c.NW;
-    const int nchunks = (Tb + C - 1) / C;
-    if (tid == 0) {
-        for (int n = 0; n < NST && n < nchunks; ++n)
-            ring_issue(ring, n, em_b, p.st, n * C, 1, min(C, Tb - n * C));
-    }
+    RingProducer prod;
+    prod.src = em_b;
+    prod.step_elems = p.st;
+    prod.stage = 0;
+    prod.remaining = Tb;
+    if (warp == prod_warp && lane == 0)
+        for (int n = 0; n < NST; ++n) ring_issue_next(ring, prod);
+    int free_at = C;  // iteration at which the oldest in-flight stage has no reader left
+    RingPos pos;
+    pos.init(em_b, p.st);
     double acc = 0.0;  // :39 cumulative blank column, fp64 running sum (thread 0)
-    uint32_t *bp_b = p.bp + (int64_t)b * p.Tmax * 2 * NW;
+    uint32_t *bp_row = p.bp + (int64_t)b * p.Tmax * 2 * NW;
     const float *col0_b = p.garbage && p.col0 ? p.col0 + (int64_t)b * p.Tmax : nullptr;
+    float *dump_row = p.dump ? p.dump + ((int64_t)b * (p.Tmax + 1) + 1) * (p.Lmax + 1) : nullptr;
 
     for (int t = 0; t < Tb; ++t) {
         const int par = t & 1;
-        if (tid == 0 && t >= 1 && ((t - 1) % C) == C - 1) {
-            const int nxt = (t - 1) / C + NST;
-            if (nxt < nchunks)
-                ring_issue(ring, nxt % NST, em_b, p.st, nxt * C, 1, min(C, Tb - nxt * C));
+        if (warp == prod_warp && t == free_at) {
+            if (lane == 0) ring_issue_next(ring, prod);
+            free_at += C;
         }
-        const int n = t / C, f = t - n * C, stage = n % NST;
-        if (f == 0) mbar_wait(&full[stage], (n / NST) & 1);
-        const float *row = ring_row(ring, stage, f, em_b, p.st, t);
-        const float eb = row[p.blank];
-        float e[K];
+        if (compute) {
+            const float *row = pos.row(ring);
+            const float eb = row[p.blank];
+            float e[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) e[k] = row[tok[k]];
-        float r[K];
+            for (int k = 0; k < K; ++k) e[k] = row[tok[k]];
+            pos.advance(ring);
+            float r[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, v[k], (lane + 31) & 31);
-        const float xin = warp > 0 ? xchg[par * 32 + warp - 1] : 0.f;
-        unsigned myword = 0;
+            for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, v[k], (lane + 31) & 31);
+            const float xin = warp > 0 ? xchg[par * 32 + warp - 1] : 0.f;
+            unsigned myword = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float prev = lane == 0 ? (k == 0 ? xin : r[k > 0 ? k - 1 : 0]) : r[k];
-            const float stayb = v[k] + eb;           // :48
-            const float stayt = v[k] + e[k];         // :49
-            const float chg = prev + e[k];           // :51
-            const float stayed = fmaxf(stayb, stayt);  // what backtrack recomputes (:96-99)
-            float nv = fmaxf(stayed, chg);
-            bool gt = chg > stayed, lt = chg < stayed;
-            if (k == 0 && tid == 0) {  // column 0 (:37 / :39) with the +inf sentinel (:42)
-                if (col0_b) {
-                    nv = col0_b[t];
-                } else {
-                    acc += (double)eb;
-                    nv = (float)acc;
+            for (int k = 0; k < K; ++k) {
+                const float prev = lane == 0 ? (k == 0 ? xin : r[k > 0 ? k - 1 : 0]) : r[k];
+                const float stayb = v[k] + eb;             // :48
+                const float stayt = v[k] + e[k];           // :49
+                const float chg = prev + e[k];             // :51
+                const float stayed = fmaxf(stayb, stayt);  // what backtrack recomputes (:96-99)
+                float nv = fmaxf(stayed, chg);
+                bool gt = chg > stayed, lt = chg < stayed;
+                if (k == 0 && tid == 0) {  // column 0 (:37 / :39) with the +inf sentinel (:42)
+                    if (col0_b) {
+                        nv = col0_b[t];
+                    } else {
+                        acc += (double)eb;
+                        nv = (float)acc;
+                    }
+                    if (t + 1 >= Tb + 1 - L) nv = INF;
+                    gt = lt = false;
                 }
-                if (t + 1 >= Tb + 1 - L) nv = INF;
-                gt = lt = false;
+                v[k] = nv;
+                const unsigned bg = __ballot_sync(FULL, gt), bl = __ballot_sync(FULL, lt);
+                if (lane == k) myword = bg;
+                if (lane == K + k) myword = bl;
             }
-            v[k] = nv;
-            const unsigned bg = __ballot_sync(FULL, gt), bl = __ballot_sync(FULL, lt);
-            if (lane == k) myword = bg;
-            if (lane == K + k) myword = bl;
-        }
-        if (lane < 2 * K) {
-            uint32_t *rowp = bp_b + (int64_t)t * 2 * NW;
-            rowp[lane < K ? warp * K + lane : NW + warp * K + (lane - K)] = myword;
-        }
-        if (ownsL) {
-            float vl = v[0];
+            if (lane < 2 * K) bp_row[lane < K ? warp * K + lane : NW + warp * K + (lane - K)] = myword;
+            bp_row += 2 * NW;
+            if (ownsL) {
+                float vl = v[0];
 #pragma unroll
-            for (int k = 1; k < K; ++k)
-                if (k == kL) vl = v[k];
-            if (vl > best) {  // first maximum (:88)
-                best = vl;
-                best_t = t + 1;
+                for (int k = 1; k < K; ++k)
+                    if (k == kL) vl = v[k];
+                if (vl > best) {  // first maximum (:88)
+                    best = vl;
+                    best_t = t + 1;
+                }
             }
-        }
-        if (p.dump) {
-            float *d = p.dump + ((int64_t)b * (p.Tmax + 1) + t + 1) * (p.Lmax + 1);
+            if (dump_row) {
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (jbase + k * 32 <= L) d[jbase + k * 32] = v[k];
+                for (int k = 0; k < K; ++k)
+                    if (jbase + k * 32 <= L) dump_row[jbase + k * 32] = v[k];
+                dump_row += p.Lmax + 1;
+            }
+            if (lane == 31) xchg[(par ^ 1) * 32 + warp] = v[K - 1];
         }
-        if (lane == 31) xchg[(par ^ 1) * 32 + warp] = v[K - 1];
         __syncthreads();
     }
     if (ownsL) p.t_start[b] = best_t;
@@ -367,7 +380,7 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     p.starts = starts; p.ends = ends; p.scores = scores; p.t_start = t_start; p.status = status;
     p.dump = trellis_dump; p.path_token = path_token; p.path_prob = path_prob;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)B), block(p.cfg.W * 32);
+    dim3 grid((unsigned)B), block((p.cfg.W + (p.cfg.W < 32 ? 1 : 0)) * 32);
 #define SSAK_LAUNCH(KK)                                                                        \
     case KK: {                                                                                 \
         auto kern = align_forward_kernel<KK>;                                                  \

@@ -24,7 +24,12 @@
 //     access is a coalesced 128-byte line, and only one value per warp crosses warps per
 //     frame (shared memory, double buffered, one CTA barrier per frame).
 //   * Emission rows of the next frames are prefetched into a shared-memory ring with
-//     cp.async.bulk (1-D TMA, completion on an mbarrier) and gathered at the label columns.
+//     cp.async.bulk (1-D TMA, completion on an mbarrier) by a dedicated producer warp and
+//     gathered at the label columns.
+//   * Numerics: every 8 frames the row is re-centred on its maximum (one integer REDUX per
+//     warp) and the subtracted amount is accumulated in fp64, so the fp32 state values stay
+//     O(10..100) instead of O(T): the rounding noise of the recursion drops by ~100x
+//     compared with a plain fp32 log-domain recursion (what ATen does).
 //   * Backward: dedicated gradient warps run one frame behind the recursion warps.  The
 //     recursion warps publish per-state posteriors (shared memory), blank posteriors are
 //     summed with an integer warp reduction in 2^-30 fixed point (deterministic), label
@@ -33,6 +38,8 @@
 #include "common.cuh"
 
 namespace ssak {
+
+constexpr int kRecenter = 8;  // frames between two re-centrings of the lattice row
 
 struct CtcCfg {
     int K;       // pairs per lane
@@ -55,10 +62,13 @@ struct CtcParams {
     const int32_t *tgt_len;
     int Lmax;
     int blank;
-    float *rows;    // [B][T][2*P_pad] half lattices (nullptr: not saved)
-    float *finals;  // [B][2][2*P_pad] frontier rows
-    float *nll2;    // [B] -log2 P kept in the workspace (no ln2 round trip before the backward)
-    float *nll;     // [B]
+    // workspace
+    double *nll2;     // [B]    -log2 P (fp64: sum of the offsets + joined frontier)
+    double *off_fin;  // [B][2] accumulated re-centring offset of each frontier row
+    float *finals;    // [B][2][2*P_pad] frontier rows (natural state order: blanks, then labels)
+    double *off_rows; // [B][T] offset of every stored row            (saved for backward)
+    float *rows;      // [B][T][2*P_pad] half lattices                (saved for backward)
+    float *nll;       // [B] out / in
     const float *grad_out;
     float *grad;
     int64_t gst, gsb;
@@ -75,18 +85,17 @@ static inline int env_int(const char *name, int dflt) {
 static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     const int64_t P = Lmax + 1;
     // Few CTAs (latency regime): more warps, fewer pairs per lane.  Many CTAs (throughput
-    // regime): fat lanes, few warps, so several utterances share an SM without barriers
-    // between many warps.
+    // regime): fat lanes, few warps, so several utterances share an SM.
     int wtarget = (2 * B <= 2 * 148) ? 8 : ((2 * B <= 6 * 148) ? 4 : 2);
     wtarget = env_int("SSAK_CTC_WARPS", wtarget);
     int K = env_int("SSAK_CTC_K", 0);
     if (K == 0) {
         K = 1;
-        while (K < 16 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
+        while (K < 8 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
     }
-    if (K != 1 && K != 2 && K != 4 && K != 8 && K != 16) return false;
+    if (K != 1 && K != 2 && K != 4 && K != 8) return false;
     const int64_t W = (P + 32 * K - 1) / (32 * K);
-    if (W > 16) return false;  // L <= 8191
+    if (W > 16) return false;  // L <= 4095
     c->K = K;
     c->W = (int)W;
     c->P_pad = 32 * K * (int)W;
@@ -99,39 +108,28 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     return true;
 }
 
-struct SmemLayout {
-    size_t full, xchg, blank_acc, ring, wlab, occ_start, cursor, occ_pos, total;
-};
-static SmemLayout smem_layout(const CtcCfg &c, int V, int Lmax, bool grad) {
-    SmemLayout s;
-    size_t o = 0;
-    s.full = o;      o += 8 * 8;                       // up to 8 stages
-    s.xchg = o;      o += 2 * 16 * sizeof(float);
-    s.blank_acc = o; o += 16;
-    o = align_up(o, 16);
-    s.ring = o;      o += (size_t)c.stages * c.chunk * c.slot_bytes;
-    s.wlab = o;
-    if (grad) {
-        o += 2 * (size_t)c.P_pad * sizeof(float);
-        s.occ_start = o; o += ((size_t)V + 1) * sizeof(int);
-        s.cursor = o;    o += (size_t)V * sizeof(int);
-        s.occ_pos = o;   o += (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
-    } else {
-        s.occ_start = s.cursor = s.occ_pos = o;
-    }
-    s.total = align_up(o, 16);
-    return s;
+// shared memory: [mbarriers 64][xchg 2x16 f32][wmax 16 f32][blank_acc 2 u32 (+pad)] ring | wlab ...
+constexpr int kSmemXchg = 64, kSmemWmax = 64 + 128, kSmemBlank = 64 + 128 + 64, kSmemRing = 272;
+static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
+    size_t o = kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
+    if (grad)
+        o += 2 * (size_t)c.P_pad * sizeof(float) + ((size_t)V + 1) * sizeof(int) + (size_t)V * sizeof(int) +
+             (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
+    return align_up(o, 16);
 }
 
 // ------------------------------------------------------------------------------ kernel
+// Warp roles: [0, W) recursion, W producer (bulk copies), (W, W+G] gradient (backward only).
 template <int K, bool GRAD>
-__global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const CtcParams p) {
+__global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const CtcCfg &c = p.cfg;
     const int b = blockIdx.x;
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (backward in time)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool compute = warp < c.W;
+    const int W = c.W;
+    const bool compute = warp < W;
+    const bool producer = warp == W;
     const unsigned FULL = 0xffffffffu;
 
     int Tb = p.in_len[b];
@@ -139,38 +137,39 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
     int L = p.tgt_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int m = Tb >> 1;
-    const int n1 = dir ? Tb - m : m;                 // frames this direction owns in forward()
-    const int tau0 = GRAD ? n1 : 0;                  // first direction-local step of this launch
+    const int n1 = dir ? Tb - m : m;        // frames this direction owns in forward()
+    const int tau0 = GRAD ? n1 : 0;         // first direction-local step of this launch
     const int nsteps = GRAD ? Tb - n1 : n1;
     const int P_pad = c.P_pad;
     const int V = p.V;
     const float *lp_b = p.lp + (int64_t)b * p.sb;
     const int32_t *tg = p.targets + p.tgt_off[b];
+    const int t_first = dir ? Tb - 1 - tau0 : tau0;   // frame of step 0
+    const int dt = dir ? -1 : 1;
 
-    // ---- shared memory carve-up (same layout function as the host) ----
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    float *xchg = reinterpret_cast<float *>(smem + 64);                  // [2][16]
-    unsigned *blank_acc = reinterpret_cast<unsigned *>(smem + 64 + 128); // [2]
-    size_t off = (64 + 128 + 16 + 15) & ~(size_t)15;
+    float *xchg = reinterpret_cast<float *>(smem + kSmemXchg);            // [2][16]
+    float *wmax = reinterpret_cast<float *>(smem + kSmemWmax);            // [16]
+    unsigned *blank_acc = reinterpret_cast<unsigned *>(smem + kSmemBlank);  // [2]
     RowRing ring;
-    ring.slots = smem + off;
+    ring.slots = smem + kSmemRing;
     ring.full = full;
     ring.chunk = c.chunk;
     ring.stages = c.stages;
     ring.slot_bytes = c.slot_bytes;
     ring.row_bytes = 4 * V;
-    off += (size_t)c.stages * c.chunk * c.slot_bytes;
-    float *wlab = reinterpret_cast<float *>(smem + off);                 // [2][P_pad]  (GRAD)
-    int *occ_start = reinterpret_cast<int *>(smem + off + 2 * (size_t)P_pad * sizeof(float));
+    float *wlab = reinterpret_cast<float *>(smem + kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes);
+    int *occ_start = reinterpret_cast<int *>(wlab + 2 * P_pad);
     int *cursor = occ_start + (V + 1);
     int *occ_pos = cursor + V;
 
     // ---- gradient prologue: trivial outcomes ----
-    float nll2 = 0.f, gs = 0.f;
+    double nll2 = 0.0;
+    float gs = 0.f;
     if (GRAD) {
         const float nll = p.nll[b];
         gs = p.grad_out[b];
-        const bool infeasible = !(nll < 3.0e38f);    // +inf (or NaN)
+        const bool infeasible = !(nll < 3.0e38f);  // +inf (or NaN)
         if (infeasible || Tb == 0) {
             // zero_infinity: every row 0.  Otherwise torch yields NaN for t < T_b.
             if (dir == 0) {
@@ -200,14 +199,14 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
     if (compute) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int pp = pbase + k * 32;            // direction-local pair index
-            int l = p.blank, lprev = -1;
+            const int pp = pbase + k * 32;  // direction-local pair index
+            int l = p.blank;
             if (pp < L) {
-                const int li = dir ? L - 1 - pp : pp; // natural label index
+                const int li = dir ? L - 1 - pp : pp;  // natural label index
                 l = tg[li];
                 l = l < 0 ? 0 : (l >= V ? V - 1 : l);
                 if (pp >= 1) {
-                    lprev = tg[dir ? li + 1 : li - 1];
+                    int lprev = tg[dir ? li + 1 : li - 1];
                     lprev = lprev < 0 ? 0 : (lprev >= V ? V - 1 : lprev);
                     if (lprev != l) skipmask |= 1u << k;
                 }
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
         }
     }
 
-    // ---- CSR label -> natural positions (backward only) ----
+    // ---- CSR label -> natural positions (backward only; deterministic order) ----
     if (GRAD) {
         for (int cc = tid; cc < V; cc += blockDim.x) cursor[cc] = 0;
         __syncthreads();
@@ -265,8 +264,10 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
 
     // ---- recursion state: virtual start row (forward) or the stored frontier (backward) ----
     float ab[K], al[K];
+    double off_mine = 0.0;  // accumulated re-centring offset: true value = state + off_mine
     if (compute) {
         const float *fin = p.finals + ((int64_t)b * 2 + dir) * 2 * P_pad;
+        if (GRAD) off_mine = p.off_fin[(int64_t)b * 2 + dir];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
@@ -285,21 +286,28 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
     __syncthreads();  // mbarrier init, CSR, xchg visible
 
     const int C = c.chunk, NST = c.stages;
-    const int nchunks = (nsteps + C - 1) / C;
-    const int dt = dir ? -1 : 1;
-    auto frame_of = [&](int i) { return dir ? Tb - 1 - (tau0 + i) : tau0 + i; };
-    if (tid == 0) {
-        for (int n = 0; n < NST && n < nchunks; ++n) {
-            const int cnt = min(C, nsteps - n * C);
-            ring_issue(ring, n, lp_b, p.st, frame_of(n * C), dt, cnt);
-        }
-    }
+    const int64_t step_elems = (int64_t)dt * p.st;
+    RingProducer prod;
+    prod.src = lp_b + (int64_t)t_first * p.st;
+    prod.step_elems = step_elems;
+    prod.stage = 0;
+    prod.remaining = nsteps;
+    if (producer && lane == 0)
+        for (int n = 0; n < NST; ++n) ring_issue_next(ring, prod);
+    const int lagfree = GRAD ? 2 : 1;  // iterations after which a frame's slot has no reader left
+    int free_at = C - 1 + lagfree;     // iteration at which the oldest in-flight stage is free
+
+    RingPos pos;  // recursion warps: frame of step i; gradient warps: frame of step i-1
+    pos.init(lp_b + (int64_t)t_first * p.st, step_elems);
 
     // other direction's stored rows (backward): register double buffer + L2 prefetch ahead
     float ob[K], ol[K], nb[K], nl_[K];
-    const float *rows_b = GRAD ? p.rows + (int64_t)b * p.T * 2 * P_pad : nullptr;
-    auto load_other = [&](int i, float *vb, float *vl) {
-        const float *row = rows_b + (int64_t)frame_of(i) * 2 * P_pad;
+    double ooff = 0.0, noff = 0.0;
+    const int64_t row_elems = 2 * (int64_t)P_pad;
+    const float *orow = GRAD ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
+    const double *ooffp = GRAD ? p.off_rows + (int64_t)b * p.T + t_first : nullptr;
+    const int64_t orow_step = (int64_t)dt * row_elems;
+    auto load_other = [&](const float *row, float *vb, float *vl) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
@@ -310,102 +318,126 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
         }
     };
     if (GRAD && compute) {
-        if (nsteps > 0) load_other(0, ob, ol);
-        if (nsteps > 1) load_other(1, nb, nl_);
+        if (nsteps > 0) { load_other(orow, ob, ol); ooff = __ldg(ooffp); }
+        if (nsteps > 1) { load_other(orow + orow_step, nb, nl_); noff = __ldg(ooffp + dt); }
     }
+    float *row_out = (!GRAD && p.rows) ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
+    double *off_out = (!GRAD && p.rows) ? p.off_rows + (int64_t)b * p.T + t_first : nullptr;
+    float *grow = GRAD ? p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb : nullptr;
+    const int64_t grow_step = (int64_t)dt * p.gst;
 
-    const int lagfree = GRAD ? 2 : 1;
     const int iters = GRAD ? nsteps + 1 : nsteps;
-    const int gtid = tid - c.W * 32, gthreads = c.G * 32;
+    const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
 
     for (int i = 0; i < iters; ++i) {
         const int par = i & 1;
-        // refill the ring stage whose last reader finished before the previous barrier
-        if (tid == 0) {
-            const int j = i - lagfree;
-            if (j >= 0 && (j % C) == C - 1) {
-                const int nxt = j / C + NST;
-                if (nxt < nchunks) {
-                    const int cnt = min(C, nsteps - nxt * C);
-                    ring_issue(ring, nxt % NST, lp_b, p.st, frame_of(nxt * C), dt, cnt);
-                }
+        if (producer) {
+            if (i == free_at) {
+                if (lane == 0) ring_issue_next(ring, prod);
+                free_at += C;
             }
-        }
-        if (compute && i < nsteps) {
-            const int n = i / C, f = i - n * C, stage = n % NST;
-            if (f == 0) mbar_wait(&full[stage], (n / NST) & 1);
-            const int t = frame_of(i);
-            const float *row = ring_row(ring, stage, f, lp_b, p.st, t);
-            const float eb2 = fmaxf(row[p.blank] * kLog2e, kNeg);
-            float el2[K];
+        } else if (compute) {
+            if (i < nsteps) {
+                const float *row = pos.row(ring);
+                const float eb2 = fmaxf(row[p.blank] * kLog2e, kNeg);
+                float el2[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) el2[k] = fmaxf(row[lab[k]] * kLog2e, kNeg);
+                for (int k = 0; k < K; ++k) el2[k] = fmaxf(row[lab[k]] * kLog2e, kNeg);
+                pos.advance(ring);
 
-            // label state of the previous pair (old values): lane rotation, warp seam via smem
-            float r[K];
+                float xin = warp > 0 ? xchg[par * 16 + warp - 1] : kNeg;
+                if (i > 0 && (i & (kRecenter - 1)) == 0) {
+                    // re-centre on the row maximum published in the previous iteration
+                    float mx = wmax[0];
+                    for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
+                    if (mx > kNegTest) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], (lane + 31) & 31);
-            const float xin = warp > 0 ? xchg[par * 16 + warp - 1] : kNeg;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float carry = lane == 0 ? (k == 0 ? xin : r[k > 0 ? k - 1 : 0]) : r[k];
-                const float A = lse2(ab[k], carry);
-                const float oth = (skipmask >> k) & 1u ? A : ab[k];
-                const float nlab = lse2(al[k], oth) + el2[k];
-                ab[k] = A + eb2;
-                al[k] = nlab;
-            }
-            if (lane == 31) xchg[(par ^ 1) * 16 + warp] = al[K - 1];
-
-            if (!GRAD) {
-                if (p.rows) {
-                    float *row_o = p.rows + ((int64_t)b * p.T + t) * 2 * P_pad;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int pp = pbase + k * 32;
-                        if (pp <= L) row_o[dir ? L - pp : pp] = ab[k];
-                        if (pp < L) row_o[P_pad + (dir ? L - 1 - pp : pp)] = al[k];
+                        for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
+                        xin -= mx;
+                        off_mine += (double)mx;
                     }
                 }
-            } else {
-                // posteriors of my states at frame t: 2^(alpha + beta - lp + nll)
-                float sbl = 0.f;
+                // label state of the previous pair (old values): lane rotation, warp seam via smem
+                float r[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], (lane + 31) & 31);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const int pp = pbase + k * 32;
-                    sbl += ex2_approx(ab[k] + ob[k] - eb2 + nll2);
-                    const float wl = ex2_approx(al[k] + ol[k] - el2[k] + nll2);
-                    if (pp < L) wlab[par * P_pad + (dir ? L - 1 - pp : pp)] = wl;
+                    const float carry = lane == 0 ? (k == 0 ? xin : r[k > 0 ? k - 1 : 0]) : r[k];
+                    const float A = lse2(ab[k], carry);
+                    const float oth = (skipmask >> k) & 1u ? A : ab[k];
+                    const float nlab = lse2(al[k], oth) + el2[k];
+                    ab[k] = A + eb2;
+                    al[k] = nlab;
                 }
-                const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
-                const unsigned tot = __reduce_add_sync(FULL, fx);
-                if (lane == 0) atomicAdd(&blank_acc[par], tot);
-                // rotate the register prefetch and fetch two steps ahead
-#pragma unroll
-                for (int k = 0; k < K; ++k) { ob[k] = nb[k]; ol[k] = nl_[k]; }
-                if (i + 2 < nsteps) load_other(i + 2, nb, nl_);
-                if (i + 10 < nsteps && lane == 0) {
-                    const float *rowp = rows_b + (int64_t)frame_of(i + 10) * 2 * P_pad;
+                if (lane == 31) xchg[(par ^ 1) * 16 + warp] = al[K - 1];
+                if ((i & (kRecenter - 1)) == kRecenter - 1) {
+                    float mx = kNeg;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int pp = pbase + k * 32;
-                        if (pp <= L) {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (dir ? L - pp : pp)));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                                rowp + P_pad + (dir ? max(L - 1 - pp, 0) : pp)));
+                        if (pp <= L) mx = fmaxf(mx, ab[k]);
+                        if (pp < L) mx = fmaxf(mx, al[k]);
+                    }
+                    mx = warp_max(mx);
+                    if (lane == 0) wmax[warp] = mx;
+                }
+
+                if (!GRAD) {
+                    if (row_out) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int pp = pbase + k * 32;
+                            if (pp <= L) row_out[dir ? L - pp : pp] = ab[k];
+                            if (pp < L) row_out[P_pad + (dir ? L - 1 - pp : pp)] = al[k];
+                        }
+                        if (tid == 0) *off_out = off_mine;
+                        row_out += orow_step;
+                        off_out += dt;
+                    }
+                } else {
+                    // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
+                    const float bracket = (float)(off_mine + ooff + nll2);
+                    float sbl = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int pp = pbase + k * 32;
+                        sbl += ex2_approx(ab[k] + ob[k] - eb2 + bracket);
+                        const float wl = ex2_approx(al[k] + ol[k] - el2[k] + bracket);
+                        if (pp < L) wlab[par * P_pad + (dir ? L - 1 - pp : pp)] = wl;
+                    }
+                    const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
+                    const unsigned tot = __reduce_add_sync(FULL, fx);
+                    if (lane == 0) atomicAdd(&blank_acc[par], tot);
+                    // rotate the register prefetch and fetch two steps ahead
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { ob[k] = nb[k]; ol[k] = nl_[k]; }
+                    ooff = noff;
+                    orow += orow_step;
+                    ooffp += dt;
+                    if (i + 2 < nsteps) {
+                        load_other(orow + orow_step, nb, nl_);
+                        noff = __ldg(ooffp + dt);
+                    }
+                    if (i + 12 < nsteps && lane == 0) {
+                        const float *rowp = orow + 11 * orow_step;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int pp = pbase + k * 32;
+                            if (pp <= L) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (dir ? L - pp : pp)));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                                    rowp + P_pad + (dir ? max(L - 1 - pp, 0) : pp)));
+                            }
                         }
                     }
                 }
             }
-        }
-        if (GRAD && !compute && i >= 1) {
+        } else if (GRAD && i >= 1) {
             // gradient row of the frame the recursion warps finished in the previous iteration
-            const int j = i - 1, pj = j & 1;
-            const int n = j / C, f = j - n * C, stage = n % NST;
-            if (f == 0) mbar_wait(&full[stage], (n / NST) & 1);
-            const int t = frame_of(j);
-            const float *row = ring_row(ring, stage, f, lp_b, p.st, t);
-            float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
+            const int pj = (i - 1) & 1;
+            const float *row = pos.row(ring);
+            pos.advance(ring);
             const float *w = wlab + pj * P_pad;
             for (int cc = gtid; cc < V; cc += gthreads) {
                 float rsum = 0.f;
@@ -415,8 +447,9 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
                     rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
                     blank_acc[pj] = 0u;
                 }
-                g[cc] = (ex2_approx(row[cc] * kLog2e) - rsum) * gs;
+                grow[cc] = (ex2_approx(row[cc] * kLog2e) - rsum) * gs;
             }
+            grow += grow_step;
         }
         __syncthreads();
     }
@@ -431,6 +464,7 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
                 if (pp <= L) fin[dir ? L - pp : pp] = ab[k];
                 if (pp < L) fin[P_pad + (dir ? L - 1 - pp : pp)] = al[k];
             }
+            if (tid == 0) p.off_fin[(int64_t)b * 2 + dir] = off_mine;
         }
     } else if (dir == 0) {
         for (int t = Tb; t < (int)p.T; ++t) {  // frames beyond the utterance: exact zeros
@@ -441,7 +475,7 @@ __global__ void __launch_bounds__(GRAD ? 640 : 512, 1) ctc_lattice_kernel(const 
 }
 
 // Join the alpha frontier (row m-1, or the virtual start row) with the beta frontier (row m):
-//   log P = lse_s( lse(alpha[s], alpha[s-1], skip ? alpha[s-2]) + beta_m[s] )
+//   log P = off_a + off_b + lse_s( lse(alpha[s], alpha[s-1], skip ? alpha[s-2]) + beta_m[s] )
 __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     __shared__ float red_m[8], red_s[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -484,8 +518,9 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
             S = S * ex2_approx(M - nm) + red_s[w] * ex2_approx(red_m[w] - nm);
             M = nm;
         }
-        const float logp2 = M + lg2_approx(S);
-        p.nll[b] = (logp2 < kNegTest) ? __int_as_float(0x7f800000) : -logp2 * kLn2;
+        const bool dead = M < kNegTest;
+        const double logp2 = (double)M + (double)log2f(S) + p.off_fin[(int64_t)b * 2] + p.off_fin[(int64_t)b * 2 + 1];
+        p.nll[b] = dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453);
         p.nll2[b] = -logp2;
     }
 }
@@ -494,17 +529,16 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
 template <bool GRAD>
 static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     const CtcCfg &c = p.cfg;
-    const SmemLayout sl = smem_layout(c, p.V, p.Lmax, GRAD);
-    if (sl.total > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)p.B, 2), block((c.W + (GRAD ? c.G : 0)) * 32);
-    if ((int)block.x > (GRAD ? 640 : 512)) return SSAK_ERR_UNSUPPORTED;
+    const size_t smem_bytes = smem_bytes_for(c, p.V, p.Lmax, GRAD);
+    if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)p.B, 2), block((c.W + 1 + (GRAD ? c.G : 0)) * 32);
 #define SSAK_LAUNCH(KK)                                                                        \
     case KK: {                                                                                 \
         auto kern = ctc_lattice_kernel<KK, GRAD>;                                              \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)sl.total);                                   \
+                                             (int)smem_bytes);                                 \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
-        kern<<<grid, block, sl.total, stream>>>(p);                                            \
+        kern<<<grid, block, smem_bytes, stream>>>(p);                                          \
         break;                                                                                 \
     }
     switch (c.K) {
@@ -512,11 +546,23 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
         SSAK_LAUNCH(2)
         SSAK_LAUNCH(4)
         SSAK_LAUNCH(8)
-        SSAK_LAUNCH(16)
         default: return SSAK_ERR_UNSUPPORTED;
     }
 #undef SSAK_LAUNCH
     return check_launch();
+}
+
+struct WsLayout { size_t nll2, off_fin, finals, off_rows, rows, total; };
+static WsLayout ws_layout(int64_t T, int64_t B, int P_pad, bool saved) {
+    WsLayout w;
+    size_t o = 0;
+    w.nll2 = o;     o += align_up((size_t)B * sizeof(double), 256);
+    w.off_fin = o;  o += align_up((size_t)B * 2 * sizeof(double), 256);
+    w.finals = o;   o += align_up((size_t)B * 2 * 2 * P_pad * sizeof(float), 256);
+    w.off_rows = o; if (saved) o += align_up((size_t)B * (size_t)T * sizeof(double), 256);
+    w.rows = o;     if (saved) o += align_up((size_t)B * (size_t)T * 2 * P_pad * sizeof(float), 256);
+    w.total = o + 256;
+    return w;
 }
 
 static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t B, int64_t V,
@@ -526,20 +572,20 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     if (!log_probs || !targets || !tgt_off || !in_len || !tgt_len || !workspace)
         return SSAK_ERR_INVALID_ARGUMENT;
     if (T < 0 || B <= 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V || T > 0x7ffffff0 ||
-        V > (1 << 20))
+        V > (1 << 20) || B > 65535 * 32)
         return SSAK_ERR_INVALID_ARGUMENT;
     if (!choose_cfg(Lmax, B, (int)V, &p->cfg)) return SSAK_ERR_UNSUPPORTED;
-    if (workspace_bytes < ssak_ctc_loss_workspace_bytes(T, B, Lmax, saved ? 1 : 0))
-        return SSAK_ERR_WORKSPACE;
+    const WsLayout w = ws_layout(T, B, p->cfg.P_pad, saved);
+    if (workspace_bytes < w.total) return SSAK_ERR_WORKSPACE;
     p->lp = log_probs; p->T = T; p->B = B; p->V = (int)V; p->st = st; p->sb = sb;
     p->targets = targets; p->tgt_off = tgt_off; p->in_len = in_len; p->tgt_len = tgt_len;
     p->Lmax = (int)Lmax; p->blank = blank;
     char *ws = reinterpret_cast<char *>(workspace);
-    const size_t hdr_bytes = align_up((size_t)B * sizeof(float), 256);
-    const size_t fin_bytes = align_up((size_t)B * 2 * 2 * p->cfg.P_pad * sizeof(float), 256);
-    p->nll2 = reinterpret_cast<float *>(ws);
-    p->finals = reinterpret_cast<float *>(ws + hdr_bytes);
-    p->rows = saved ? reinterpret_cast<float *>(ws + hdr_bytes + fin_bytes) : nullptr;
+    p->nll2 = reinterpret_cast<double *>(ws + w.nll2);
+    p->off_fin = reinterpret_cast<double *>(ws + w.off_fin);
+    p->finals = reinterpret_cast<float *>(ws + w.finals);
+    p->off_rows = saved ? reinterpret_cast<double *>(ws + w.off_rows) : nullptr;
+    p->rows = saved ? reinterpret_cast<float *>(ws + w.rows) : nullptr;
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
     return SSAK_OK;
@@ -553,10 +599,7 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
                                                 int save_for_backward) {
     CtcCfg c;
     if (T < 0 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
-    size_t bytes = align_up((size_t)B * sizeof(float), 256) +
-                   align_up((size_t)B * 2 * 2 * c.P_pad * sizeof(float), 256);
-    if (save_for_backward) bytes += (size_t)B * (size_t)T * 2 * c.P_pad * sizeof(float);
-    return bytes + 256;
+    return ws_layout(T, B, c.P_pad, save_for_backward != 0).total;
 }
 
 extern "C" int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t B, int64_t V,

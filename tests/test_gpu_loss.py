@@ -204,6 +204,8 @@ def test_loss_full_size_c2(planted):
     torch_err = (g32.double() - g64).abs().max().item()
     print(f"C2 planted={planted}: grad err vs fp64 truth: ours {ours_err:.3e}, torch fp32 CPU {torch_err:.3e}")
     assert ours_err <= max(GRAD_ATOL, 1.5 * torch_err + 1e-5)
-    assert grad.sum(-1).abs().max().item() < 5e-3
+    rowsum = grad.sum(-1).abs().max().item()
+    print(f"max |row sum| {rowsum:.3e}")
+    assert rowsum < 2e-3
     for b in (0, 21, 63):
         assert (grad[int(il[b]):, b] == 0).all()

@@ -55,6 +55,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking probe of the phase with the given parity
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -140,10 +161,13 @@ struct RingPos {
         a15_step = (uint32_t)((step_elems * 4) & 15);
     }
     // wait for the chunk when entering it, return the V floats of the current frame
-    __device__ __forceinline__ const float *row(const RowRing &r) const {
-        if (f == 0) mbar_wait(&r.full[stage], (uint32_t)phase);
+    __device__ __forceinline__ const float *row(const RowRing &r) const { return row(r, r.full); }
+    // same, waiting on another per-stage barrier array (e.g. "rows post-processed")
+    __device__ __forceinline__ const float *row(const RowRing &r, uint64_t *bars) const {
+        if (f == 0) mbar_wait(&bars[stage], (uint32_t)phase);
         return reinterpret_cast<const float *>(r.slots + (size_t)slot * r.slot_bytes + a15);
     }
+    __device__ __forceinline__ bool last_of_chunk(const RowRing &r) const { return f == r.chunk - 1; }
     __device__ __forceinline__ void advance(const RowRing &r) {
         a15 = (a15 + a15_step) & 15u;
         ++slot;

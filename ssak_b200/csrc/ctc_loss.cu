@@ -21,11 +21,16 @@
 //     native MUFU ops; emissions are scaled by log2(e) when gathered).
 //   * Pairs are spread cyclically over the lanes of a warp (pair = warp*32K + k*32 + lane), so
 //     the neighbour state comes from one lane rotation (warp shuffle) per k, every global row
-//     access is a coalesced 128-byte line, and only one value per warp crosses warps per
-//     frame (shared memory, double buffered, one CTA barrier per frame).
-//   * Emission rows of the next frames are prefetched into a shared-memory ring with
-//     cp.async.bulk (1-D TMA, completion on an mbarrier) by a dedicated producer warp and
-//     gathered at the label columns.
+//     access is a coalesced 128-byte line at an immediate offset, and only one value per warp
+//     crosses warps per frame (shared memory, double buffered, one named barrier per frame
+//     among the recursion/gradient warps).  Both directions keep states in natural order; the
+//     beta CTA pairs (label p-1, blank p) and rotates lanes the other way.  States beyond the
+//     utterance's 2L+1 are pinned to log(0) by a sentinel emission slot, so the time loop has
+//     no validity predicates.
+//   * A dedicated producer warp, decoupled from the per-frame barrier (mbarriers only),
+//     prefetches the emission rows of the next frames into a shared-memory ring with
+//     cp.async.bulk (1-D TMA) and pre-scales them to the log2 domain; in the backward call it
+//     also streams the other direction's stored lattice rows into a second ring.
 //   * Numerics: every 8 frames the row is re-centred on its maximum (one integer REDUX per
 //     warp) and the subtracted amount is accumulated in fp64, so the fp32 state values stay
 //     O(10..100) instead of O(T): the rounding noise of the recursion drops by ~100x
@@ -42,14 +47,21 @@ namespace ssak {
 constexpr int kRecenter = 8;  // frames between two re-centrings of the lattice row
 
 struct CtcCfg {
-    int K;       // pairs per lane
-    int W;       // recursion warps
-    int G;       // gradient warps (backward kernel only)
-    int P_pad;   // pair capacity = 32*K*W
-    int chunk;   // frames per ring stage
-    int stages;  // ring stages
+    int K;          // pairs per lane
+    int W;          // recursion warps
+    int G;          // gradient warps (backward kernel only)
+    int P_pad;      // pair capacity = 32*K*W
+    int row_elems;  // floats per stored lattice row (see "row layout")
+    int chunk;      // frames per emission ring stage
+    int stages;     // emission ring stages
     int slot_bytes;
+    int or_chunk;   // rows per stage of the "other direction" ring (backward)
+    int or_stages;
 };
+// Row layout (floats): [0,P_pad) blank states | [P_pad] spare | [P_pad+1, 2P_pad+1) label states
+//                      | [2P_pad+2, 2P_pad+4) fp64 re-centring offset | pad to 2P_pad+8.
+// Label p lives at P_pad+1+p.  The beta CTA's thread for pair q owns (label q-1, blank q), i.e.
+// positions (P_pad+q, q): both directions use immediate offsets from one per-thread base.
 
 struct CtcParams {
     const float *lp;
@@ -63,12 +75,10 @@ struct CtcParams {
     int Lmax;
     int blank;
     // workspace
-    double *nll2;     // [B]    -log2 P (fp64: sum of the offsets + joined frontier)
-    double *off_fin;  // [B][2] accumulated re-centring offset of each frontier row
-    float *finals;    // [B][2][2*P_pad] frontier rows (natural state order: blanks, then labels)
-    double *off_rows; // [B][T] offset of every stored row            (saved for backward)
-    float *rows;      // [B][T][2*P_pad] half lattices                (saved for backward)
-    float *nll;       // [B] out / in
+    double *nll2;   // [B]    -log2 P (fp64: sum of the offsets + joined frontier)
+    float *finals;  // [B][2][row_elems] frontier rows
+    float *rows;    // [B][T][row_elems] half lattices (saved for backward)
+    float *nll;     // [B] out / in
     const float *grad_out;
     float *grad;
     int64_t gst, gsb;
@@ -84,9 +94,10 @@ static inline int env_int(const char *name, int dflt) {
 // Launch shape from (Lmax, B) only, so forward and backward agree on the workspace layout.
 static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     const int64_t P = Lmax + 1;
-    // Few CTAs (latency regime): more warps, fewer pairs per lane.  Many CTAs (throughput
-    // regime): fat lanes, few warps, so several utterances share an SM.
-    int wtarget = (2 * B <= 2 * 148) ? 8 : ((2 * B <= 6 * 148) ? 4 : 2);
+    // Few CTAs (latency regime): one recursion warp per SM sub-partition.  Many CTAs
+    // (throughput regime): fat lanes, few warps, so several utterances share an SM.
+    const bool few = 2 * B <= 2 * 148;
+    int wtarget = (2 * B <= 6 * 148) ? 4 : 2;
     wtarget = env_int("SSAK_CTC_WARPS", wtarget);
     int K = env_int("SSAK_CTC_K", 0);
     if (K == 0) {
@@ -99,27 +110,39 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->K = K;
     c->W = (int)W;
     c->P_pad = 32 * K * (int)W;
+    c->row_elems = 2 * c->P_pad + 8;
     c->G = V <= 64 ? 2 : 4;
     c->slot_bytes = ring_slot_bytes(V);
     int chunk = 8;
     while (chunk > 1 && chunk * c->slot_bytes > 16384) chunk >>= 1;
     c->chunk = chunk;
     c->stages = 4;
+    const int row_bytes = c->row_elems * 4;
+    const int budget = few ? 96 * 1024 : 40 * 1024;
+    int oc = 8;
+    while (oc > 1 && oc * 3 * row_bytes > budget) oc >>= 1;
+    c->or_chunk = oc;
+    c->or_stages = 3;
+    if (oc == 1) {
+        int st = budget / row_bytes;
+        c->or_stages = st < 2 ? 2 : (st > 8 ? 8 : st);
+    }
     return true;
 }
 
-// shared memory: [mbarriers 64][xchg 2x16 f32][wmax 16 f32][blank_acc 2 u32 (+pad)] ring | wlab ...
-constexpr int kSmemXchg = 64, kSmemWmax = 64 + 128, kSmemBlank = 64 + 128 + 64, kSmemRing = 272;
+// shared memory map (bytes)
+constexpr int kBarEmFull = 0, kBarEmReady = 64, kBarEmEmpty = 128, kBarOrFull = 192, kBarOrEmpty = 256;
+constexpr int kSmemXchg = 320, kSmemWmax = 448, kSmemBlank = 512, kSmemRing = 528;
 static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
     size_t o = kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
     if (grad)
-        o += 2 * (size_t)c.P_pad * sizeof(float) + ((size_t)V + 1) * sizeof(int) + (size_t)V * sizeof(int) +
-             (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
+        o += (size_t)c.or_stages * c.or_chunk * c.row_elems * 4 + 2 * (size_t)(c.P_pad + 8) * sizeof(float) +
+             ((size_t)V + 1) * sizeof(int) + (size_t)V * sizeof(int) + (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
     return align_up(o, 16);
 }
 
 // ------------------------------------------------------------------------------ kernel
-// Warp roles: [0, W) recursion, W producer (bulk copies), (W, W+G] gradient (backward only).
+// Warp roles: [0, W) recursion, W producer (bulk copies + scaling), (W, W+G] gradient (backward).
 template <int K, bool GRAD>
 __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -142,24 +165,32 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     const int nsteps = GRAD ? Tb - n1 : n1;
     const int P_pad = c.P_pad;
     const int V = p.V;
+    const int row_elems = c.row_elems;
     const float *lp_b = p.lp + (int64_t)b * p.sb;
     const int32_t *tg = p.targets + p.tgt_off[b];
-    const int t_first = dir ? Tb - 1 - tau0 : tau0;   // frame of step 0
+    const int t_first = dir ? Tb - 1 - tau0 : tau0;  // frame of step 0
     const int dt = dir ? -1 : 1;
 
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    float *xchg = reinterpret_cast<float *>(smem + kSmemXchg);            // [2][16]
-    float *wmax = reinterpret_cast<float *>(smem + kSmemWmax);            // [16]
+    uint64_t *em_full = reinterpret_cast<uint64_t *>(smem + kBarEmFull);
+    uint64_t *em_ready = reinterpret_cast<uint64_t *>(smem + kBarEmReady);
+    uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + kBarEmEmpty);
+    uint64_t *or_full = reinterpret_cast<uint64_t *>(smem + kBarOrFull);
+    uint64_t *or_empty = reinterpret_cast<uint64_t *>(smem + kBarOrEmpty);
+    float *xchg = reinterpret_cast<float *>(smem + kSmemXchg);              // [2][16]
+    float *wmax = reinterpret_cast<float *>(smem + kSmemWmax);              // [16]
     unsigned *blank_acc = reinterpret_cast<unsigned *>(smem + kSmemBlank);  // [2]
     RowRing ring;
     ring.slots = smem + kSmemRing;
-    ring.full = full;
+    ring.full = em_full;
     ring.chunk = c.chunk;
     ring.stages = c.stages;
     ring.slot_bytes = c.slot_bytes;
     ring.row_bytes = 4 * V;
-    float *wlab = reinterpret_cast<float *>(smem + kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes);
-    int *occ_start = reinterpret_cast<int *>(wlab + 2 * P_pad);
+    unsigned char *or_slots = smem + kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
+    const int row_bytes = row_elems * 4;
+    const int WL = P_pad + 8;
+    float *wlab = reinterpret_cast<float *>(or_slots + (size_t)c.or_stages * c.or_chunk * row_bytes);  // [2][WL]
+    int *occ_start = reinterpret_cast<int *>(wlab + 2 * WL);
     int *cursor = occ_start + (V + 1);
     int *occ_pos = cursor + V;
 
@@ -185,33 +216,45 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         nll2 = p.nll2[b];
     }
 
+    const int n_consumers = W + (GRAD ? c.G : 0);
     if (tid == 0) {
-        for (int s = 0; s < c.stages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < c.stages; ++s) {
+            mbar_init(&em_full[s], 1);
+            mbar_init(&em_ready[s], 1);
+            mbar_init(&em_empty[s], n_consumers);
+        }
+        for (int s = 0; s < c.or_stages; ++s) {
+            mbar_init(&or_full[s], 1);
+            mbar_init(&or_empty[s], W);
+        }
         mbar_fence_init();
         blank_acc[0] = 0u;
         blank_acc[1] = 0u;
     }
 
-    // ---- per-thread static data: labels of my K pairs (direction-local order) ----
-    int lab[K];
+    // ---- per-thread static data: emission byte offsets of my K labels, skip flags ----
+    // alpha: pair p = (blank p, label p);  beta: pair q = (label q-1, blank q)
+    int lab_off[K];
     unsigned skipmask = 0;
     const int pbase = warp * 32 * K + lane;
     if (compute) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int pp = pbase + k * 32;  // direction-local pair index
-            int l = p.blank;
-            if (pp < L) {
-                const int li = dir ? L - 1 - pp : pp;  // natural label index
-                l = tg[li];
+            const int pp = pbase + k * 32;
+            const int li = dir ? pp - 1 : pp;  // natural index of my label
+            int off = 4 * V;                   // sentinel slot: emission log(0) -> state stays log(0)
+            if (li >= 0 && li < L) {
+                int l = tg[li];
                 l = l < 0 ? 0 : (l >= V ? V - 1 : l);
-                if (pp >= 1) {
-                    int lprev = tg[dir ? li + 1 : li - 1];
-                    lprev = lprev < 0 ? 0 : (lprev >= V ? V - 1 : lprev);
-                    if (lprev != l) skipmask |= 1u << k;
+                off = 4 * l;
+                const int lo = dir ? li + 1 : li - 1;  // the label a skip transition comes from
+                if (lo >= 0 && lo < L) {
+                    int l2 = tg[lo];
+                    l2 = l2 < 0 ? 0 : (l2 >= V ? V - 1 : l2);
+                    if (l2 != l) skipmask |= 1u << k;
                 }
             }
-            lab[k] = l;
+            lab_off[k] = off;
         }
     }
 
@@ -265,87 +308,134 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     // ---- recursion state: virtual start row (forward) or the stored frontier (backward) ----
     float ab[K], al[K];
     double off_mine = 0.0;  // accumulated re-centring offset: true value = state + off_mine
+    const int lab_pos = P_pad + 1 - dir + pbase;  // row position of my k=0 label state
     if (compute) {
-        const float *fin = p.finals + ((int64_t)b * 2 + dir) * 2 * P_pad;
-        if (GRAD) off_mine = p.off_fin[(int64_t)b * 2 + dir];
+        const float *fin = p.finals + ((int64_t)b * 2 + dir) * row_elems;
+        if (GRAD) off_mine = *reinterpret_cast<const double *>(fin + 2 * P_pad + 2);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
             if (GRAD) {
-                const int pb = dir ? L - pp : pp;
-                const int pl = dir ? L - 1 - pp : pp;
-                ab[k] = pp <= L ? fin[pb] : kNeg;
-                al[k] = pp < L ? fin[P_pad + pl] : kNeg;
+                ab[k] = fin[pp];
+                al[k] = fin[lab_pos + k * 32];
             } else {
-                ab[k] = pp == 0 ? 0.f : kNeg;
+                ab[k] = pp == (dir ? L : 0) ? 0.f : kNeg;
                 al[k] = kNeg;
             }
         }
-        if (lane == 31) xchg[warp] = al[K - 1];
+        if (lane == (dir ? 0 : 31)) xchg[warp] = dir ? al[0] : al[K - 1];
     }
-    __syncthreads();  // mbarrier init, CSR, xchg visible
+    __syncthreads();  // mbarrier init, CSR, xchg visible; last CTA-wide barrier
 
     const int C = c.chunk, NST = c.stages;
+    const int nchunks = (nsteps + C - 1) / C;
     const int64_t step_elems = (int64_t)dt * p.st;
-    RingProducer prod;
-    prod.src = lp_b + (int64_t)t_first * p.st;
-    prod.step_elems = step_elems;
-    prod.stage = 0;
-    prod.remaining = nsteps;
-    if (producer && lane == 0)
-        for (int n = 0; n < NST; ++n) ring_issue_next(ring, prod);
-    const int lagfree = GRAD ? 2 : 1;  // iterations after which a frame's slot has no reader left
-    int free_at = C - 1 + lagfree;     // iteration at which the oldest in-flight stage is free
+    const float *first_row = lp_b + (int64_t)t_first * p.st;
 
-    RingPos pos;  // recursion warps: frame of step i; gradient warps: frame of step i-1
-    pos.init(lp_b + (int64_t)t_first * p.st, step_elems);
-
-    // other direction's stored rows (backward): register double buffer + L2 prefetch ahead
-    float ob[K], ol[K], nb[K], nl_[K];
-    double ooff = 0.0, noff = 0.0;
-    const int64_t row_elems = 2 * (int64_t)P_pad;
-    const float *orow = GRAD ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
-    const double *ooffp = GRAD ? p.off_rows + (int64_t)b * p.T + t_first : nullptr;
-    const int64_t orow_step = (int64_t)dt * row_elems;
-    auto load_other = [&](const float *row, float *vb, float *vl) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int pp = pbase + k * 32;
-            const int pb = dir ? L - pp : pp;
-            const int pl = dir ? L - 1 - pp : pp;
-            vb[k] = pp <= L ? __ldg(row + pb) : kNeg;
-            vl[k] = pp < L ? __ldg(row + P_pad + pl) : kNeg;
+    if (producer) {
+        // ================= producer warp: TMA issue + in-place scaling, mbarriers only ============
+        RingProducer prod;
+        prod.src = first_row;
+        prod.step_elems = step_elems;
+        prod.stage = 0;
+        prod.remaining = nsteps;
+        int em_issued = 0, em_round = 0;   // round: how many times the issue stage was used before
+        int em_scaled = 0, scale_left = nsteps;
+        RingPos spos;
+        spos.init(first_row, step_elems);
+        const int Co = c.or_chunk, No = c.or_stages;
+        const int or_nchunks = GRAD ? (nsteps + Co - 1) / Co : 0;
+        int or_issued = 0, or_stage = 0, or_round = 0, or_left = nsteps;
+        const float *or_src = GRAD ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
+        const int64_t or_step = (int64_t)dt * row_elems;
+        while (em_scaled < nchunks || or_issued < or_nchunks) {
+            bool progress = false;
+            if (em_issued < nchunks) {
+                bool free_ = em_round == 0;
+                if (!free_) free_ = __shfl_sync(FULL, (int)mbar_test(&em_empty[prod.stage], (em_round - 1) & 1), 0);
+                if (free_) {
+                    const int stg = prod.stage;
+                    if (lane == 0) ring_issue_next(ring, prod);
+                    prod.stage = __shfl_sync(FULL, prod.stage, 0);
+                    if (prod.stage <= stg) ++em_round;  // wrapped (or single stage)
+                    ++em_issued;
+                    progress = true;
+                }
+            }
+            if (em_scaled < em_issued) {
+                if (__shfl_sync(FULL, (int)mbar_test(&em_full[spos.stage], (uint32_t)spos.phase), 0)) {
+                    const int n = scale_left < C ? scale_left : C;
+                    const int stg = spos.stage;
+                    for (int f = 0; f < n; ++f) {
+                        float *row = reinterpret_cast<float *>(ring.slots + (size_t)spos.slot * ring.slot_bytes + spos.a15);
+                        for (int cc = lane; cc < V; cc += 32) row[cc] = fmaxf(row[cc] * kLog2e, kNeg);
+                        if (lane == 0) row[V] = kNeg;  // sentinel emission for states beyond 2L+1
+                        spos.advance(ring);
+                    }
+                    // a partial last chunk leaves the cursor mid-stage; it is never used again
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&em_ready[stg]);
+                    scale_left -= n;
+                    ++em_scaled;
+                    progress = true;
+                }
+            }
+            if (GRAD && or_issued < or_nchunks) {
+                bool free_ = or_round == 0;
+                if (!free_) free_ = __shfl_sync(FULL, (int)mbar_test(&or_empty[or_stage], (or_round - 1) & 1), 0);
+                if (free_) {
+                    const int n = or_left < Co ? or_left : Co;
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&or_full[or_stage], (uint32_t)(n * row_bytes));
+                        unsigned char *dst = or_slots + (size_t)or_stage * Co * row_bytes;
+                        for (int f = 0; f < n; ++f, dst += row_bytes)
+                            bulk_g2s(dst, or_src + (int64_t)f * or_step, (uint32_t)row_bytes, &or_full[or_stage]);
+                    }
+                    or_src += (int64_t)n * or_step;
+                    or_left -= n;
+                    if (++or_stage == No) { or_stage = 0; ++or_round; }
+                    ++or_issued;
+                    progress = true;
+                }
+            }
+            if (!progress) __nanosleep(20);
         }
-    };
-    if (GRAD && compute) {
-        if (nsteps > 0) { load_other(orow, ob, ol); ooff = __ldg(ooffp); }
-        if (nsteps > 1) { load_other(orow + orow_step, nb, nl_); noff = __ldg(ooffp + dt); }
+        return;
     }
-    float *row_out = (!GRAD && p.rows) ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
-    double *off_out = (!GRAD && p.rows) ? p.off_rows + (int64_t)b * p.T + t_first : nullptr;
+
+    // ================= recursion and gradient warps ==========================================
+    const int nbar = n_consumers * 32;
+    RingPos pos;  // recursion warps: frame of step i; gradient warps: frame of step i-1
+    pos.init(first_row, step_elems);
+    // cursor over the other direction's rows (backward)
+    int of = 0, ostage = 0, ophase = 0, oslot = 0;
+    const int Co = c.or_chunk, No = c.or_stages;
+
+    const int seam_lane = dir ? 31 : 0, out_lane = dir ? 0 : 31;
+    const int nb_lane = dir ? (lane + 1) & 31 : (lane + 31) & 31;
+    const int nb_warp = dir ? warp + 1 : warp - 1;
+    const bool has_nb_warp = dir ? (warp < W - 1) : (warp > 0);
+    float *st_b = (!GRAD && p.rows) ? p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase : nullptr;
+    const int64_t st_step = (int64_t)dt * row_elems;
     float *grow = GRAD ? p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb : nullptr;
     const int64_t grow_step = (int64_t)dt * p.gst;
-
     const int iters = GRAD ? nsteps + 1 : nsteps;
     const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
 
     for (int i = 0; i < iters; ++i) {
         const int par = i & 1;
-        if (producer) {
-            if (i == free_at) {
-                if (lane == 0) ring_issue_next(ring, prod);
-                free_at += C;
-            }
-        } else if (compute) {
+        if (compute) {
             if (i < nsteps) {
-                const float *row = pos.row(ring);
-                const float eb2 = fmaxf(row[p.blank] * kLog2e, kNeg);
+                const unsigned char *row = reinterpret_cast<const unsigned char *>(pos.row(ring, em_ready));
+                const float eb2 = reinterpret_cast<const float *>(row)[p.blank];
                 float el2[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) el2[k] = fmaxf(row[lab[k]] * kLog2e, kNeg);
+                for (int k = 0; k < K; ++k) el2[k] = *reinterpret_cast<const float *>(row + lab_off[k]);
+                const bool em_last = pos.last_of_chunk(ring) || i == nsteps - 1;
+                const int em_stage = pos.stage;
                 pos.advance(ring);
 
-                float xin = warp > 0 ? xchg[par * 16 + warp - 1] : kNeg;
+                float xin = has_nb_warp ? xchg[par * 16 + nb_warp] : kNeg;
                 if (i > 0 && (i & (kRecenter - 1)) == 0) {
                     // re-centre on the row maximum published in the previous iteration
                     float mx = wmax[0];
@@ -357,88 +447,84 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                         off_mine += (double)mx;
                     }
                 }
-                // label state of the previous pair (old values): lane rotation, warp seam via smem
+                // label state of the neighbouring pair (old values): lane rotation, warp seam via smem
                 float r[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], (lane + 31) & 31);
+                for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float carry = lane == 0 ? (k == 0 ? xin : r[k > 0 ? k - 1 : 0]) : r[k];
+                    const float seam_f = k == 0 ? xin : r[k > 0 ? k - 1 : 0];          // alpha: pair k-1
+                    const float seam_b = k == K - 1 ? xin : r[k < K - 1 ? k + 1 : k];  // beta: pair k+1
+                    const float carry = lane == seam_lane ? (dir ? seam_b : seam_f) : r[k];
                     const float A = lse2(ab[k], carry);
                     const float oth = (skipmask >> k) & 1u ? A : ab[k];
                     const float nlab = lse2(al[k], oth) + el2[k];
                     ab[k] = A + eb2;
                     al[k] = nlab;
                 }
-                if (lane == 31) xchg[(par ^ 1) * 16 + warp] = al[K - 1];
+                if (lane == out_lane) xchg[(par ^ 1) * 16 + warp] = dir ? al[0] : al[K - 1];
                 if ((i & (kRecenter - 1)) == kRecenter - 1) {
                     float mx = kNeg;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int pp = pbase + k * 32;
-                        if (pp <= L) mx = fmaxf(mx, ab[k]);
-                        if (pp < L) mx = fmaxf(mx, al[k]);
-                    }
+                    for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
                     mx = warp_max(mx);
                     if (lane == 0) wmax[warp] = mx;
                 }
 
                 if (!GRAD) {
-                    if (row_out) {
+                    if (st_b) {
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            const int pp = pbase + k * 32;
-                            if (pp <= L) row_out[dir ? L - pp : pp] = ab[k];
-                            if (pp < L) row_out[P_pad + (dir ? L - 1 - pp : pp)] = al[k];
+                            st_b[k * 32] = ab[k];
+                            st_b[P_pad + 1 - dir + k * 32] = al[k];
                         }
-                        if (tid == 0) *off_out = off_mine;
-                        row_out += orow_step;
-                        off_out += dt;
+                        if (tid == 0) {
+                            st_b[dir ? 2 * P_pad : P_pad] = kNeg;  // the one label slot this direction skips
+                            *reinterpret_cast<double *>(st_b + 2 * P_pad + 2) = off_mine;
+                        }
+                        st_b += st_step;
                     }
                 } else {
                     // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
+                    if (of == 0) mbar_wait(&or_full[ostage], (uint32_t)ophase);
+                    const float *orow = reinterpret_cast<const float *>(or_slots + (size_t)oslot * row_bytes);
+                    const double ooff = *reinterpret_cast<const double *>(orow + 2 * P_pad + 2);
                     const float bracket = (float)(off_mine + ooff + nll2);
                     float sbl = 0.f;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const int pp = pbase + k * 32;
-                        sbl += ex2_approx(ab[k] + ob[k] - eb2 + bracket);
-                        const float wl = ex2_approx(al[k] + ol[k] - el2[k] + bracket);
-                        if (pp < L) wlab[par * P_pad + (dir ? L - 1 - pp : pp)] = wl;
+                        sbl += ex2_approx(ab[k] + orow[pbase + k * 32] - eb2 + bracket);
+                        wlab[par * WL + 1 - dir + pbase + k * 32] =
+                            ex2_approx(al[k] + orow[lab_pos + k * 32] - el2[k] + bracket);
                     }
                     const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
                     const unsigned tot = __reduce_add_sync(FULL, fx);
                     if (lane == 0) atomicAdd(&blank_acc[par], tot);
-                    // rotate the register prefetch and fetch two steps ahead
-#pragma unroll
-                    for (int k = 0; k < K; ++k) { ob[k] = nb[k]; ol[k] = nl_[k]; }
-                    ooff = noff;
-                    orow += orow_step;
-                    ooffp += dt;
-                    if (i + 2 < nsteps) {
-                        load_other(orow + orow_step, nb, nl_);
-                        noff = __ldg(ooffp + dt);
+                    // advance the other-row cursor; release the stage after its last row
+                    const bool o_last = of == Co - 1 || i == nsteps - 1;
+                    if (o_last) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&or_empty[ostage]);
                     }
-                    if (i + 12 < nsteps && lane == 0) {
-                        const float *rowp = orow + 11 * orow_step;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int pp = pbase + k * 32;
-                            if (pp <= L) {
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (dir ? L - pp : pp)));
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                                    rowp + P_pad + (dir ? max(L - 1 - pp, 0) : pp)));
-                            }
-                        }
+                    ++oslot;
+                    if (++of == Co) {
+                        of = 0;
+                        if (++ostage == No) { ostage = 0; ophase ^= 1; oslot = 0; }
                     }
+                }
+                if (em_last) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&em_empty[em_stage]);
                 }
             }
         } else if (GRAD && i >= 1) {
             // gradient row of the frame the recursion warps finished in the previous iteration
             const int pj = (i - 1) & 1;
-            const float *row = pos.row(ring);
+            const float *row = pos.row(ring, em_ready);
+            const bool em_last = pos.last_of_chunk(ring) || i == nsteps;
+            const int em_stage = pos.stage;
             pos.advance(ring);
-            const float *w = wlab + pj * P_pad;
+            const float *w = wlab + pj * WL + 1;
             for (int cc = gtid; cc < V; cc += gthreads) {
                 float rsum = 0.f;
                 const int q1 = occ_start[cc + 1];
@@ -447,29 +533,36 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                     rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
                     blank_acc[pj] = 0u;
                 }
-                grow[cc] = (ex2_approx(row[cc] * kLog2e) - rsum) * gs;
+                grow[cc] = (ex2_approx(row[cc]) - rsum) * gs;  // row is already in log2 units
             }
             grow += grow_step;
+            if (em_last) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+            }
         }
-        __syncthreads();
+        named_bar_sync(1, nbar);
     }
 
     if (!GRAD) {
-        // frontier row for the join kernel / the backward call (natural positions)
+        // frontier row for the join kernel / the backward call
         if (compute) {
-            float *fin = p.finals + ((int64_t)b * 2 + dir) * 2 * P_pad;
+            float *fin = p.finals + ((int64_t)b * 2 + dir) * row_elems + pbase;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const int pp = pbase + k * 32;
-                if (pp <= L) fin[dir ? L - pp : pp] = ab[k];
-                if (pp < L) fin[P_pad + (dir ? L - 1 - pp : pp)] = al[k];
+                fin[k * 32] = ab[k];
+                fin[P_pad + 1 - dir + k * 32] = al[k];
             }
-            if (tid == 0) p.off_fin[(int64_t)b * 2 + dir] = off_mine;
+            if (tid == 0) {
+                fin[dir ? 2 * P_pad : P_pad] = kNeg;
+                *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = off_mine;
+            }
         }
     } else if (dir == 0) {
+        const int nthr = nbar, me = compute ? tid : tid - 32;  // every warp but the producer
         for (int t = Tb; t < (int)p.T; ++t) {  // frames beyond the utterance: exact zeros
             float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
-            for (int cc = tid; cc < V; cc += blockDim.x) g[cc] = 0.f;
+            for (int cc = me; cc < V; cc += nthr) g[cc] = 0.f;
         }
     }
 }
@@ -481,9 +574,10 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int L = p.tgt_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
-    const int P_pad = p.cfg.P_pad;
-    const float *fa = p.finals + (int64_t)b * 2 * 2 * P_pad;
-    const float *fb = fa + 2 * P_pad;
+    const int P_pad = p.cfg.P_pad, row_elems = p.cfg.row_elems;
+    const float *fa = p.finals + (int64_t)b * 2 * row_elems;
+    const float *fb = fa + row_elems;
+    const float *fal = fa + P_pad + 1, *fbl = fb + P_pad + 1;  // label p at [p]
     const int32_t *tg = p.targets + p.tgt_off[b];
     float mx = kNeg, sm = 0.f;  // running max and sum of 2^(x - mx)
     auto push = [&](float x) {
@@ -493,13 +587,13 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     };
     for (int pp = tid; pp <= L; pp += 256) {
         const float a_b = fa[pp];
-        const float a_lp = pp > 0 ? fa[P_pad + pp - 1] : kNeg;
+        const float a_lp = pp > 0 ? fal[pp - 1] : kNeg;
         const float A = lse2(a_b, a_lp);
         push(A + fb[pp]);
         if (pp < L) {
             bool skip = false;
             if (pp > 0) skip = tg[pp] != tg[pp - 1];
-            push(lse2(fa[P_pad + pp], skip ? A : a_b) + fb[P_pad + pp]);
+            push(lse2(fal[pp], skip ? A : a_b) + fbl[pp]);
         }
     }
 #pragma unroll
@@ -519,7 +613,9 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
             M = nm;
         }
         const bool dead = M < kNegTest;
-        const double logp2 = (double)M + (double)log2f(S) + p.off_fin[(int64_t)b * 2] + p.off_fin[(int64_t)b * 2 + 1];
+        const double off_a = *reinterpret_cast<const double *>(fa + 2 * P_pad + 2);
+        const double off_b = *reinterpret_cast<const double *>(fb + 2 * P_pad + 2);
+        const double logp2 = (double)M + (double)log2f(S) + off_a + off_b;
         p.nll[b] = dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453);
         p.nll2[b] = -logp2;
     }
@@ -552,15 +648,13 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
-struct WsLayout { size_t nll2, off_fin, finals, off_rows, rows, total; };
-static WsLayout ws_layout(int64_t T, int64_t B, int P_pad, bool saved) {
+struct WsLayout { size_t nll2, finals, rows, total; };
+static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
     WsLayout w;
     size_t o = 0;
-    w.nll2 = o;     o += align_up((size_t)B * sizeof(double), 256);
-    w.off_fin = o;  o += align_up((size_t)B * 2 * sizeof(double), 256);
-    w.finals = o;   o += align_up((size_t)B * 2 * 2 * P_pad * sizeof(float), 256);
-    w.off_rows = o; if (saved) o += align_up((size_t)B * (size_t)T * sizeof(double), 256);
-    w.rows = o;     if (saved) o += align_up((size_t)B * (size_t)T * 2 * P_pad * sizeof(float), 256);
+    w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
+    w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
+    w.rows = o;   if (saved) o += align_up((size_t)B * (size_t)T * row_elems * sizeof(float), 256);
     w.total = o + 256;
     return w;
 }
@@ -574,17 +668,16 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     if (T < 0 || B <= 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V || T > 0x7ffffff0 ||
         V > (1 << 20) || B > 65535 * 32)
         return SSAK_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     if (!choose_cfg(Lmax, B, (int)V, &p->cfg)) return SSAK_ERR_UNSUPPORTED;
-    const WsLayout w = ws_layout(T, B, p->cfg.P_pad, saved);
+    const WsLayout w = ws_layout(T, B, p->cfg.row_elems, saved);
     if (workspace_bytes < w.total) return SSAK_ERR_WORKSPACE;
     p->lp = log_probs; p->T = T; p->B = B; p->V = (int)V; p->st = st; p->sb = sb;
     p->targets = targets; p->tgt_off = tgt_off; p->in_len = in_len; p->tgt_len = tgt_len;
     p->Lmax = (int)Lmax; p->blank = blank;
     char *ws = reinterpret_cast<char *>(workspace);
     p->nll2 = reinterpret_cast<double *>(ws + w.nll2);
-    p->off_fin = reinterpret_cast<double *>(ws + w.off_fin);
     p->finals = reinterpret_cast<float *>(ws + w.finals);
-    p->off_rows = saved ? reinterpret_cast<double *>(ws + w.off_rows) : nullptr;
     p->rows = saved ? reinterpret_cast<float *>(ws + w.rows) : nullptr;
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
@@ -599,7 +692,7 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
                                                 int save_for_backward) {
     CtcCfg c;
     if (T < 0 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
-    return ws_layout(T, B, c.P_pad, save_for_backward != 0).total;
+    return ws_layout(T, B, c.row_elems, save_for_backward != 0).total;
 }
 
 extern "C" int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t B, int64_t V,

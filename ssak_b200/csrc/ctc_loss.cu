@@ -40,6 +40,8 @@
 //     summed with an integer warp reduction in 2^-30 fixed point (deterministic), label
 //     posteriors are summed by the gradient warps through a per-utterance CSR
 //     (label -> positions) built once, and full gradient rows are written coalesced.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ssak {
@@ -132,7 +134,7 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
 
 // shared memory map (bytes)
 constexpr int kBarEmFull = 0, kBarEmReady = 64, kBarEmEmpty = 128, kBarOrFull = 192, kBarOrEmpty = 256;
-constexpr int kSmemXchg = 320, kSmemWmax = 448, kSmemBlank = 512, kSmemRing = 528;
+constexpr int kSmemXchg = 320, kSmemWmax = 480, kSmemBlank = 544, kSmemRing = 560;
 static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
     size_t o = kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
     if (grad)
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + kBarEmEmpty);
     uint64_t *or_full = reinterpret_cast<uint64_t *>(smem + kBarOrFull);
     uint64_t *or_empty = reinterpret_cast<uint64_t *>(smem + kBarOrEmpty);
-    float *xchg = reinterpret_cast<float *>(smem + kSmemXchg);              // [2][16]
+    float *xchg = reinterpret_cast<float *>(smem + kSmemXchg);              // [2][18]: guard, W seams, guard
     float *wmax = reinterpret_cast<float *>(smem + kSmemWmax);              // [16]
     unsigned *blank_acc = reinterpret_cast<unsigned *>(smem + kSmemBlank);  // [2]
     RowRing ring;
@@ -231,6 +233,8 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         blank_acc[0] = 0u;
         blank_acc[1] = 0u;
     }
+    if (tid < 36) xchg[tid] = kNeg;  // seam guards (and every seam until its warp writes it)
+    __syncthreads();
 
     // ---- per-thread static data: emission byte offsets of my K labels, skip flags ----
     // alpha: pair p = (blank p, label p);  beta: pair q = (label q-1, blank q)
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                 al[k] = kNeg;
             }
         }
-        if (lane == (dir ? 0 : 31)) xchg[warp] = dir ? al[0] : al[K - 1];
+        if (lane == (dir ? 0 : 31)) xchg[1 + warp] = dir ? al[0] : al[K - 1];
     }
     __syncthreads();  // mbarrier init, CSR, xchg visible; last CTA-wide barrier
 
@@ -367,9 +371,18 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                     const int n = scale_left < C ? scale_left : C;
                     const int stg = spos.stage;
                     for (int f = 0; f < n; ++f) {
-                        float *row = reinterpret_cast<float *>(ring.slots + (size_t)spos.slot * ring.slot_bytes + spos.a15);
-                        for (int cc = lane; cc < V; cc += 32) row[cc] = fmaxf(row[cc] * kLog2e, kNeg);
-                        if (lane == 0) row[V] = kNeg;  // sentinel emission for states beyond 2L+1
+                        // scale to log2 units and move the row to offset 0 of its slot (the bulk copy lands
+                        // it a15 bytes in); ascending order + whole-warp read-then-write makes the
+                        // in-place shift safe
+                        float *dst = reinterpret_cast<float *>(ring.slots + (size_t)spos.slot * ring.slot_bytes);
+                        const float *src = reinterpret_cast<const float *>(reinterpret_cast<unsigned char *>(dst) + spos.a15);
+                        for (int c0 = 0; c0 < V; c0 += 32) {
+                            const int cc = c0 + lane;
+                            const float x = cc < V ? src[cc] : 0.f;
+                            __syncwarp();
+                            if (cc < V) dst[cc] = fmaxf(x * kLog2e, kNeg);
+                        }
+                        if (lane == 0) dst[V] = kNeg;  // sentinel emission for states beyond 2L+1
                         spos.advance(ring);
                     }
                     // a partial last chunk leaves the cursor mid-stage; it is never used again
@@ -405,144 +418,170 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
 
     // ================= recursion and gradient warps ==========================================
     const int nbar = n_consumers * 32;
-    RingPos pos;  // recursion warps: frame of step i; gradient warps: frame of step i-1
-    pos.init(first_row, step_elems);
+    const int nslots = C * NST, slot_bytes = c.slot_bytes;
+    const unsigned char *em_base = ring.slots;
+    // emission cursor: rows sit at offset 0 of their slot (the producer realigns them)
+    const unsigned char *em_row = em_base;
+    int em_slot = 0, em_left = 0, em_stage = 0, em_phase = 0;
     // cursor over the other direction's rows (backward)
-    int of = 0, ostage = 0, ophase = 0, oslot = 0;
-    const int Co = c.or_chunk, No = c.or_stages;
+    const int Co = c.or_chunk, No = c.or_stages, or_nslots = Co * No;
+    const unsigned char *or_row = or_slots;
+    int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
 
-    const int seam_lane = dir ? 31 : 0, out_lane = dir ? 0 : 31;
-    const int nb_lane = dir ? (lane + 1) & 31 : (lane + 31) & 31;
-    const int nb_warp = dir ? warp + 1 : warp - 1;
-    const bool has_nb_warp = dir ? (warp < W - 1) : (warp > 0);
     float *st_b = (!GRAD && p.rows) ? p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase : nullptr;
     const int64_t st_step = (int64_t)dt * row_elems;
     float *grow = GRAD ? p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb : nullptr;
     const int64_t grow_step = (int64_t)dt * p.gst;
     const int iters = GRAD ? nsteps + 1 : nsteps;
     const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
-
-    for (int i = 0; i < iters; ++i) {
-        const int par = i & 1;
-        if (compute) {
-            if (i < nsteps) {
-                const unsigned char *row = reinterpret_cast<const unsigned char *>(pos.row(ring, em_ready));
-                const float eb2 = reinterpret_cast<const float *>(row)[p.blank];
-                float el2[K];
+    const int blank_off = 4 * p.blank;
+    unsigned skip_m[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) el2[k] = *reinterpret_cast<const float *>(row + lab_off[k]);
-                const bool em_last = pos.last_of_chunk(ring) || i == nsteps - 1;
-                const int em_stage = pos.stage;
-                pos.advance(ring);
+    for (int k = 0; k < K; ++k) skip_m[k] = (skipmask >> k) & 1u ? 0xffffffffu : 0u;
+    auto sel = [](unsigned m, float a, float bb) {  // m ? a : bb, one LOP3
+        return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
+    };
 
-                float xin = has_nb_warp ? xchg[par * 16 + nb_warp] : kNeg;
-                if (i > 0 && (i & (kRecenter - 1)) == 0) {
-                    // re-centre on the row maximum published in the previous iteration
-                    float mx = wmax[0];
-                    for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
-                    if (mx > kNegTest) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
-                        xin -= mx;
-                        off_mine += (double)mx;
+    auto run = [&](auto dir_tag) {
+        constexpr int DIR = decltype(dir_tag)::value;
+        const unsigned seam_m = lane == (DIR ? 31 : 0) ? 0xffffffffu : 0u;
+        const int out_lane = DIR ? 0 : 31;
+        const int nb_lane = DIR ? (lane + 1) & 31 : (lane + 31) & 31;
+        const int x_in = 1 + warp + (DIR ? 1 : -1), x_out = 1 + warp;
+        for (int i = 0; i < iters; ++i) {
+            const int par = i & 1;
+            if (compute) {
+                if (i < nsteps) {
+                    if (em_left == 0) {
+                        mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
+                        em_left = C;
                     }
-                }
-                // label state of the neighbouring pair (old values): lane rotation, warp seam via smem
-                float r[K];
+                    const float eb2 = *reinterpret_cast<const float *>(em_row + blank_off);
+                    float el2[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float seam_f = k == 0 ? xin : r[k > 0 ? k - 1 : 0];          // alpha: pair k-1
-                    const float seam_b = k == K - 1 ? xin : r[k < K - 1 ? k + 1 : k];  // beta: pair k+1
-                    const float carry = lane == seam_lane ? (dir ? seam_b : seam_f) : r[k];
-                    const float A = lse2(ab[k], carry);
-                    const float oth = (skipmask >> k) & 1u ? A : ab[k];
-                    const float nlab = lse2(al[k], oth) + el2[k];
-                    ab[k] = A + eb2;
-                    al[k] = nlab;
-                }
-                if (lane == out_lane) xchg[(par ^ 1) * 16 + warp] = dir ? al[0] : al[K - 1];
-                if ((i & (kRecenter - 1)) == kRecenter - 1) {
-                    float mx = kNeg;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
-                    mx = warp_max(mx);
-                    if (lane == 0) wmax[warp] = mx;
-                }
+                    for (int k = 0; k < K; ++k) el2[k] = *reinterpret_cast<const float *>(em_row + lab_off[k]);
+                    em_row += slot_bytes;
+                    if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
 
-                if (!GRAD) {
-                    if (st_b) {
+                    float xin = xchg[par * 18 + x_in];
+                    if (i > 0 && (i & (kRecenter - 1)) == 0) {
+                        // re-centre on the row maximum published in the previous iteration
+                        float mx = wmax[0];
+                        for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
+                        if (mx > kNegTest) {
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            st_b[k * 32] = ab[k];
-                            st_b[P_pad + 1 - dir + k * 32] = al[k];
+                            for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
+                            xin -= mx;
+                            off_mine += (double)mx;
                         }
-                        if (tid == 0) {
-                            st_b[dir ? 2 * P_pad : P_pad] = kNeg;  // the one label slot this direction skips
-                            *reinterpret_cast<double *>(st_b + 2 * P_pad + 2) = off_mine;
-                        }
-                        st_b += st_step;
                     }
-                } else {
-                    // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
-                    if (of == 0) mbar_wait(&or_full[ostage], (uint32_t)ophase);
-                    const float *orow = reinterpret_cast<const float *>(or_slots + (size_t)oslot * row_bytes);
-                    const double ooff = *reinterpret_cast<const double *>(orow + 2 * P_pad + 2);
-                    const float bracket = (float)(off_mine + ooff + nll2);
-                    float sbl = 0.f;
+                    // label state of the neighbouring pair (old values): lane rotation, warp seam via smem
+                    float r[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        sbl += ex2_approx(ab[k] + orow[pbase + k * 32] - eb2 + bracket);
-                        wlab[par * WL + 1 - dir + pbase + k * 32] =
-                            ex2_approx(al[k] + orow[lab_pos + k * 32] - el2[k] + bracket);
+                        const float seamv = DIR ? (k == K - 1 ? xin : r[k < K - 1 ? k + 1 : k])
+                                                : (k == 0 ? xin : r[k > 0 ? k - 1 : 0]);
+                        const float carry = sel(seam_m, seamv, r[k]);
+                        const float A = lse2(ab[k], carry);
+                        const float oth = sel(skip_m[k], A, ab[k]);
+                        const float nlab = lse2(al[k], oth) + el2[k];
+                        ab[k] = A + eb2;
+                        al[k] = nlab;
                     }
-                    const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
-                    const unsigned tot = __reduce_add_sync(FULL, fx);
-                    if (lane == 0) atomicAdd(&blank_acc[par], tot);
-                    // advance the other-row cursor; release the stage after its last row
-                    const bool o_last = of == Co - 1 || i == nsteps - 1;
-                    if (o_last) {
+                    if (lane == out_lane) xchg[(par ^ 1) * 18 + x_out] = DIR ? al[0] : al[K - 1];
+                    if ((i & (kRecenter - 1)) == kRecenter - 1) {
+                        float mx = kNeg;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
+                        mx = warp_max(mx);
+                        if (lane == 0) wmax[warp] = mx;
+                    }
+
+                    if (!GRAD) {
+                        if (st_b) {
+                            float *st_l = st_b + (P_pad + 1 - DIR);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                st_b[k * 32] = ab[k];
+                                st_l[k * 32] = al[k];
+                            }
+                            if (tid == 0) {
+                                st_b[DIR ? 2 * P_pad : P_pad] = kNeg;  // the one label slot this direction skips
+                                *reinterpret_cast<double *>(st_b + 2 * P_pad + 2) = off_mine;
+                            }
+                            st_b += st_step;
+                        }
+                    } else {
+                        // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
+                        if (or_left == 0) {
+                            mbar_wait(&or_full[ostage], (uint32_t)ophase);
+                            or_left = Co;
+                        }
+                        const float *orow = reinterpret_cast<const float *>(or_row) + pbase;
+                        const float *orow_l = orow + (P_pad + 1 - DIR);
+                        const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
+                        const float bracket = (float)(off_mine + ooff + nll2);
+                        float *wl = wlab + par * WL + 1 - DIR + pbase;
+                        float sbl = 0.f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            sbl += ex2_approx(ab[k] + orow[k * 32] - eb2 + bracket);
+                            wl[k * 32] = ex2_approx(al[k] + orow_l[k * 32] - el2[k] + bracket);
+                        }
+                        const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
+                        const unsigned tot = __reduce_add_sync(FULL, fx);
+                        if (lane == 0) atomicAdd(&blank_acc[par], tot);
+                        or_row += row_bytes;
+                        if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
+                        if (--or_left == 0 || i == nsteps - 1) {  // release the stage after its last row
+                            or_left = 0;
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&or_empty[ostage]);
+                            if (++ostage == No) { ostage = 0; ophase ^= 1; }
+                        }
+                    }
+                    if (--em_left == 0 || i == nsteps - 1) {
+                        em_left = 0;
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&or_empty[ostage]);
-                    }
-                    ++oslot;
-                    if (++of == Co) {
-                        of = 0;
-                        if (++ostage == No) { ostage = 0; ophase ^= 1; oslot = 0; }
+                        if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+                        if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
                     }
                 }
-                if (em_last) {
+            } else if (GRAD && i >= 1) {
+                // gradient row of the frame the recursion warps finished in the previous iteration
+                const int pj = (i - 1) & 1;
+                if (em_left == 0) {
+                    mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
+                    em_left = C;
+                }
+                const float *row = reinterpret_cast<const float *>(em_row);
+                em_row += slot_bytes;
+                if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
+                const float *w = wlab + pj * WL + 1;
+                for (int cc = gtid; cc < V; cc += gthreads) {
+                    float rsum = 0.f;
+                    const int q1 = occ_start[cc + 1];
+                    for (int q = occ_start[cc]; q < q1; ++q) rsum += w[occ_pos[q]];
+                    if (cc == p.blank) {
+                        rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
+                        blank_acc[pj] = 0u;
+                    }
+                    grow[cc] = (ex2_approx(row[cc]) - rsum) * gs;  // row is already in log2 units
+                }
+                grow += grow_step;
+                if (--em_left == 0 || i == nsteps) {
+                    em_left = 0;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+                    if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
                 }
             }
-        } else if (GRAD && i >= 1) {
-            // gradient row of the frame the recursion warps finished in the previous iteration
-            const int pj = (i - 1) & 1;
-            const float *row = pos.row(ring, em_ready);
-            const bool em_last = pos.last_of_chunk(ring) || i == nsteps;
-            const int em_stage = pos.stage;
-            pos.advance(ring);
-            const float *w = wlab + pj * WL + 1;
-            for (int cc = gtid; cc < V; cc += gthreads) {
-                float rsum = 0.f;
-                const int q1 = occ_start[cc + 1];
-                for (int q = occ_start[cc]; q < q1; ++q) rsum += w[occ_pos[q]];
-                if (cc == p.blank) {
-                    rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
-                    blank_acc[pj] = 0u;
-                }
-                grow[cc] = (ex2_approx(row[cc]) - rsum) * gs;  // row is already in log2 units
-            }
-            grow += grow_step;
-            if (em_last) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&em_empty[em_stage]);
-            }
+            named_bar_sync(1, nbar);
         }
-        named_bar_sync(1, nbar);
-    }
+    };
+    if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
 
     if (!GRAD) {
         // frontier row for the join kernel / the backward call

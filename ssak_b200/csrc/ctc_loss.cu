@@ -115,10 +115,10 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->row_elems = 2 * c->P_pad + 8;
     c->G = V <= 64 ? 2 : 4;
     c->slot_bytes = ring_slot_bytes(V);
-    int chunk = 8;
-    while (chunk > 1 && chunk * c->slot_bytes > 16384) chunk >>= 1;
-    c->chunk = chunk;
-    c->stages = 4;
+    c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
+    int stages = (64 * 1024) / (c->chunk * c->slot_bytes);
+    c->stages = stages > 4 ? 4 : stages;
+    if (c->stages < 2) return false;                 // V too large for the emission ring
     const int row_bytes = c->row_elems * 4;
     const int budget = few ? 96 * 1024 : 40 * 1024;
     int oc = 8;
@@ -145,7 +145,7 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
 
 // ------------------------------------------------------------------------------ kernel
 // Warp roles: [0, W) recursion, W producer (bulk copies + scaling), (W, W+G] gradient (backward).
-template <int K, bool GRAD>
+template <int K, bool GRAD, int CH>
 __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const CtcCfg &c = p.cfg;
@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     }
     __syncthreads();  // mbarrier init, CSR, xchg visible; last CTA-wide barrier
 
-    const int C = c.chunk, NST = c.stages;
+    constexpr int C = CH;
+    const int NST = c.stages;
     const int nchunks = (nsteps + C - 1) / C;
     const int64_t step_elems = (int64_t)dt * p.st;
     const float *first_row = lp_b + (int64_t)t_first * p.st;
@@ -418,22 +419,11 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
 
     // ================= recursion and gradient warps ==========================================
     const int nbar = n_consumers * 32;
-    const int nslots = C * NST, slot_bytes = c.slot_bytes;
+    const int slot_bytes = c.slot_bytes;
     const unsigned char *em_base = ring.slots;
-    // emission cursor: rows sit at offset 0 of their slot (the producer realigns them)
-    const unsigned char *em_row = em_base;
-    int em_slot = 0, em_left = 0, em_stage = 0, em_phase = 0;
-    // cursor over the other direction's rows (backward)
     const int Co = c.or_chunk, No = c.or_stages, or_nslots = Co * No;
-    const unsigned char *or_row = or_slots;
-    int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
-
-    float *st_b = (!GRAD && p.rows) ? p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase : nullptr;
     const int64_t st_step = (int64_t)dt * row_elems;
-    float *grow = GRAD ? p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb : nullptr;
     const int64_t grow_step = (int64_t)dt * p.gst;
-    const int iters = GRAD ? nsteps + 1 : nsteps;
-    const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
     const int blank_off = 4 * p.blank;
     unsigned skip_m[K];
 #pragma unroll
@@ -442,40 +432,56 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
     };
 
-    auto run = [&](auto dir_tag) {
-        constexpr int DIR = decltype(dir_tag)::value;
-        const unsigned seam_m = lane == (DIR ? 31 : 0) ? 0xffffffffu : 0u;
-        const int out_lane = DIR ? 0 : 31;
-        const int nb_lane = DIR ? (lane + 1) & 31 : (lane + 31) & 31;
-        const int x_in = 1 + warp + (DIR ? 1 : -1), x_out = 1 + warp;
-        for (int i = 0; i < iters; ++i) {
-            const int par = i & 1;
-            if (compute) {
-                if (i < nsteps) {
-                    if (em_left == 0) {
-                        mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
-                        em_left = C;
+    if (compute) {
+        // ---------------- recursion warps: chunk-unrolled time loop ----------------
+        auto run = [&](auto dir_tag) {
+            constexpr int DIR = decltype(dir_tag)::value;
+            const unsigned seam_m = lane == (DIR ? 31 : 0) ? 0xffffffffu : 0u;
+            const bool is_out = lane == (DIR ? 0 : 31);
+            const int nb_lane = DIR ? (lane + 1) & 31 : (lane + 31) & 31;
+            const float *x_in = xchg + 1 + warp + (DIR ? 1 : -1);
+            float *x_out = xchg + 1 + warp;
+            // row pointers: pair (pbase + 32k) -> blank at [pbase+32k], label at [P_pad+1-DIR+pbase+32k]
+            const bool save = !GRAD && p.rows != nullptr;
+            unsigned char *st_ptr =
+                save ? reinterpret_cast<unsigned char *>(p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase) : nullptr;
+            const int64_t st_step_b = st_step * 4;
+            const int lab_delta = P_pad + 1 - DIR;
+            const int lab_delta_b = lab_delta * 4, spare_b = (DIR ? 2 * P_pad : P_pad) * 4, off_b = (2 * P_pad + 2) * 4;
+            const unsigned char *or_row = or_slots;
+            int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
+            float *wl_base = GRAD ? wlab + 1 - DIR + pbase : nullptr;
+            int em_stage = 0, em_phase = 0;
+            const unsigned char *em_chunk = em_base;
+            int remaining = nsteps;
+            bool first_chunk = true;
+            while (remaining > 0) {
+                const int n = remaining < CH ? remaining : CH;
+                mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
+                float xfix = 0.f;  // correction for the seam value written before the re-centring
+                if (!first_chunk) {
+                    // re-centre on the row maximum published at the end of the previous chunk
+                    float mx = wmax[0];
+                    for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
+                    if (mx > kNegTest) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
+                        xfix = mx;
+                        off_mine += (double)mx;
                     }
-                    const float eb2 = *reinterpret_cast<const float *>(em_row + blank_off);
+                }
+                first_chunk = false;
+                const double base_d = off_mine + nll2;
+#pragma unroll
+                for (int f = 0; f < CH; ++f) {
+                    if (f >= n) break;
+                    const unsigned char *row = em_chunk + f * slot_bytes;
+                    const float eb2 = *reinterpret_cast<const float *>(row + blank_off);
                     float el2[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) el2[k] = *reinterpret_cast<const float *>(em_row + lab_off[k]);
-                    em_row += slot_bytes;
-                    if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
-
-                    float xin = xchg[par * 18 + x_in];
-                    if (i > 0 && (i & (kRecenter - 1)) == 0) {
-                        // re-centre on the row maximum published in the previous iteration
-                        float mx = wmax[0];
-                        for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
-                        if (mx > kNegTest) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
-                            xin -= mx;
-                            off_mine += (double)mx;
-                        }
-                    }
-                    // label state of the neighbouring pair (old values): lane rotation, warp seam via smem
+                    for (int k = 0; k < K; ++k) el2[k] = *reinterpret_cast<const float *>(row + lab_off[k]);
+                    float xin = x_in[(f & 1) * 18];
+                    if (f == 0) xin -= xfix;
                     float r[K];
 #pragma unroll
                     for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
@@ -490,28 +496,28 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                         ab[k] = A + eb2;
                         al[k] = nlab;
                     }
-                    if (lane == out_lane) xchg[(par ^ 1) * 18 + x_out] = DIR ? al[0] : al[K - 1];
-                    if ((i & (kRecenter - 1)) == kRecenter - 1) {
+                    if (is_out) x_out[((f & 1) ^ 1) * 18] = DIR ? al[0] : al[K - 1];
+                    if (f == CH - 1) {  // publish the row maximum for the next chunk's re-centring
                         float mx = kNeg;
 #pragma unroll
                         for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
                         mx = warp_max(mx);
                         if (lane == 0) wmax[warp] = mx;
                     }
-
                     if (!GRAD) {
-                        if (st_b) {
-                            float *st_l = st_b + (P_pad + 1 - DIR);
+                        if (save) {
+                            float *sb = reinterpret_cast<float *>(st_ptr);
+                            float *sl = reinterpret_cast<float *>(st_ptr + lab_delta_b);
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
-                                st_b[k * 32] = ab[k];
-                                st_l[k * 32] = al[k];
+                                sb[k * 32] = ab[k];
+                                sl[k * 32] = al[k];
                             }
                             if (tid == 0) {
-                                st_b[DIR ? 2 * P_pad : P_pad] = kNeg;  // the one label slot this direction skips
-                                *reinterpret_cast<double *>(st_b + 2 * P_pad + 2) = off_mine;
+                                *reinterpret_cast<float *>(st_ptr + spare_b) = kNeg;  // the label slot this direction skips
+                                *reinterpret_cast<double *>(st_ptr + off_b) = off_mine;
                             }
-                            st_b += st_step;
+                            st_ptr += st_step_b;
                         }
                     } else {
                         // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
@@ -520,68 +526,79 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                             or_left = Co;
                         }
                         const float *orow = reinterpret_cast<const float *>(or_row) + pbase;
-                        const float *orow_l = orow + (P_pad + 1 - DIR);
                         const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
-                        const float bracket = (float)(off_mine + ooff + nll2);
-                        float *wl = wlab + par * WL + 1 - DIR + pbase;
+                        const float bracket = (float)(base_d + ooff);
+                        const float cb = bracket - eb2;
+                        float *wl = wl_base + (f & 1) * WL;
                         float sbl = 0.f;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            sbl += ex2_approx(ab[k] + orow[k * 32] - eb2 + bracket);
-                            wl[k * 32] = ex2_approx(al[k] + orow_l[k * 32] - el2[k] + bracket);
+                            sbl += ex2_approx(ab[k] + orow[k * 32] + cb);
+                            wl[k * 32] = ex2_approx(al[k] + orow[lab_delta + k * 32] + (bracket - el2[k]));
                         }
                         const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
                         const unsigned tot = __reduce_add_sync(FULL, fx);
-                        if (lane == 0) atomicAdd(&blank_acc[par], tot);
+                        if (lane == 0) atomicAdd(&blank_acc[f & 1], tot);
                         or_row += row_bytes;
                         if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
-                        if (--or_left == 0 || i == nsteps - 1) {  // release the stage after its last row
+                        if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
                             or_left = 0;
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&or_empty[ostage]);
                             if (++ostage == No) { ostage = 0; ophase ^= 1; }
                         }
                     }
-                    if (--em_left == 0 || i == nsteps - 1) {
-                        em_left = 0;
+                    if (f == n - 1) {  // release the emission stage before the barrier
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&em_empty[em_stage]);
-                        if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
                     }
+                    named_bar_sync(1, nbar);
                 }
-            } else if (GRAD && i >= 1) {
-                // gradient row of the frame the recursion warps finished in the previous iteration
-                const int pj = (i - 1) & 1;
-                if (em_left == 0) {
-                    mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
-                    em_left = C;
+                remaining -= n;
+                em_chunk += CH * slot_bytes;
+                if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
+            }
+            if (GRAD) named_bar_sync(1, nbar);  // the gradient warps' last frame
+        };
+        if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
+    } else if (GRAD) {
+        // ---------------- gradient warps: one frame behind the recursion warps ----------------
+        const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
+        float *grow = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
+        const unsigned char *em_row = em_base;
+        int em_slot = 0, em_left = 0, em_stage = 0, em_phase = 0;
+        const int nslots = CH * NST;
+        named_bar_sync(1, nbar);  // frame 0 is being computed
+        for (int i = 1; i <= nsteps; ++i) {
+            const int pj = (i - 1) & 1;
+            if (em_left == 0) {
+                mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
+                em_left = CH;
+            }
+            const float *row = reinterpret_cast<const float *>(em_row);
+            em_row += slot_bytes;
+            if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
+            const float *w = wlab + pj * WL + 1;
+            for (int cc = gtid; cc < V; cc += gthreads) {
+                float rsum = 0.f;
+                const int q1 = occ_start[cc + 1];
+                for (int q = occ_start[cc]; q < q1; ++q) rsum += w[occ_pos[q]];
+                if (cc == p.blank) {
+                    rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
+                    blank_acc[pj] = 0u;
                 }
-                const float *row = reinterpret_cast<const float *>(em_row);
-                em_row += slot_bytes;
-                if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
-                const float *w = wlab + pj * WL + 1;
-                for (int cc = gtid; cc < V; cc += gthreads) {
-                    float rsum = 0.f;
-                    const int q1 = occ_start[cc + 1];
-                    for (int q = occ_start[cc]; q < q1; ++q) rsum += w[occ_pos[q]];
-                    if (cc == p.blank) {
-                        rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
-                        blank_acc[pj] = 0u;
-                    }
-                    grow[cc] = (ex2_approx(row[cc]) - rsum) * gs;  // row is already in log2 units
-                }
-                grow += grow_step;
-                if (--em_left == 0 || i == nsteps) {
-                    em_left = 0;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&em_empty[em_stage]);
-                    if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
-                }
+                grow[cc] = (ex2_approx(row[cc]) - rsum) * gs;  // row is already in log2 units
+            }
+            grow += grow_step;
+            if (--em_left == 0 || i == nsteps) {
+                em_left = 0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+                if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
             }
             named_bar_sync(1, nbar);
         }
-    };
-    if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
+    }
 
     if (!GRAD) {
         // frontier row for the join kernel / the backward call
@@ -667,15 +684,18 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     const size_t smem_bytes = smem_bytes_for(c, p.V, p.Lmax, GRAD);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
     dim3 grid((unsigned)p.B, 2), block((c.W + 1 + (GRAD ? c.G : 0)) * 32);
-#define SSAK_LAUNCH(KK)                                                                        \
-    case KK: {                                                                                 \
-        auto kern = ctc_lattice_kernel<KK, GRAD>;                                              \
+#define SSAK_LAUNCH2(KK, CC)                                                                   \
+    {                                                                                          \
+        auto kern = ctc_lattice_kernel<KK, GRAD, CC>;                                          \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem_bytes);                                 \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
         kern<<<grid, block, smem_bytes, stream>>>(p);                                          \
-        break;                                                                                 \
     }
+#define SSAK_LAUNCH(KK)                                                                        \
+    case KK:                                                                                   \
+        if (c.chunk == 8) SSAK_LAUNCH2(KK, 8) else SSAK_LAUNCH2(KK, 4)                         \
+        break;
     switch (c.K) {
         SSAK_LAUNCH(1)
         SSAK_LAUNCH(2)
@@ -683,6 +703,7 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
         SSAK_LAUNCH(8)
         default: return SSAK_ERR_UNSUPPORTED;
     }
+#undef SSAK_LAUNCH2
 #undef SSAK_LAUNCH
     return check_launch();
 }

@@ -29,8 +29,8 @@
 //     no validity predicates.
 //   * A dedicated producer warp, decoupled from the per-frame barrier (mbarriers only),
 //     prefetches the emission rows of the next frames into a shared-memory ring with
-//     cp.async.bulk (1-D TMA) and pre-scales them to the log2 domain; in the backward call it
-//     also streams the other direction's stored lattice rows into a second ring.
+//     cp.async.bulk (1-D TMA); in the backward call it also streams the other direction's
+//     stored lattice rows into a second ring.  Nothing but the copy engine touches the rows.
 //   * Numerics: every 8 frames the row is re-centred on its maximum (one integer REDUX per
 //     warp) and the subtracted amount is accumulated in fp64, so the fp32 state values stay
 //     O(10..100) instead of O(T): the rounding noise of the recursion drops by ~100x
@@ -99,7 +99,7 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     // Few CTAs (latency regime): one recursion warp per SM sub-partition.  Many CTAs
     // (throughput regime): fat lanes, few warps, so several utterances share an SM.
     const bool few = 2 * B <= 2 * 148;
-    int wtarget = (2 * B <= 6 * 148) ? 4 : 2;
+    int wtarget = few ? 8 : ((2 * B <= 6 * 148) ? 4 : 2);
     wtarget = env_int("SSAK_CTC_WARPS", wtarget);
     int K = env_int("SSAK_CTC_K", 0);
     if (K == 0) {
@@ -222,7 +222,6 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     if (tid == 0) {
         for (int s = 0; s < c.stages; ++s) {
             mbar_init(&em_full[s], 1);
-            mbar_init(&em_ready[s], 1);
             mbar_init(&em_empty[s], n_consumers);
         }
         for (int s = 0; s < c.or_stages; ++s) {
@@ -234,6 +233,10 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         blank_acc[1] = 0u;
     }
     if (tid < 36) xchg[tid] = kNeg;  // seam guards (and every seam until its warp writes it)
+    // Sentinel emission log(0) for the states beyond 2L+1: the last 16 bytes of every ring slot are never
+    // written by the bulk copies (a row lands within the first slot_bytes-16 bytes).
+    for (int i = tid; i < c.stages * CH * 4; i += blockDim.x)
+        *reinterpret_cast<float *>(ring.slots + (size_t)(i >> 2) * c.slot_bytes + c.slot_bytes - 16 + (i & 3) * 4) = kNeg;
     __syncthreads();
 
     // ---- per-thread static data: emission byte offsets of my K labels, skip flags ----
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
             const int li = dir ? pp - 1 : pp;  // natural index of my label
-            int off = 4 * V;                   // sentinel slot: emission log(0) -> state stays log(0)
+            int off = c.slot_bytes - 16;       // sentinel words: emission log(0) -> state stays log(0)
             if (li >= 0 && li < L) {
                 int l = tg[li];
                 l = l < 0 ? 0 : (l >= V ? V - 1 : l);
@@ -345,15 +348,12 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         prod.stage = 0;
         prod.remaining = nsteps;
         int em_issued = 0, em_round = 0;   // round: how many times the issue stage was used before
-        int em_scaled = 0, scale_left = nsteps;
-        RingPos spos;
-        spos.init(first_row, step_elems);
         const int Co = c.or_chunk, No = c.or_stages;
         const int or_nchunks = GRAD ? (nsteps + Co - 1) / Co : 0;
         int or_issued = 0, or_stage = 0, or_round = 0, or_left = nsteps;
         const float *or_src = GRAD ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
         const int64_t or_step = (int64_t)dt * row_elems;
-        while (em_scaled < nchunks || or_issued < or_nchunks) {
+        while (em_issued < nchunks || or_issued < or_nchunks) {
             bool progress = false;
             if (em_issued < nchunks) {
                 bool free_ = em_round == 0;
@@ -364,33 +364,6 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                     prod.stage = __shfl_sync(FULL, prod.stage, 0);
                     if (prod.stage <= stg) ++em_round;  // wrapped (or single stage)
                     ++em_issued;
-                    progress = true;
-                }
-            }
-            if (em_scaled < em_issued) {
-                if (__shfl_sync(FULL, (int)mbar_test(&em_full[spos.stage], (uint32_t)spos.phase), 0)) {
-                    const int n = scale_left < C ? scale_left : C;
-                    const int stg = spos.stage;
-                    for (int f = 0; f < n; ++f) {
-                        // scale to log2 units and move the row to offset 0 of its slot (the bulk copy lands
-                        // it a15 bytes in); ascending order + whole-warp read-then-write makes the
-                        // in-place shift safe
-                        float *dst = reinterpret_cast<float *>(ring.slots + (size_t)spos.slot * ring.slot_bytes);
-                        const float *src = reinterpret_cast<const float *>(reinterpret_cast<unsigned char *>(dst) + spos.a15);
-                        for (int c0 = 0; c0 < V; c0 += 32) {
-                            const int cc = c0 + lane;
-                            const float x = cc < V ? src[cc] : 0.f;
-                            __syncwarp();
-                            if (cc < V) dst[cc] = fmaxf(x * kLog2e, kNeg);
-                        }
-                        if (lane == 0) dst[V] = kNeg;  // sentinel emission for states beyond 2L+1
-                        spos.advance(ring);
-                    }
-                    // a partial last chunk leaves the cursor mid-stage; it is never used again
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&em_ready[stg]);
-                    scale_left -= n;
-                    ++em_scaled;
                     progress = true;
                 }
             }
@@ -425,6 +398,8 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     const int64_t st_step = (int64_t)dt * row_elems;
     const int64_t grow_step = (int64_t)dt * p.gst;
     const int blank_off = 4 * p.blank;
+    const unsigned a15_0 = (unsigned)(reinterpret_cast<uintptr_t>(first_row) & 15);
+    const unsigned a15_step = (unsigned)((step_elems * 4) & 15);  // CH * a15_step % 16 == 0
     unsigned skip_m[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) skip_m[k] = (skipmask >> k) & 1u ? 0xffffffffu : 0u;
@@ -457,7 +432,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
             bool first_chunk = true;
             while (remaining > 0) {
                 const int n = remaining < CH ? remaining : CH;
-                mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
+                mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
                 float xfix = 0.f;  // correction for the seam value written before the re-centring
                 if (!first_chunk) {
                     // re-centre on the row maximum published at the end of the previous chunk
@@ -475,11 +450,13 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
 #pragma unroll
                 for (int f = 0; f < CH; ++f) {
                     if (f >= n) break;
-                    const unsigned char *row = em_chunk + f * slot_bytes;
-                    const float eb2 = *reinterpret_cast<const float *>(row + blank_off);
+                    // the bulk copy lands the row (addr & 15) bytes into its slot; raw natural-log values
+                    const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
+                    const float eb2 = fmaxf(*reinterpret_cast<const float *>(row + blank_off) * kLog2e, kNeg);
                     float el2[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) el2[k] = *reinterpret_cast<const float *>(row + lab_off[k]);
+                    for (int k = 0; k < K; ++k)
+                        el2[k] = fmaxf(*reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
                     float xin = x_in[(f & 1) * 18];
                     if (f == 0) xin -= xfix;
                     float r[K];
@@ -567,15 +544,17 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         float *grow = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
         const unsigned char *em_row = em_base;
         int em_slot = 0, em_left = 0, em_stage = 0, em_phase = 0;
+        unsigned a15 = a15_0;
         const int nslots = CH * NST;
         named_bar_sync(1, nbar);  // frame 0 is being computed
         for (int i = 1; i <= nsteps; ++i) {
             const int pj = (i - 1) & 1;
             if (em_left == 0) {
-                mbar_wait(&em_ready[em_stage], (uint32_t)em_phase);
+                mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
                 em_left = CH;
             }
-            const float *row = reinterpret_cast<const float *>(em_row);
+            const float *row = reinterpret_cast<const float *>(em_row + a15);
+            a15 = (a15 + a15_step) & 15u;
             em_row += slot_bytes;
             if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
             const float *w = wlab + pj * WL + 1;
@@ -587,7 +566,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                     rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
                     blank_acc[pj] = 0u;
                 }
-                grow[cc] = (ex2_approx(row[cc]) - rsum) * gs;  // row is already in log2 units
+                grow[cc] = (ex2_approx(row[cc] * kLog2e) - rsum) * gs;
             }
             grow += grow_step;
             if (--em_left == 0 || i == nsteps) {

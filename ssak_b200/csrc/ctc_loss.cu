@@ -104,16 +104,18 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     int K = env_int("SSAK_CTC_K", 0);
     if (K == 0) {
         K = 1;
-        while (K < 8 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
+        while (K < 4 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
     }
     if (K != 1 && K != 2 && K != 4 && K != 8) return false;
+    if (K < 8 && (P + 32 * K - 1) / (32 * K) > 8) K = 8;  // K <= 4 kernels are built for <= 8 recursion warps
     const int64_t W = (P + 32 * K - 1) / (32 * K);
     if (W > 16) return false;  // L <= 4095
     c->K = K;
     c->W = (int)W;
     c->P_pad = 32 * K * (int)W;
     c->row_elems = 2 * c->P_pad + 8;
-    c->G = V <= 64 ? 2 : 4;
+    c->G = V <= 64 ? 2 : (V <= 512 ? 4 : 8);   // gradient warps: <= 32 columns per thread for V <= 8192
+    if (K == 8 && c->W + 1 + c->G > 21) c->G = 21 - 1 - c->W;
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
     int stages = (64 * 1024) / (c->chunk * c->slot_bytes);
@@ -146,7 +148,8 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
 // ------------------------------------------------------------------------------ kernel
 // Warp roles: [0, W) recursion, W producer (bulk copies + scaling), (W, W+G] gradient (backward).
 template <int K, bool GRAD, int CH>
-__global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const CtcParams p) {
+__global__ void __launch_bounds__(K == 8 ? (GRAD ? 672 : 544) : (GRAD ? 544 : 288), 1)
+ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const CtcCfg &c = p.cfg;
     const int b = blockIdx.x;
@@ -265,7 +268,10 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         }
     }
 
-    // ---- CSR label -> natural positions (backward only; deterministic order) ----
+    // ---- label-sorted order of the label states (backward only; deterministic) ----
+    // occ_start[c] .. occ_start[c+1] are the slots of label c; occ_pos[i] is the slot of natural label i.
+    // The recursion warps publish label posteriors directly in this order, so that the gradient
+    // warps sum contiguous runs.
     if (GRAD) {
         for (int cc = tid; cc < V; cc += blockDim.x) cursor[cc] = 0;
         __syncthreads();
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                     const unsigned mm = __match_any_sync(act, l);
                     const int rank = __popc(mm & ((1u << lane) - 1u));
                     const int base = cursor[l];
-                    occ_pos[base + rank] = i;
+                    occ_pos[i] = base + rank;  // natural label index -> slot in label-sorted order
                     __syncwarp(act);
                     if (rank == 0) cursor[l] = base + __popc(mm);
                 }
@@ -401,8 +407,16 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
     const unsigned a15_0 = (unsigned)(reinterpret_cast<uintptr_t>(first_row) & 15);
     const unsigned a15_step = (unsigned)((step_elems * 4) & 15);  // CH * a15_step % 16 == 0
     unsigned skip_m[K];
+    int wl_off[K];  // byte offset of my label posterior in the label-sorted buffer (backward)
 #pragma unroll
-    for (int k = 0; k < K; ++k) skip_m[k] = (skipmask >> k) & 1u ? 0xffffffffu : 0u;
+    for (int k = 0; k < K; ++k) {
+        skip_m[k] = (skipmask >> k) & 1u ? 0xffffffffu : 0u;
+        wl_off[k] = 4 * (WL - 1);  // dump slot for the states beyond 2L+1
+        if (GRAD && compute) {
+            const int li = dir ? pbase + k * 32 - 1 : pbase + k * 32;
+            if (li >= 0 && li < L) wl_off[k] = 4 * occ_pos[li];
+        }
+    }
     auto sel = [](unsigned m, float a, float bb) {  // m ? a : bb, one LOP3
         return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
     };
@@ -425,7 +439,7 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
             const int lab_delta_b = lab_delta * 4, spare_b = (DIR ? 2 * P_pad : P_pad) * 4, off_b = (2 * P_pad + 2) * 4;
             const unsigned char *or_row = or_slots;
             int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
-            float *wl_base = GRAD ? wlab + 1 - DIR + pbase : nullptr;
+            unsigned char *wl_bytes = reinterpret_cast<unsigned char *>(wlab);
             int em_stage = 0, em_phase = 0;
             const unsigned char *em_chunk = em_base;
             int remaining = nsteps;
@@ -506,12 +520,13 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
                         const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
                         const float bracket = (float)(base_d + ooff);
                         const float cb = bracket - eb2;
-                        float *wl = wl_base + (f & 1) * WL;
+                        unsigned char *wl = wl_bytes + (f & 1) * (WL * 4);
                         float sbl = 0.f;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             sbl += ex2_approx(ab[k] + orow[k * 32] + cb);
-                            wl[k * 32] = ex2_approx(al[k] + orow[lab_delta + k * 32] + (bracket - el2[k]));
+                            *reinterpret_cast<float *>(wl + wl_off[k]) =
+                                ex2_approx(al[k] + orow[lab_delta + k * 32] + (bracket - el2[k]));
                         }
                         const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
                         const unsigned tot = __reduce_add_sync(FULL, fx);
@@ -546,6 +561,11 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
         int em_slot = 0, em_left = 0, em_stage = 0, em_phase = 0;
         unsigned a15 = a15_0;
         const int nslots = CH * NST;
+        // my columns: gtid + j*gthreads; bit j of `present`: the column has label states (or is blank)
+        unsigned present = 0;
+        int ncol = 0;
+        for (int cc = gtid; cc < V; cc += gthreads, ++ncol)
+            if (ncol < 32 && (occ_start[cc + 1] > occ_start[cc] || cc == p.blank)) present |= 1u << ncol;
         named_bar_sync(1, nbar);  // frame 0 is being computed
         for (int i = 1; i <= nsteps; ++i) {
             const int pj = (i - 1) & 1;
@@ -557,16 +577,22 @@ __global__ void __launch_bounds__(GRAD ? 672 : 544, 1) ctc_lattice_kernel(const 
             a15 = (a15 + a15_step) & 15u;
             em_row += slot_bytes;
             if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
-            const float *w = wlab + pj * WL + 1;
-            for (int cc = gtid; cc < V; cc += gthreads) {
-                float rsum = 0.f;
-                const int q1 = occ_start[cc + 1];
-                for (int q = occ_start[cc]; q < q1; ++q) rsum += w[occ_pos[q]];
-                if (cc == p.blank) {
-                    rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
-                    blank_acc[pj] = 0u;
+            const float *w = wlab + pj * WL;
+#pragma unroll 4
+            for (int j = 0; j < ncol; ++j) {
+                const int cc = gtid + j * gthreads;
+                float val = ex2_approx(row[cc] * kLog2e);
+                if ((present >> (j & 31)) & 1u || j >= 32) {
+                    float rsum = 0.f;
+                    const int q1 = occ_start[cc + 1];
+                    for (int q = occ_start[cc]; q < q1; ++q) rsum += w[q];  // contiguous run
+                    if (cc == p.blank) {
+                        rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
+                        blank_acc[pj] = 0u;
+                    }
+                    val -= rsum;
                 }
-                grow[cc] = (ex2_approx(row[cc] * kLog2e) - rsum) * gs;
+                grow[cc] = val * gs;
             }
             grow += grow_step;
             if (--em_left == 0 || i == nsteps) {

@@ -46,7 +46,6 @@
 
 namespace ssak {
 
-constexpr int kRecenter = 8;  // frames between two re-centrings of the lattice row
 
 struct CtcCfg {
     int K;          // pairs per lane
@@ -135,13 +134,14 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
 }
 
 // shared memory map (bytes)
-constexpr int kBarEmFull = 0, kBarEmReady = 64, kBarEmEmpty = 128, kBarOrFull = 192, kBarOrEmpty = 256;
-constexpr int kSmemXchg = 320, kSmemWmax = 480, kSmemBlank = 544, kSmemRing = 560;
+constexpr int kBarEmFull = 0, kBarEmEmpty = 64, kBarOrFull = 128, kBarOrEmpty = 192, kBarPostEmpty = 256, kBarPostFull = 272;
+constexpr int kSmemXchg = 400, kSmemWmax = 560, kSmemRing = 640;
 static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
     size_t o = kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
     if (grad)
-        o += (size_t)c.or_stages * c.or_chunk * c.row_elems * 4 + 2 * (size_t)(c.P_pad + 8) * sizeof(float) +
-             ((size_t)V + 1) * sizeof(int) + (size_t)V * sizeof(int) + (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
+        o += (size_t)c.or_stages * c.or_chunk * c.row_elems * 4 + 2 * (size_t)c.chunk * (c.P_pad + 8) * sizeof(float) +
+             2 * (size_t)c.chunk * sizeof(unsigned) + ((size_t)V + 1) * sizeof(int) + (size_t)V * sizeof(int) +
+             (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
     return align_up(o, 16);
 }
 
@@ -177,13 +177,13 @@ ctc_lattice_kernel(const CtcParams p) {
     const int dt = dir ? -1 : 1;
 
     uint64_t *em_full = reinterpret_cast<uint64_t *>(smem + kBarEmFull);
-    uint64_t *em_ready = reinterpret_cast<uint64_t *>(smem + kBarEmReady);
     uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + kBarEmEmpty);
     uint64_t *or_full = reinterpret_cast<uint64_t *>(smem + kBarOrFull);
     uint64_t *or_empty = reinterpret_cast<uint64_t *>(smem + kBarOrEmpty);
+    uint64_t *post_empty = reinterpret_cast<uint64_t *>(smem + kBarPostEmpty);  // [2]  per chunk buffer
+    uint64_t *post_full = reinterpret_cast<uint64_t *>(smem + kBarPostFull);    // [2*CH] per frame slot
     float *xchg = reinterpret_cast<float *>(smem + kSmemXchg);              // [2][18]: guard, W seams, guard
     float *wmax = reinterpret_cast<float *>(smem + kSmemWmax);              // [16]
-    unsigned *blank_acc = reinterpret_cast<unsigned *>(smem + kSmemBlank);  // [2]
     RowRing ring;
     ring.slots = smem + kSmemRing;
     ring.full = em_full;
@@ -194,8 +194,10 @@ ctc_lattice_kernel(const CtcParams p) {
     unsigned char *or_slots = smem + kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
     const int row_bytes = row_elems * 4;
     const int WL = P_pad + 8;
-    float *wlab = reinterpret_cast<float *>(or_slots + (size_t)c.or_stages * c.or_chunk * row_bytes);  // [2][WL]
-    int *occ_start = reinterpret_cast<int *>(wlab + 2 * WL);
+    // posterior ring (backward): 2 chunk buffers x CH frames, label posteriors in label-sorted order
+    float *wlab = reinterpret_cast<float *>(or_slots + (size_t)c.or_stages * c.or_chunk * row_bytes);  // [2*CH][WL]
+    unsigned *blank_acc = reinterpret_cast<unsigned *>(wlab + 2 * CH * WL);                            // [2*CH]
+    int *occ_start = reinterpret_cast<int *>(blank_acc + 2 * CH);
     int *cursor = occ_start + (V + 1);
     int *occ_pos = cursor + V;
 
@@ -231,9 +233,15 @@ ctc_lattice_kernel(const CtcParams p) {
             mbar_init(&or_full[s], 1);
             mbar_init(&or_empty[s], W);
         }
+        if (GRAD) {
+            for (int s = 0; s < 2 * CH; ++s) {
+                mbar_init(&post_full[s], W);
+                blank_acc[s] = 0u;
+            }
+            mbar_init(&post_empty[0], c.G);
+            mbar_init(&post_empty[1], c.G);
+        }
         mbar_fence_init();
-        blank_acc[0] = 0u;
-        blank_acc[1] = 0u;
     }
     if (tid < 36) xchg[tid] = kNeg;  // seam guards (and every seam until its warp writes it)
     // Sentinel emission log(0) for the states beyond 2L+1: the last 16 bytes of every ring slot are never
@@ -397,7 +405,7 @@ ctc_lattice_kernel(const CtcParams p) {
     }
 
     // ================= recursion and gradient warps ==========================================
-    const int nbar = n_consumers * 32;
+    const int nbar = W * 32;  // the per-frame barrier is among the recursion warps only
     const int slot_bytes = c.slot_bytes;
     const unsigned char *em_base = ring.slots;
     const int Co = c.or_chunk, No = c.or_stages, or_nslots = Co * No;
@@ -444,6 +452,7 @@ ctc_lattice_kernel(const CtcParams p) {
             const unsigned char *em_chunk = em_base;
             int remaining = nsteps;
             bool first_chunk = true;
+            int chunk_idx = 0;
             while (remaining > 0) {
                 const int n = remaining < CH ? remaining : CH;
                 mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
@@ -461,6 +470,9 @@ ctc_lattice_kernel(const CtcParams p) {
                 }
                 first_chunk = false;
                 const double base_d = off_mine + nll2;
+                if (GRAD && chunk_idx >= 2)  // the gradient warps must be done with this posterior buffer
+                    mbar_wait(&post_empty[chunk_idx & 1], (uint32_t)(((chunk_idx >> 1) - 1) & 1));
+                const int pbuf = (chunk_idx & 1) * CH;
 #pragma unroll
                 for (int f = 0; f < CH; ++f) {
                     if (f >= n) break;
@@ -520,7 +532,7 @@ ctc_lattice_kernel(const CtcParams p) {
                         const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
                         const float bracket = (float)(base_d + ooff);
                         const float cb = bracket - eb2;
-                        unsigned char *wl = wl_bytes + (f & 1) * (WL * 4);
+                        unsigned char *wl = wl_bytes + (pbuf + f) * (WL * 4);
                         float sbl = 0.f;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
@@ -530,7 +542,11 @@ ctc_lattice_kernel(const CtcParams p) {
                         }
                         const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
                         const unsigned tot = __reduce_add_sync(FULL, fx);
-                        if (lane == 0) atomicAdd(&blank_acc[f & 1], tot);
+                        __syncwarp();
+                        if (lane == 0) {
+                            atomicAdd(&blank_acc[pbuf + f], tot);
+                            mbar_arrive(&post_full[pbuf + f]);  // release: this warp's posteriors of the frame
+                        }
                         or_row += row_bytes;
                         if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
                         if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
@@ -547,61 +563,90 @@ ctc_lattice_kernel(const CtcParams p) {
                     named_bar_sync(1, nbar);
                 }
                 remaining -= n;
+                ++chunk_idx;
                 em_chunk += CH * slot_bytes;
                 if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
             }
-            if (GRAD) named_bar_sync(1, nbar);  // the gradient warps' last frame
         };
         if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
     } else if (GRAD) {
-        // ---------------- gradient warps: one frame behind the recursion warps ----------------
+        // ---------------- gradient warps: consume the posterior ring, mbarriers only ----------------
         const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
         float *grow = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
-        const unsigned char *em_row = em_base;
-        int em_slot = 0, em_left = 0, em_stage = 0, em_phase = 0;
-        unsigned a15 = a15_0;
-        const int nslots = CH * NST;
-        // my columns: gtid + j*gthreads; bit j of `present`: the column has label states (or is blank)
+        const unsigned char *em_chunk = em_base;
+        int em_stage = 0, em_phase = 0;
+        // 128-bit path when every emission row and every gradient row is 16-byte aligned
+        const bool vec = a15_0 == 0 && a15_step == 0 && (V & 3) == 0 && ((p.gst | p.gsb) & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0;
+        const int ncols = vec ? V >> 2 : V;  // work items: groups of 4 columns, or columns
+        // bit j of `present`: my j-th item has label states (or is the blank column)
         unsigned present = 0;
-        int ncol = 0;
-        for (int cc = gtid; cc < V; cc += gthreads, ++ncol)
-            if (ncol < 32 && (occ_start[cc + 1] > occ_start[cc] || cc == p.blank)) present |= 1u << ncol;
-        named_bar_sync(1, nbar);  // frame 0 is being computed
-        for (int i = 1; i <= nsteps; ++i) {
-            const int pj = (i - 1) & 1;
-            if (em_left == 0) {
-                mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
-                em_left = CH;
+        {
+            int j = 0;
+            for (int it = gtid; it < ncols; it += gthreads, ++j) {
+                const int c0 = vec ? 4 * it : it, c1 = vec ? c0 + 4 : c0 + 1;
+                if (j < 32 && (occ_start[c1] > occ_start[c0] || (p.blank >= c0 && p.blank < c1))) present |= 1u << j;
             }
-            const float *row = reinterpret_cast<const float *>(em_row + a15);
-            a15 = (a15 + a15_step) & 15u;
-            em_row += slot_bytes;
-            if (++em_slot == nslots) { em_slot = 0; em_row = em_base; }
-            const float *w = wlab + pj * WL;
-#pragma unroll 4
-            for (int j = 0; j < ncol; ++j) {
-                const int cc = gtid + j * gthreads;
-                float val = ex2_approx(row[cc] * kLog2e);
-                if ((present >> (j & 31)) & 1u || j >= 32) {
-                    float rsum = 0.f;
-                    const int q1 = occ_start[cc + 1];
-                    for (int q = occ_start[cc]; q < q1; ++q) rsum += w[q];  // contiguous run
-                    if (cc == p.blank) {
-                        rsum += (float)blank_acc[pj] * (1.0f / 1073741824.0f);
-                        blank_acc[pj] = 0u;
+        }
+        auto label_mass = [&](int cc, const float *w, int slot) {  // posterior mass of column cc at this frame
+            float rsum = 0.f;
+            const int q1 = occ_start[cc + 1];
+            for (int q = occ_start[cc]; q < q1; ++q) rsum += w[q];  // contiguous run (label-sorted order)
+            if (cc == p.blank) {
+                rsum += (float)blank_acc[slot] * (1.0f / 1073741824.0f);
+                blank_acc[slot] = 0u;
+            }
+            return rsum;
+        };
+        int remaining = nsteps, chunk_idx = 0;
+        unsigned a15 = a15_0;
+        while (remaining > 0) {
+            const int n = remaining < CH ? remaining : CH;
+            mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+            const int pbuf = (chunk_idx & 1) * CH;
+            for (int f = 0; f < n; ++f) {
+                const int slot = pbuf + f;
+                mbar_wait(&post_full[slot], (uint32_t)((chunk_idx >> 1) & 1));
+                const float *w = wlab + slot * WL;
+                const unsigned char *rowb = em_chunk + f * slot_bytes + a15;
+                a15 = (a15 + a15_step) & 15u;
+                if (vec) {
+                    const float4 *row4 = reinterpret_cast<const float4 *>(rowb);
+                    float4 *g4 = reinterpret_cast<float4 *>(grow);
+                    int j = 0;
+                    for (int it = gtid; it < ncols; it += gthreads, ++j) {
+                        const float4 x = row4[it];
+                        float4 v = make_float4(ex2_approx(x.x * kLog2e), ex2_approx(x.y * kLog2e),
+                                               ex2_approx(x.z * kLog2e), ex2_approx(x.w * kLog2e));
+                        if (j >= 32 || ((present >> j) & 1u)) {
+                            v.x -= label_mass(4 * it, w, slot);
+                            v.y -= label_mass(4 * it + 1, w, slot);
+                            v.z -= label_mass(4 * it + 2, w, slot);
+                            v.w -= label_mass(4 * it + 3, w, slot);
+                        }
+                        g4[it] = make_float4(v.x * gs, v.y * gs, v.z * gs, v.w * gs);
                     }
-                    val -= rsum;
+                } else {
+                    const float *row = reinterpret_cast<const float *>(rowb);
+                    int j = 0;
+                    for (int cc = gtid; cc < V; cc += gthreads, ++j) {
+                        float val = ex2_approx(row[cc] * kLog2e);
+                        if (j >= 32 || ((present >> j) & 1u)) val -= label_mass(cc, w, slot);
+                        grow[cc] = val * gs;
+                    }
                 }
-                grow[cc] = val * gs;
+                grow += grow_step;
             }
-            grow += grow_step;
-            if (--em_left == 0 || i == nsteps) {
-                em_left = 0;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&em_empty[em_stage]);
-                if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
+            // release the emission stage and the posterior buffer
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&em_empty[em_stage]);
+                mbar_arrive(&post_empty[chunk_idx & 1]);
             }
-            named_bar_sync(1, nbar);
+            remaining -= n;
+            ++chunk_idx;
+            em_chunk += CH * slot_bytes;
+            if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
         }
     }
 
@@ -620,7 +665,7 @@ ctc_lattice_kernel(const CtcParams p) {
             }
         }
     } else if (dir == 0) {
-        const int nthr = nbar, me = compute ? tid : tid - 32;  // every warp but the producer
+        const int nthr = n_consumers * 32, me = compute ? tid : tid - 32;  // every warp but the producer
         for (int t = Tb; t < (int)p.T; ++t) {  // frames beyond the utterance: exact zeros
             float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
             for (int cc = me; cc < V; cc += nthr) g[cc] = 0.f;

@@ -113,15 +113,16 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->W = (int)W;
     c->P_pad = 32 * K * (int)W;
     c->row_elems = 2 * c->P_pad + 8;
-    c->G = V <= 64 ? 2 : (V <= 512 ? 4 : 8);   // gradient warps: <= 32 columns per thread for V <= 8192
+    // gradient warps: few when many CTAs share an SM (they only cost occupancy), more when one CTA owns it
+    c->G = few ? (V <= 512 ? 4 : 8) : (V <= 64 ? 1 : (V <= 512 ? 2 : 4));
     if (K == 8 && c->W + 1 + c->G > 21) c->G = 21 - 1 - c->W;
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
-    int stages = (64 * 1024) / (c->chunk * c->slot_bytes);
+    int stages = ((few ? 64 : 36) * 1024) / (c->chunk * c->slot_bytes);
     c->stages = stages > 4 ? 4 : stages;
     if (c->stages < 2) return false;                 // V too large for the emission ring
     const int row_bytes = c->row_elems * 4;
-    const int budget = few ? 96 * 1024 : 40 * 1024;
+    const int budget = few ? 96 * 1024 : 24 * 1024;
     int oc = 8;
     while (oc > 1 && oc * 3 * row_bytes > budget) oc >>= 1;
     c->or_chunk = oc;
@@ -571,19 +572,21 @@ ctc_lattice_kernel(const CtcParams p) {
         if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
     } else if (GRAD) {
         // ---------------- gradient warps: consume the posterior ring, mbarriers only ----------------
-        const int gtid = tid - (W + 1) * 32, gthreads = c.G * 32;
-        float *grow = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
+        // Each gradient warp takes whole frames (frame f of a chunk goes to warp f mod G), so the
+        // per-frame latency (barrier probe, run sums, exp, store) overlaps across warps.
+        const int gwarp = warp - (W + 1), G = c.G;
+        float *grow_chunk = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
         const unsigned char *em_chunk = em_base;
         int em_stage = 0, em_phase = 0;
         // 128-bit path when every emission row and every gradient row is 16-byte aligned
         const bool vec = a15_0 == 0 && a15_step == 0 && (V & 3) == 0 && ((p.gst | p.gsb) & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0;
         const int ncols = vec ? V >> 2 : V;  // work items: groups of 4 columns, or columns
-        // bit j of `present`: my j-th item has label states (or is the blank column)
+        // bit j of `present`: my j-th item (lane + 32 j) has label states (or is the blank column)
         unsigned present = 0;
         {
             int j = 0;
-            for (int it = gtid; it < ncols; it += gthreads, ++j) {
+            for (int it = lane; it < ncols; it += 32, ++j) {
                 const int c0 = vec ? 4 * it : it, c1 = vec ? c0 + 4 : c0 + 1;
                 if (j < 32 && (occ_start[c1] > occ_start[c0] || (p.blank >= c0 && p.blank < c1))) present |= 1u << j;
             }
@@ -599,22 +602,21 @@ ctc_lattice_kernel(const CtcParams p) {
             return rsum;
         };
         int remaining = nsteps, chunk_idx = 0;
-        unsigned a15 = a15_0;
         while (remaining > 0) {
             const int n = remaining < CH ? remaining : CH;
             mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
             const int pbuf = (chunk_idx & 1) * CH;
-            for (int f = 0; f < n; ++f) {
+            for (int f = gwarp; f < n; f += G) {
                 const int slot = pbuf + f;
                 mbar_wait(&post_full[slot], (uint32_t)((chunk_idx >> 1) & 1));
                 const float *w = wlab + slot * WL;
-                const unsigned char *rowb = em_chunk + f * slot_bytes + a15;
-                a15 = (a15 + a15_step) & 15u;
+                const unsigned char *rowb = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
+                float *grow = grow_chunk + (int64_t)f * grow_step;
                 if (vec) {
                     const float4 *row4 = reinterpret_cast<const float4 *>(rowb);
                     float4 *g4 = reinterpret_cast<float4 *>(grow);
                     int j = 0;
-                    for (int it = gtid; it < ncols; it += gthreads, ++j) {
+                    for (int it = lane; it < ncols; it += 32, ++j) {
                         const float4 x = row4[it];
                         float4 v = make_float4(ex2_approx(x.x * kLog2e), ex2_approx(x.y * kLog2e),
                                                ex2_approx(x.z * kLog2e), ex2_approx(x.w * kLog2e));
@@ -629,13 +631,12 @@ ctc_lattice_kernel(const CtcParams p) {
                 } else {
                     const float *row = reinterpret_cast<const float *>(rowb);
                     int j = 0;
-                    for (int cc = gtid; cc < V; cc += gthreads, ++j) {
+                    for (int cc = lane; cc < V; cc += 32, ++j) {
                         float val = ex2_approx(row[cc] * kLog2e);
                         if (j >= 32 || ((present >> j) & 1u)) val -= label_mass(cc, w, slot);
                         grow[cc] = val * gs;
                     }
                 }
-                grow += grow_step;
             }
             // release the emission stage and the posterior buffer
             __syncwarp();
@@ -645,6 +646,7 @@ ctc_lattice_kernel(const CtcParams p) {
             }
             remaining -= n;
             ++chunk_idx;
+            grow_chunk += (int64_t)CH * grow_step;
             em_chunk += CH * slot_bytes;
             if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
         }

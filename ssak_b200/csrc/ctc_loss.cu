@@ -116,8 +116,10 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     // gradient warps: few when many CTAs share an SM (they only cost occupancy), more when one CTA owns it
     c->G = few ? (V <= 512 ? 4 : 8) : (V <= 64 ? 1 : (V <= 512 ? 2 : 4));
     if (K == 8 && c->W + 1 + c->G > 21) c->G = 21 - 1 - c->W;
+    // (set below once the chunk is known: G <= chunk, every gradient warp owns a frame of every chunk)
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
+    if (c->G > c->chunk) c->G = c->chunk;            // no idle gradient warp may run ahead of the ring
     int stages = ((few ? 64 : 36) * 1024) / (c->chunk * c->slot_bytes);
     c->stages = stages > 4 ? 4 : stages;
     if (c->stages < 2) return false;                 // V too large for the emission ring

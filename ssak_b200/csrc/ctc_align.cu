@@ -21,7 +21,7 @@
 namespace ssak {
 
 struct AlignCfg {
-    int K, W, NW;  // states per lane, warps, 32-bit words per bit plane per frame (= K*W)
+    int K, W, NW;  // states per lane, recursion warps, 32-state groups per frame (= K*W)
     int chunk, stages, slot_bytes;
 };
 
@@ -35,8 +35,9 @@ struct AlignParams {
     int Lmax;
     const int32_t *em_len, *tok_len;
     int blank, garbage;
-    const float *col0;
-    uint32_t *bp;        // [B][Tmax][2][NW]
+    const float *col0;   // caller's column 0 (first_as_garbage) or nullptr
+    float *col0_eff;     // [B][Tmax] column 0 of trellis rows 1..T_b incl. the +inf sentinel (workspace)
+    uint32_t *bp;        // [B][Tmax][W][2K] decision bits: per warp K words "changed>stayed", K words "<"
     unsigned char *rec;  // [B][Tmax] decision flags of the frames on the path
     int32_t *starts, *ends, *t_start, *status;
     double *scores;
@@ -56,25 +57,56 @@ static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
     if (s && *s) K = atoi(s);
     if (K == 0) {
         K = 1;
-        while (K < 16 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
+        while (K < 8 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
     }
     if (K != 1 && K != 2 && K != 4 && K != 8 && K != 16) return false;
-    int64_t W = (P + 32 * K - 1) / (32 * K);
-    if (W > 32 && K < 8) { K = 8; W = (P + 32 * K - 1) / (32 * K); }
-    if (W > (K == 16 ? 16 : 32)) return false;  // L <= 8191
+    if (K < 16 && (P + 32 * K - 1) / (32 * K) > 31) K = 16;  // one warp of the CTA is the producer
+    const int64_t W = (P + 32 * K - 1) / (32 * K);
+    if (W > (K == 16 ? 16 : 31)) return false;  // L <= 8191
     c->K = K;
     c->W = (int)W;
     c->NW = K * (int)W;
     c->slot_bytes = ring_slot_bytes(V);
-    int chunk = 8;
-    while (chunk > 1 && chunk * c->slot_bytes > 16384) chunk >>= 1;
-    c->chunk = chunk;
-    c->stages = 4;
-    return true;
+    c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;
+    int stages = (64 * 1024) / (c->chunk * c->slot_bytes);
+    c->stages = stages > 4 ? 4 : stages;
+    return c->stages >= 2;
 }
 
-template <int K>
-__global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(const AlignParams p) {
+// Column 0 of the trellis (:37 / :39) for rows 1..T_b, with the +inf sentinel of :42.  The cumulative
+// variant is the fp64 running sum of the blank column rounded to fp32 per element (torch.cumsum on the
+// CPU): strictly sequential by definition, so one warp per utterance fetches 32 frames at a time and
+// runs the 32 dependent fp64 adds through shuffles.
+__global__ void __launch_bounds__(32) align_col0_kernel(const AlignParams p) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    int Tb = p.em_len[b];
+    Tb = Tb < 0 ? 0 : (Tb > (int)p.Tmax ? (int)p.Tmax : Tb);
+    int L = p.tok_len[b];
+    L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
+    const float INF = __int_as_float(0x7f800000);
+    const float *em_b = p.em + (int64_t)b * p.sb + p.blank;
+    float *out = p.col0_eff + (int64_t)b * p.Tmax;
+    const float *c0 = p.garbage && p.col0 ? p.col0 + (int64_t)b * p.Tmax : nullptr;
+    double acc = 0.0;
+    for (int t0 = 0; t0 < Tb; t0 += 32) {
+        const int t = t0 + lane;
+        float x = 0.f;
+        if (t < Tb) x = c0 ? c0[t] : em_b[(int64_t)t * p.st];
+        float mine = x;
+        if (!c0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                acc += (double)__shfl_sync(0xffffffffu, x, i);
+                if (lane == i) mine = (float)acc;
+            }
+        }
+        if (t < Tb) out[t] = (t + 1 >= Tb + 1 - L) ? INF : mine;
+    }
+}
+
+// Warp roles: [0, W) recursion, W producer (bulk copies of the emission rows, mbarriers only).
+template <int K, int CH>
+__global__ void __launch_bounds__(K == 16 ? 544 : 1024, 1) align_forward_kernel(const AlignParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const AlignCfg &c = p.cfg;
     const int b = blockIdx.x;
@@ -83,7 +115,6 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
     const float INF = __int_as_float(0x7f800000);
     const int W = c.W;
     const bool compute = warp < W;
-    const int prod_warp = W < 32 ? W : 0;  // dedicated producer warp when the CTA has room
 
     int Tb = p.em_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.Tmax ? (int)p.Tmax : Tb);
@@ -103,34 +134,40 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
     const float *em_b = p.em + (int64_t)b * p.sb;
     const int32_t *tk = p.tokens + (int64_t)b * p.tok_stride;
 
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    float *xchg = reinterpret_cast<float *>(smem + 64);  // [2][32]
+    uint64_t *em_full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + 64);
+    float *xchg = reinterpret_cast<float *>(smem + 128);  // [2][34]: guard, W seams
     RowRing ring;
-    ring.slots = smem + 64 + 256;
-    ring.full = full;
-    ring.chunk = c.chunk;
+    ring.slots = smem + 416;
+    ring.full = em_full;
+    ring.chunk = CH;
     ring.stages = c.stages;
     ring.slot_bytes = c.slot_bytes;
     ring.row_bytes = 4 * V;
+    const int NST = c.stages, slot_bytes = c.slot_bytes;
 
     if (tid == 0) {
-        for (int s = 0; s < c.stages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&em_full[s], 1);
+            mbar_init(&em_empty[s], W);
+        }
         mbar_fence_init();
     }
+    if (tid < 68) xchg[tid] = -INF;
 
     // states of this thread, their tokens, trellis row 0 (:35, :41, :42)
     const int jbase = warp * 32 * K + lane;
-    int tok[K];
+    int tok_off[K];
     float v[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = jbase + k * 32;
         int tkn = p.blank;
-        if (j >= 1 && j <= L) {
+        if (compute && j >= 1 && j <= L) {
             tkn = tk[j - 1];
             tkn = tkn < 0 ? 0 : (tkn >= V ? V - 1 : tkn);
         }
-        tok[k] = tkn;
+        tok_off[k] = 4 * tkn;
         v[k] = j == 0 ? (L >= Tb + 1 ? INF : 0.f) : -INF;
     }
     const int jL_rel = L - warp * 32 * K;  // state L inside this warp?
@@ -144,69 +181,102 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
         for (int k = 0; k < K; ++k)
             if (jbase + k * 32 <= L) d[jbase + k * 32] = v[k];
     }
-    if (compute && lane == 31) xchg[warp] = v[K - 1];
     __syncthreads();
+    if (compute && lane == 31) xchg[1 + warp] = v[K - 1];
+    __syncthreads();  // last CTA-wide barrier
 
-    const int C = c.chunk, NST = c.stages, NW = c.NW;
-    RingProducer prod;
-    prod.src = em_b;
-    prod.step_elems = p.st;
-    prod.stage = 0;
-    prod.remaining = Tb;
-    if (warp == prod_warp && lane == 0)
-        for (int n = 0; n < NST; ++n) ring_issue_next(ring, prod);
-    int free_at = C;  // iteration at which the oldest in-flight stage has no reader left
-    RingPos pos;
-    pos.init(em_b, p.st);
-    double acc = 0.0;  // :39 cumulative blank column, fp64 running sum (thread 0)
-    uint32_t *bp_row = p.bp + (int64_t)b * p.Tmax * 2 * NW;
-    const float *col0_b = p.garbage && p.col0 ? p.col0 + (int64_t)b * p.Tmax : nullptr;
-    float *dump_row = p.dump ? p.dump + ((int64_t)b * (p.Tmax + 1) + 1) * (p.Lmax + 1) : nullptr;
-
-    for (int t = 0; t < Tb; ++t) {
-        const int par = t & 1;
-        if (warp == prod_warp && t == free_at) {
-            if (lane == 0) ring_issue_next(ring, prod);
-            free_at += C;
+    const int nchunks = (Tb + CH - 1) / CH;
+    if (!compute) {
+        // ================= producer warp =================
+        RingProducer prod;
+        prod.src = em_b;
+        prod.step_elems = p.st;
+        prod.stage = 0;
+        prod.remaining = Tb;
+        int issued = 0, round = 0;
+        while (issued < nchunks) {
+            bool free_ = round == 0;
+            if (!free_) free_ = __shfl_sync(FULL, (int)mbar_test(&em_empty[prod.stage], (round - 1) & 1), 0);
+            if (free_) {
+                const int stg = prod.stage;
+                if (lane == 0) ring_issue_next(ring, prod);
+                prod.stage = __shfl_sync(FULL, prod.stage, 0);
+                if (prod.stage <= stg) ++round;
+                ++issued;
+            } else {
+                __nanosleep(20);
+            }
         }
-        if (compute) {
-            const float *row = pos.row(ring);
-            const float eb = row[p.blank];
+        return;
+    }
+
+    // ================= recursion warps: chunk-unrolled time loop =================
+    const int nbar = W * 32, NW = c.NW;
+    const unsigned a15_0 = (unsigned)(reinterpret_cast<uintptr_t>(em_b) & 15);
+    const unsigned a15_step = (unsigned)((p.st * 4) & 15);
+    const int blank_off = 4 * p.blank;
+    const unsigned seam_m = lane == 0 ? 0xffffffffu : 0u;
+    const unsigned zero_m = tid == 0 ? 0xffffffffu : 0u;  // the thread that owns trellis column 0
+    auto sel = [](unsigned m, float a, float bb) {
+        return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
+    };
+    const float *x_in = xchg + warp;  // seam of warp-1 (index 0 is the guard)
+    float *x_out = xchg + 1 + warp;
+    uint32_t *bp_ptr = p.bp + (int64_t)b * p.Tmax * 2 * NW + warp * 2 * K;
+    const float *c0_ptr = p.col0_eff + (int64_t)b * p.Tmax;
+    float *dump_row = p.dump ? p.dump + ((int64_t)b * (p.Tmax + 1) + 1) * (p.Lmax + 1) + jbase : nullptr;
+    const unsigned char *em_base = ring.slots, *em_chunk = em_base;
+    int em_stage = 0, em_phase = 0, remaining = Tb, t = 0;
+    float c0n[CH];  // column-0 values of the next chunk (thread 0), fetched one chunk ahead
+#pragma unroll
+    for (int f = 0; f < CH; ++f) c0n[f] = (tid == 0 && f < Tb) ? __ldg(c0_ptr + f) : 0.f;
+
+    while (remaining > 0) {
+        const int n = remaining < CH ? remaining : CH;
+        float c0[CH];
+#pragma unroll
+        for (int f = 0; f < CH; ++f) {
+            c0[f] = c0n[f];
+            c0n[f] = (tid == 0 && t + CH + f < Tb) ? __ldg(c0_ptr + t + CH + f) : 0.f;
+        }
+        mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+#pragma unroll
+        for (int f = 0; f < CH; ++f) {
+            if (f >= n) break;
+            const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
+            const float eb = *reinterpret_cast<const float *>(row + blank_off);
             float e[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) e[k] = row[tok[k]];
-            pos.advance(ring);
+            for (int k = 0; k < K; ++k) e[k] = *reinterpret_cast<const float *>(row + tok_off[k]);
+            const float xin = x_in[(f & 1) * 34];
             float r[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, v[k], (lane + 31) & 31);
-            const float xin = warp > 0 ? xchg[par * 32 + warp - 1] : 0.f;
-            unsigned myword = 0;
+            uint32_t words[2 * K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const float prev = lane == 0 ? (k == 0 ? xin : r[k > 0 ? k - 1 : 0]) : r[k];
+                const float prev = sel(seam_m, k == 0 ? xin : r[k > 0 ? k - 1 : 0], r[k]);
                 const float stayb = v[k] + eb;             // :48
                 const float stayt = v[k] + e[k];           // :49
                 const float chg = prev + e[k];             // :51
                 const float stayed = fmaxf(stayb, stayt);  // what backtrack recomputes (:96-99)
                 float nv = fmaxf(stayed, chg);
-                bool gt = chg > stayed, lt = chg < stayed;
-                if (k == 0 && tid == 0) {  // column 0 (:37 / :39) with the +inf sentinel (:42)
-                    if (col0_b) {
-                        nv = col0_b[t];
-                    } else {
-                        acc += (double)eb;
-                        nv = (float)acc;
-                    }
-                    if (t + 1 >= Tb + 1 - L) nv = INF;
-                    gt = lt = false;
-                }
+                if (k == 0) nv = sel(zero_m, c0[f], nv);   // column 0 (:37 / :39 / :42), never read back as a decision
                 v[k] = nv;
-                const unsigned bg = __ballot_sync(FULL, gt), bl = __ballot_sync(FULL, lt);
-                if (lane == k) myword = bg;
-                if (lane == K + k) myword = bl;
+                words[k] = __ballot_sync(FULL, chg > stayed);
+                words[K + k] = __ballot_sync(FULL, chg < stayed);
             }
-            if (lane < 2 * K) bp_row[lane < K ? warp * K + lane : NW + warp * K + (lane - K)] = myword;
-            bp_row += 2 * NW;
+            if (lane == 31) x_out[((f & 1) ^ 1) * 34] = v[K - 1];
+            if (lane == 0) {
+                if (K == 1) {
+                    *reinterpret_cast<uint2 *>(bp_ptr) = make_uint2(words[0], words[1]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2 * K; q += 4)
+                        *reinterpret_cast<uint4 *>(bp_ptr + q) = make_uint4(words[q], words[q + 1], words[q + 2], words[q + 3]);
+                }
+            }
+            bp_ptr += 2 * NW;
             if (ownsL) {
                 float vl = v[0];
 #pragma unroll
@@ -214,18 +284,25 @@ __global__ void __launch_bounds__(K == 16 ? 512 : 1024, 1) align_forward_kernel(
                     if (k == kL) vl = v[k];
                 if (vl > best) {  // first maximum (:88)
                     best = vl;
-                    best_t = t + 1;
+                    best_t = t + f + 1;
                 }
             }
             if (dump_row) {
 #pragma unroll
                 for (int k = 0; k < K; ++k)
-                    if (jbase + k * 32 <= L) dump_row[jbase + k * 32] = v[k];
+                    if (jbase + k * 32 <= L) dump_row[k * 32] = v[k];
                 dump_row += p.Lmax + 1;
             }
-            if (lane == 31) xchg[(par ^ 1) * 32 + warp] = v[K - 1];
+            if (f == n - 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+            }
+            named_bar_sync(1, nbar);
         }
-        __syncthreads();
+        remaining -= n;
+        t += n;
+        em_chunk += CH * slot_bytes;
+        if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
     }
     if (ownsL) p.t_start[b] = best_t;
 }
@@ -238,7 +315,7 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
     Tb = Tb < 0 ? 0 : (Tb > (int)p.Tmax ? (int)p.Tmax : Tb);
     int L = p.tok_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
-    const int NW = p.cfg.NW;
+    const int NW = p.cfg.NW, KK = p.cfg.K;
     const uint32_t *bp_b = p.bp + (int64_t)b * p.Tmax * 2 * NW;
     unsigned char *rec = p.rec + (int64_t)b * p.Tmax;
     int32_t *st_b = p.starts + (int64_t)b * p.Lmax;
@@ -253,15 +330,17 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
             // lane i holds the 32-state window [base, base+32) of trellis row t-i
             const int base = max(j - 31, 0);
             const int i0 = base >> 5, sh = base & 31;
+            // 32-state group g lives at word (g / K) * 2K + (g % K) ("changed > stayed"), +K ("<")
+            const int w0 = (i0 / KK) * 2 * KK + (i0 % KK), w1 = ((i0 + 1) / KK) * 2 * KK + ((i0 + 1) % KK);
             uint32_t g0 = 0, g1 = 0, l0 = 0, l1 = 0;
             const int rr = t - lane;
             if (rr >= 1) {
                 const uint32_t *rowp = bp_b + (int64_t)(rr - 1) * 2 * NW;
-                g0 = __ldg(rowp + i0);
-                l0 = __ldg(rowp + NW + i0);
+                g0 = __ldg(rowp + w0);
+                l0 = __ldg(rowp + w0 + KK);
                 if (i0 + 1 < NW) {
-                    g1 = __ldg(rowp + i0 + 1);
-                    l1 = __ldg(rowp + NW + i0 + 1);
+                    g1 = __ldg(rowp + w1);
+                    l1 = __ldg(rowp + w1 + KK);
                 }
             }
             const uint32_t wg = __funnelshift_r(g0, g1, sh), wl = __funnelshift_r(l0, l1, sh);
@@ -334,7 +413,7 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
 }
 
 static size_t align_smem_bytes(const AlignCfg &c) {
-    return align_up(64 + 256 + (size_t)c.stages * c.chunk * c.slot_bytes, 16);
+    return align_up(416 + (size_t)c.stages * c.chunk * c.slot_bytes, 16);
 }
 
 }  // namespace ssak
@@ -345,7 +424,7 @@ extern "C" size_t ssak_align_workspace_bytes(int64_t B, int64_t Tmax, int64_t Lm
     AlignCfg c;
     if (B <= 0 || Tmax < 0 || Lmax < 0 || !choose_align_cfg(Lmax, B, 64, &c)) return 0;
     return align_up((size_t)B * (size_t)Tmax * 2 * c.NW * sizeof(uint32_t), 256) +
-           align_up((size_t)B * (size_t)Tmax, 256) + 256;
+           align_up((size_t)B * (size_t)Tmax, 256) + align_up((size_t)B * (size_t)Tmax * sizeof(float), 256) + 256;
 }
 
 extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax, int64_t V,
@@ -375,21 +454,29 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     p.garbage = first_as_garbage; p.col0 = col0;
     char *ws = reinterpret_cast<char *>(workspace);
     p.bp = reinterpret_cast<uint32_t *>(ws);
-    p.rec = reinterpret_cast<unsigned char *>(
-        ws + align_up((size_t)B * (size_t)Tmax * 2 * p.cfg.NW * sizeof(uint32_t), 256));
+    const size_t bp_bytes = align_up((size_t)B * (size_t)Tmax * 2 * p.cfg.NW * sizeof(uint32_t), 256);
+    p.rec = reinterpret_cast<unsigned char *>(ws + bp_bytes);
+    p.col0_eff = reinterpret_cast<float *>(ws + bp_bytes + align_up((size_t)B * (size_t)Tmax, 256));
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     p.starts = starts; p.ends = ends; p.scores = scores; p.t_start = t_start; p.status = status;
     p.dump = trellis_dump; p.path_token = path_token; p.path_prob = path_prob;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)B), block((p.cfg.W + (p.cfg.W < 32 ? 1 : 0)) * 32);
-#define SSAK_LAUNCH(KK)                                                                        \
-    case KK: {                                                                                 \
-        auto kern = align_forward_kernel<KK>;                                                  \
+    align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
+    int rc = check_launch();
+    if (rc != SSAK_OK) return rc;
+    dim3 grid((unsigned)B), block((p.cfg.W + 1) * 32);
+#define SSAK_LAUNCH2(KK, CC)                                                                   \
+    {                                                                                          \
+        auto kern = align_forward_kernel<KK, CC>;                                              \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem_bytes);                                 \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
         kern<<<grid, block, smem_bytes, s>>>(p);                                               \
-        break;                                                                                 \
     }
+#define SSAK_LAUNCH(KK)                                                                        \
+    case KK:                                                                                   \
+        if (p.cfg.chunk == 8) SSAK_LAUNCH2(KK, 8) else SSAK_LAUNCH2(KK, 4)                     \
+        break;
     switch (p.cfg.K) {
         SSAK_LAUNCH(1)
         SSAK_LAUNCH(2)
@@ -399,7 +486,8 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
         default: return SSAK_ERR_UNSUPPORTED;
     }
 #undef SSAK_LAUNCH
-    int rc = check_launch();
+#undef SSAK_LAUNCH2
+    rc = check_launch();
     if (rc != SSAK_OK) return rc;
     align_backtrace_kernel<<<(unsigned)B, 128, 0, s>>>(p);
     return check_launch();

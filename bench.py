@@ -162,7 +162,7 @@ def run_ours(args, rank, world, local_rank):
     lp, tg, il, tl, cells = make_batch(name, 1234 + 2 + 1000 * rank)   # weak scaling: own batch per rank
     lp_pin, grad_pin = lp.pin_memory(), torch.empty_like(lp).pin_memory()
     lp_d = lp_pin.to(dev, non_blocking=True)
-    tg_d, il_d, tl_d = tg.to(dev), il.to(dev), tl.to(dev)
+    tg_d, il_d, tl_d = tg.to(dev, torch.int32), il.to(dev, torch.int32), tl.to(dev, torch.int32)
     flush = torch.zeros(96 * 1024 * 1024, dtype=torch.float32, device=dev)      # 384 MB > 126 MB L2
 
     def step():
@@ -256,11 +256,12 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"{name}: CTC loss fwd+bwd, B={B} per GPU, T={T}, V={V}, L in [{Lmin},{Lmax}], "
                                    f"T_b in [{Tmin},{T}], planted-alignment emissions, reduction=mean, zero_infinity",
                        "cells_per_step_per_gpu": cells, "l2": "flushed (384 MB write) before every timed step",
+                       "inputs": "log_probs fp32 [T,B,V] contiguous, int32 padded targets / lengths, resident in HBM",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
             "e2e": {"value": total * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
                     "path": "ssak_ctc_loss_host (C ABI): pinned host log-probs in, nll + full gradient out"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 4 * args.steps,   # lattice fwd, join, reduce, lattice bwd
             "roofline": {"bound": "hbm", "kernel": "ctc_lattice_kernel<K,true> (backward: recursion + gradient)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "peak_source": hbm_src,

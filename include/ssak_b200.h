@@ -105,6 +105,16 @@ SSAK_API int ssak_ctc_loss_backward(const float *grad_out, const float *log_prob
                                     int64_t g_stride_t, int64_t g_stride_b, void *workspace,
                                     size_t workspace_bytes, ssak_stream_t stream);
 
+/* Reduction of aten::ctc_loss (site-packages/torch/nn/functional.py:3042-3115) fused into one launch:
+ *   reduction 0 'none' (loss_out[B]), 1 'mean' = mean_b(nll_b / clamp(L_b,1)), 2 'sum',
+ *   3 'mean_volume' = sum_b nll_b / sum_b L_b (NeMo, ssak/train/nemo/yamls/model.yaml:3);
+ *   zero_infinity replaces +inf by 0.  grad_scale[B] (may be NULL) receives d loss / d nll_b
+ *   (0 for the samples zero_infinity removed), i.e. what grad_out of ssak_ctc_loss_backward is
+ *   after multiplication by the upstream scalar gradient. */
+SSAK_API int ssak_ctc_loss_reduce(const float *neg_log_likelihood, const int32_t *target_lengths,
+                                  int64_t B, int32_t reduction, int32_t zero_infinity, float *loss_out,
+                                  float *grad_scale, ssak_stream_t stream);
+
 /* =========================================================================================
  * Forced alignment.  Replaces get_trellis + backtrack + merge_repeats
  *   (ssak/utils/align_transcriptions.py:27-70, 79-123, 141-157), i.e. the reference's own

@@ -731,6 +731,47 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     }
 }
 
+// Fused reduction ('none' | 'mean' | 'sum' | 'mean_volume') + zero_infinity + d loss / d nll_b.
+__global__ void __launch_bounds__(256) ctc_reduce_kernel(const float *nll, const int32_t *tgt_len, int64_t B,
+                                                         int reduction, int zero_inf, float *loss_out,
+                                                         float *grad_scale) {
+    __shared__ double red_a[8], red_b[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a = 0.0, l = 0.0;
+    for (int64_t b = tid; b < B; b += 256) {
+        float x = nll[b];
+        const bool dropped = zero_inf && !(x < 3.0e38f);
+        if (dropped) x = 0.f;
+        const int L = tgt_len[b];
+        const float denom = (float)(L < 1 ? 1 : L);
+        if (reduction == 0) loss_out[b] = x;
+        float g = dropped ? 0.f : 1.f;
+        if (reduction == 1) { a += (double)(x / denom); g = g / (denom * (float)B); }
+        else { a += (double)x; }
+        l += (double)L;
+        if (grad_scale && reduction != 3) grad_scale[b] = g;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        l += __shfl_xor_sync(0xffffffffu, l, d);
+    }
+    if (lane == 0) { red_a[warp] = a; red_b[warp] = l; }
+    __syncthreads();
+    double A = 0.0, Lsum = 0.0;
+    for (int w = 0; w < 8; ++w) { A += red_a[w]; Lsum += red_b[w]; }
+    if (Lsum < 1.0) Lsum = 1.0;
+    if (tid == 0) {
+        if (reduction == 1) loss_out[0] = (float)(A / (double)B);
+        else if (reduction == 2) loss_out[0] = (float)A;
+        else if (reduction == 3) loss_out[0] = (float)(A / Lsum);
+    }
+    if (grad_scale && reduction == 3)
+        for (int64_t b = tid; b < B; b += 256) {
+            const bool dropped = zero_inf && !(nll[b] < 3.0e38f);
+            grad_scale[b] = dropped ? 0.f : (float)(1.0 / Lsum);
+        }
+}
+
 // ---------------------------------------------------------------------------- launchers
 template <bool GRAD>
 static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
@@ -850,4 +891,14 @@ extern "C" int ssak_ctc_loss_backward(const float *grad_out, const float *log_pr
     p.grad_out = grad_out; p.grad = grad; p.gst = g_stride_t; p.gsb = g_stride_b;
     p.zero_inf = zero_infinity;
     return launch_lattice<true>(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ssak_ctc_loss_reduce(const float *neg_log_likelihood, const int32_t *target_lengths,
+                                    int64_t B, int32_t reduction, int32_t zero_infinity, float *loss_out,
+                                    float *grad_scale, ssak_stream_t stream) {
+    if (!neg_log_likelihood || !target_lengths || !loss_out || B <= 0 || reduction < 0 || reduction > 3)
+        return SSAK_ERR_INVALID_ARGUMENT;
+    ctc_reduce_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        neg_log_likelihood, target_lengths, B, reduction, zero_infinity, loss_out, grad_scale);
+    return check_launch();
 }

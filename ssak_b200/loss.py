@@ -38,38 +38,62 @@ def _as_length_tensor(x, B: int, device, name: str):
     return dev, host
 
 
+_RED_CODE = {"none": 0, "mean": 1, "sum": 2, "mean_volume": 3}
+_OFFSET_CACHE = {}
+
+
+def _padded_offsets(B: int, smax: int, device):
+    key = (B, smax, str(device))
+    t = _OFFSET_CACHE.get(key)
+    if t is None:
+        if len(_OFFSET_CACHE) > 64:
+            _OFFSET_CACHE.clear()
+        t = torch.arange(B, device=device, dtype=torch.int64) * smax
+        _OFFSET_CACHE[key] = t
+    return t
+
+
 class _CTCLossFunction(torch.autograd.Function):
-    """aten::_ctc_loss / _ctc_loss_backward on libssak_b200.so: forward -> nll[B]."""
+    """aten::_ctc_loss + the reduction of aten::ctc_loss / aten::_ctc_loss_backward on libssak_b200.so.
+    forward: 3 launches (half lattices, join, reduction); backward: 1 launch (+ one scale)."""
 
     @staticmethod
-    def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity):
+    def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity,
+                reduction):
         L = _lib.lib()
         T, B, V = log_probs.shape
+        dev = log_probs.device
         save = bool(ctx.needs_input_grad[0])
         ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, max_target_len, int(save))
         if ws_bytes == 0:
             raise _lib.SsakB200Error(
                 f"ctc_loss: shape not supported (T={T}, B={B}, max target length={max_target_len})")
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=log_probs.device)
-        nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
-        stream = torch.cuda.current_stream(log_probs.device).cuda_stream
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        red = _RED_CODE[reduction]
+        loss = torch.empty(B if red == 0 else (), dtype=torch.float32, device=dev)
+        gscale = torch.empty(B, dtype=torch.float32, device=dev) if save else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
         rc = L.ssak_ctc_loss_forward(log_probs.data_ptr(), T, B, V, log_probs.stride(0), log_probs.stride(1),
                                      targets.data_ptr(), tgt_off.data_ptr(), in_len.data_ptr(),
                                      tgt_len.data_ptr(), max_target_len, blank, int(save), nll.data_ptr(),
                                      ws.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "ssak_ctc_loss_forward")
+        rc = L.ssak_ctc_loss_reduce(nll.data_ptr(), tgt_len.data_ptr(), B, red, int(zero_infinity),
+                                    loss.data_ptr(), _lib.ptr(gscale), stream)
+        _lib.check(rc, "ssak_ctc_loss_reduce")
         if save:
-            ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws)
+            ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale)
             ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes)
-        return nll
+        return loss
 
     @staticmethod
-    def backward(ctx, grad_nll):
-        log_probs, targets, tgt_off, in_len, tgt_len, nll, ws = ctx.saved_tensors
+    def backward(ctx, grad_loss):
+        log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale = ctx.saved_tensors
         max_target_len, blank, zero_infinity, ws_bytes = ctx.meta
         L = _lib.lib()
         T, B, V = log_probs.shape
-        g = grad_nll.to(torch.float32).contiguous()
+        g = (gscale * grad_loss.to(torch.float32)).contiguous()   # [B]: upstream x d loss / d nll_b
         # same (dense) layout as log_probs: HF hands in a transposed [B,T,V] buffer and its
         # log_softmax backward reads the gradient in that layout
         grad = torch.empty_like(log_probs)
@@ -83,15 +107,13 @@ class _CTCLossFunction(torch.autograd.Function):
                                           int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
                                           grad.stride(1), ws.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "ssak_ctc_loss_backward")
-        return grad, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None
 
 
-def ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, blank=0, zero_infinity=False):
-    """Per-utterance negative log-likelihood [B] (+inf when infeasible), differentiable w.r.t.
-    `log_probs` with torch's gradient convention.  Arguments as torch.nn.functional.ctc_loss."""
+def _prepare(log_probs, targets, input_lengths, target_lengths, blank):
+    """Argument checking / normalisation shared by the public entry points (torch's rules)."""
     _lib.require_cuda(log_probs, "log_probs")
-    unbatched = log_probs.dim() == 2
-    if unbatched:
+    if log_probs.dim() == 2:
         log_probs = log_probs.unsqueeze(1)
         if isinstance(targets, torch.Tensor) and targets.dim() == 1:
             targets = targets.unsqueeze(0)
@@ -111,12 +133,14 @@ def ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, bl
         targets = torch.as_tensor(targets)
     if targets.is_floating_point():
         raise RuntimeError("targets must be integral")
-    tg = targets.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+    tg = targets
+    if tg.device != dev or tg.dtype != torch.int32 or not tg.is_contiguous():
+        tg = tg.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
     if tg.dim() == 2:
         if tg.size(0) != B:
             raise RuntimeError(f"targets must have batch size {B}")
         smax = tg.size(1)
-        tgt_off = torch.arange(B, device=dev, dtype=torch.int64) * smax
+        tgt_off = _padded_offsets(B, smax, dev)
         max_target_len = smax
         if tgt_host is not None:
             if max(tgt_host, default=0) > smax:
@@ -140,9 +164,13 @@ def ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, bl
         raise RuntimeError("Expected target_lengths to have non-negative values")
     if tg.numel() == 0:
         tg = torch.zeros(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        return _CTCLossFunction.apply(log_probs, tg, tgt_off, in_len, tgt_len, int(max_target_len),
-                                      int(blank), bool(zero_infinity)), tgt_len
+    return log_probs, tg, tgt_off, in_len, tgt_len, int(max_target_len)
+
+
+def ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, blank=0, zero_infinity=False):
+    """Per-utterance negative log-likelihood [B] (0 instead of +inf with zero_infinity), differentiable
+    w.r.t. `log_probs` with torch's gradient convention.  Arguments as torch.nn.functional.ctc_loss."""
+    return ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, "none", zero_infinity)
 
 
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean",
@@ -152,17 +180,12 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reducti
     Extra reduction "mean_volume" = sum(nll) / sum(target_lengths) (NeMo, model.yaml:3)."""
     if reduction not in _REDUCTIONS:
         raise ValueError(f"{reduction} is not a valid value for reduction")
-    nll, tgt_len = ctc_neg_log_likelihood(log_probs, targets, input_lengths, target_lengths, blank,
-                                          zero_infinity)
-    if zero_infinity:
-        nll = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll)
-    if reduction == "none":
-        return nll[0] if log_probs.dim() == 2 else nll
-    if reduction == "sum":
-        return nll.sum()
-    if reduction == "mean_volume":
-        return nll.sum() / tgt_len.sum().clamp_min(1).to(nll.dtype)
-    return (nll / tgt_len.clamp_min(1).to(nll.dtype)).mean()
+    unbatched = isinstance(log_probs, torch.Tensor) and log_probs.dim() == 2
+    lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, input_lengths, target_lengths, blank)
+    with torch.cuda.device(lp.device):
+        out = _CTCLossFunction.apply(lp, tg, tgt_off, in_len, tgt_len, lmax, int(blank), bool(zero_infinity),
+                                     reduction)
+    return out[0] if (unbatched and reduction == "none") else out
 
 
 def sb_ctc_loss(log_probs, targets, input_lens, target_lens, blank_index, reduction="mean"):

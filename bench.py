@@ -167,7 +167,12 @@ def run_ours(args, rank, world, local_rank):
 
     def step():
         x = lp_d.detach().requires_grad_(True)
-        loss = ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True)
+        if world > 1:   # utterance-sharded batch: local lattices + ONE all-reduce of 2 scalars (NCCL)
+            from ssak_b200.shard import sharded_ctc_loss
+            loss = sharded_ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True,
+                                    global_batch=B * world)
+        else:
+            loss = ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True)
         loss.backward()
         return loss, x.grad
 
@@ -221,7 +226,7 @@ def run_ours(args, rank, world, local_rank):
     # parity gate on the timed configuration: the host-ABI result equals the torch-facing one
     _, g = step()
     torch.cuda.synchronize()
-    gscale = (1.0 / (B * tl.clamp_min(1).float())).view(1, B, 1)
+    gscale = (1.0 / (B * world * tl.clamp_min(1).float())).view(1, B, 1)
     assert (g.cpu() - grad_pin * gscale).abs().max().item() < 1e-6
 
     times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)

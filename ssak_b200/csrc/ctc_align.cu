@@ -193,19 +193,13 @@ __global__ void __launch_bounds__(K == 16 ? 544 : 1024, 1) align_forward_kernel(
         prod.step_elems = p.st;
         prod.stage = 0;
         prod.remaining = Tb;
-        int issued = 0, round = 0;
-        while (issued < nchunks) {
-            bool free_ = round == 0;
-            if (!free_) free_ = __shfl_sync(FULL, (int)mbar_test(&em_empty[prod.stage], (round - 1) & 1), 0);
-            if (free_) {
-                const int stg = prod.stage;
-                if (lane == 0) ring_issue_next(ring, prod);
-                prod.stage = __shfl_sync(FULL, prod.stage, 0);
-                if (prod.stage <= stg) ++round;
-                ++issued;
-            } else {
-                __nanosleep(20);
-            }
+        int round = 0;
+        for (int n = 0; n < nchunks; ++n) {
+            if (round > 0) mbar_wait(&em_empty[prod.stage], (uint32_t)((round - 1) & 1));  // hardware-suspended wait
+            const int stg = prod.stage;
+            if (lane == 0) ring_issue_next(ring, prod);
+            prod.stage = __shfl_sync(FULL, prod.stage, 0);
+            if (prod.stage <= stg) ++round;
         }
         return;
     }

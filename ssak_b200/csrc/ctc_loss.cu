@@ -115,7 +115,7 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->row_elems = 2 * c->P_pad + 8;
     // gradient warps: few when many CTAs share an SM (they only cost occupancy), more when one CTA owns it
     c->G = few ? (V <= 512 ? 4 : 8) : (V <= 64 ? 1 : (V <= 512 ? 2 : 4));
-    if (K == 8 && c->W + 1 + c->G > 21) c->G = 21 - 1 - c->W;
+    if (K == 8 && c->W + 2 + c->G > 22) c->G = 22 - 2 - c->W;
     // (set below once the chunk is known: G <= chunk, every gradient warp owns a frame of every chunk)
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
@@ -149,9 +149,9 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
 }
 
 // ------------------------------------------------------------------------------ kernel
-// Warp roles: [0, W) recursion, W producer (bulk copies + scaling), (W, W+G] gradient (backward).
+// Warp roles: [0, W) recursion; W emission producer; backward only: W+1 lattice-row producer, then G gradient warps.
 template <int K, bool GRAD, int CH>
-__global__ void __launch_bounds__(K == 8 ? (GRAD ? 672 : 544) : (GRAD ? 544 : 288), 1)
+__global__ void __launch_bounds__(K == 8 ? (GRAD ? 704 : 544) : (GRAD ? 576 : 288), 1)
 ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const CtcCfg &c = p.cfg;
@@ -160,7 +160,8 @@ ctc_lattice_kernel(const CtcParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = c.W;
     const bool compute = warp < W;
-    const bool producer = warp == W;
+    constexpr int NPROD = GRAD ? 2 : 1;  // producer warps
+    const bool producer = warp >= W && warp < W + NPROD;
     const unsigned FULL = 0xffffffffu;
 
     int Tb = p.in_len[b];
@@ -358,51 +359,42 @@ ctc_lattice_kernel(const CtcParams p) {
     const float *first_row = lp_b + (int64_t)t_first * p.st;
 
     if (producer) {
-        // ================= producer warp: TMA issue + in-place scaling, mbarriers only ============
-        RingProducer prod;
-        prod.src = first_row;
-        prod.step_elems = step_elems;
-        prod.stage = 0;
-        prod.remaining = nsteps;
-        int em_issued = 0, em_round = 0;   // round: how many times the issue stage was used before
-        const int Co = c.or_chunk, No = c.or_stages;
-        const int or_nchunks = GRAD ? (nsteps + Co - 1) / Co : 0;
-        int or_issued = 0, or_stage = 0, or_round = 0, or_left = nsteps;
-        const float *or_src = GRAD ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
-        const int64_t or_step = (int64_t)dt * row_elems;
-        while (em_issued < nchunks || or_issued < or_nchunks) {
-            bool progress = false;
-            if (em_issued < nchunks) {
-                bool free_ = em_round == 0;
-                if (!free_) free_ = __shfl_sync(FULL, (int)mbar_test(&em_empty[prod.stage], (em_round - 1) & 1), 0);
-                if (free_) {
-                    const int stg = prod.stage;
-                    if (lane == 0) ring_issue_next(ring, prod);
-                    prod.stage = __shfl_sync(FULL, prod.stage, 0);
-                    if (prod.stage <= stg) ++em_round;  // wrapped (or single stage)
-                    ++em_issued;
-                    progress = true;
-                }
+        // ================= producer warps: bulk-copy issue, blocking mbarrier waits only ==========
+        // warp W streams the emission rows; in the backward call warp W+1 streams the other
+        // direction's stored lattice rows.  try_wait suspends the warp in hardware: no polling.
+        if (warp == W) {
+            RingProducer prod;
+            prod.src = first_row;
+            prod.step_elems = step_elems;
+            prod.stage = 0;
+            prod.remaining = nsteps;
+            int round = 0;
+            for (int n = 0; n < nchunks; ++n) {
+                if (round > 0) mbar_wait(&em_empty[prod.stage], (uint32_t)((round - 1) & 1));
+                const int stg = prod.stage;
+                if (lane == 0) ring_issue_next(ring, prod);
+                prod.stage = __shfl_sync(FULL, prod.stage, 0);
+                if (prod.stage <= stg) ++round;
             }
-            if (GRAD && or_issued < or_nchunks) {
-                bool free_ = or_round == 0;
-                if (!free_) free_ = __shfl_sync(FULL, (int)mbar_test(&or_empty[or_stage], (or_round - 1) & 1), 0);
-                if (free_) {
-                    const int n = or_left < Co ? or_left : Co;
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&or_full[or_stage], (uint32_t)(n * row_bytes));
-                        unsigned char *dst = or_slots + (size_t)or_stage * Co * row_bytes;
-                        for (int f = 0; f < n; ++f, dst += row_bytes)
-                            bulk_g2s(dst, or_src + (int64_t)f * or_step, (uint32_t)row_bytes, &or_full[or_stage]);
-                    }
-                    or_src += (int64_t)n * or_step;
-                    or_left -= n;
-                    if (++or_stage == No) { or_stage = 0; ++or_round; }
-                    ++or_issued;
-                    progress = true;
+        } else {
+            const int Co = c.or_chunk, No = c.or_stages;
+            const int or_nchunks = (nsteps + Co - 1) / Co;
+            int or_stage = 0, or_round = 0, or_left = nsteps;
+            const float *or_src = p.rows + ((int64_t)b * p.T + t_first) * row_elems;
+            const int64_t or_step = (int64_t)dt * row_elems;
+            for (int n = 0; n < or_nchunks; ++n) {
+                if (or_round > 0) mbar_wait(&or_empty[or_stage], (uint32_t)((or_round - 1) & 1));
+                const int cnt = or_left < Co ? or_left : Co;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&or_full[or_stage], (uint32_t)(cnt * row_bytes));
+                    unsigned char *dst = or_slots + (size_t)or_stage * Co * row_bytes;
+                    for (int f = 0; f < cnt; ++f, dst += row_bytes)
+                        bulk_g2s(dst, or_src + (int64_t)f * or_step, (uint32_t)row_bytes, &or_full[or_stage]);
                 }
+                or_src += (int64_t)cnt * or_step;
+                or_left -= cnt;
+                if (++or_stage == No) { or_stage = 0; ++or_round; }
             }
-            if (!progress) __nanosleep(20);
         }
         return;
     }
@@ -576,7 +568,7 @@ ctc_lattice_kernel(const CtcParams p) {
         // ---------------- gradient warps: consume the posterior ring, mbarriers only ----------------
         // Each gradient warp takes whole frames (frame f of a chunk goes to warp f mod G), so the
         // per-frame latency (barrier probe, run sums, exp, store) overlaps across warps.
-        const int gwarp = warp - (W + 1), G = c.G;
+        const int gwarp = warp - (W + NPROD), G = c.G;
         float *grow_chunk = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
         const unsigned char *em_chunk = em_base;
         int em_stage = 0, em_phase = 0;
@@ -669,7 +661,7 @@ ctc_lattice_kernel(const CtcParams p) {
             }
         }
     } else if (dir == 0) {
-        const int nthr = n_consumers * 32, me = compute ? tid : tid - 32;  // every warp but the producer
+        const int nthr = n_consumers * 32, me = compute ? tid : tid - 32 * NPROD;  // every warp but the producers
         for (int t = Tb; t < (int)p.T; ++t) {  // frames beyond the utterance: exact zeros
             float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
             for (int cc = me; cc < V; cc += nthr) g[cc] = 0.f;
@@ -778,7 +770,7 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     const CtcCfg &c = p.cfg;
     const size_t smem_bytes = smem_bytes_for(c, p.V, p.Lmax, GRAD);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)p.B, 2), block((c.W + 1 + (GRAD ? c.G : 0)) * 32);
+    dim3 grid((unsigned)p.B, 2), block((c.W + (GRAD ? 2 + c.G : 1)) * 32);
 #define SSAK_LAUNCH2(KK, CC)                                                                   \
     {                                                                                          \
         auto kern = ctc_lattice_kernel<KK, GRAD, CC>;                                          \

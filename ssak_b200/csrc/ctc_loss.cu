@@ -97,8 +97,8 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     const int64_t P = Lmax + 1;
     // Few CTAs (latency regime): one recursion warp per SM sub-partition.  Many CTAs
     // (throughput regime): fat lanes, few warps, so several utterances share an SM.
-    const bool few = 2 * B <= 2 * 148;
-    int wtarget = few ? 8 : ((2 * B <= 6 * 148) ? 4 : 2);
+    const bool few = env_int("SSAK_CTC_FEW", 2 * B <= 2 * 148 ? 1 : 0) != 0;
+    int wtarget = few ? 8 : 4;
     wtarget = env_int("SSAK_CTC_WARPS", wtarget);
     int K = env_int("SSAK_CTC_K", 0);
     if (K == 0) {
@@ -114,25 +114,29 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->P_pad = 32 * K * (int)W;
     c->row_elems = 2 * c->P_pad + 8;
     // gradient warps: few when many CTAs share an SM (they only cost occupancy), more when one CTA owns it
-    c->G = few ? (V <= 512 ? 4 : 8) : (V <= 64 ? 1 : (V <= 512 ? 2 : 4));
+    c->G = few ? (V <= 512 ? 4 : 8) : (V <= 512 ? 2 : 4);
     if (K == 8 && c->W + 2 + c->G > 22) c->G = 22 - 2 - c->W;
     // (set below once the chunk is known: G <= chunk, every gradient warp owns a frame of every chunk)
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
     if (c->G > c->chunk) c->G = c->chunk;            // no idle gradient warp may run ahead of the ring
-    int stages = ((few ? 64 : 36) * 1024) / (c->chunk * c->slot_bytes);
+    // >= 3 stages: two chunks of look-ahead are needed to cover the HBM latency of the bulk copies
+    int stages = (64 * 1024) / (c->chunk * c->slot_bytes);
     c->stages = stages > 4 ? 4 : stages;
     if (c->stages < 2) return false;                 // V too large for the emission ring
     const int row_bytes = c->row_elems * 4;
-    const int budget = few ? 96 * 1024 : 24 * 1024;
-    int oc = 8;
-    while (oc > 1 && oc * 3 * row_bytes > budget) oc >>= 1;
-    c->or_chunk = oc;
-    c->or_stages = 3;
-    if (oc == 1) {
-        int st = budget / row_bytes;
-        c->or_stages = st < 2 ? 2 : (st > 8 ? 8 : st);
-    }
+    // other-direction rows (backward): chunks of 2 rows, as many stages as the budget allows (>= 8 rows
+    // of look-ahead when they fit: one row is consumed per frame and a bulk copy takes ~1-2 us)
+    const int budget = few ? 96 * 1024 : 40 * 1024;
+    c->or_chunk = 2;
+    int ost = budget / (2 * row_bytes);
+    if (ost < 2) { c->or_chunk = 1; ost = budget / row_bytes; }
+    c->or_stages = ost < 2 ? 2 : (ost > 8 ? 8 : ost);
+    c->G = env_int("SSAK_CTC_G", c->G);
+    if (c->G > c->chunk) c->G = c->chunk;
+    c->or_chunk = env_int("SSAK_CTC_OR_CHUNK", c->or_chunk);
+    c->or_stages = env_int("SSAK_CTC_OR_STAGES", c->or_stages);
+    if (c->or_stages > 8 || c->or_stages < 2 || c->or_chunk < 1) return false;
     return true;
 }
 
@@ -143,7 +147,7 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
     size_t o = kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
     if (grad)
         o += (size_t)c.or_stages * c.or_chunk * c.row_elems * 4 + 2 * (size_t)c.chunk * (c.P_pad + 8) * sizeof(float) +
-             2 * (size_t)c.chunk * sizeof(unsigned) + ((size_t)V + 1) * sizeof(int) + (size_t)V * sizeof(int) +
+             2 * (size_t)c.chunk * sizeof(unsigned) + ((size_t)V + 2) * sizeof(int) + (size_t)V * sizeof(int) +
              (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
     return align_up(o, 16);
 }
@@ -202,7 +206,7 @@ ctc_lattice_kernel(const CtcParams p) {
     float *wlab = reinterpret_cast<float *>(or_slots + (size_t)c.or_stages * c.or_chunk * row_bytes);  // [2*CH][WL]
     unsigned *blank_acc = reinterpret_cast<unsigned *>(wlab + 2 * CH * WL);                            // [2*CH]
     int *occ_start = reinterpret_cast<int *>(blank_acc + 2 * CH);
-    int *cursor = occ_start + (V + 1);
+    int *cursor = occ_start + (V + 2);  // counting-sort cursors, then the list of columns that carry posterior mass
     int *occ_pos = cursor + V;
 
     // ---- gradient prologue: trivial outcomes ----
@@ -327,6 +331,17 @@ ctc_lattice_kernel(const CtcParams p) {
                 }
                 __syncwarp();
             }
+            // compact list of the columns with posterior mass (labels of this utterance + blank), ascending
+            int np = 0;
+            for (int c0 = 0; c0 < V; c0 += 32) {
+                const int cc = c0 + lane;
+                const bool has = cc < V && (occ_start[cc + 1] > occ_start[cc] || cc == p.blank);
+                const unsigned bal = __ballot_sync(FULL, has);
+                __syncwarp();
+                if (has) cursor[np + __popc(bal & ((1u << lane) - 1u))] = cc;
+                np += __popc(bal);
+            }
+            if (lane == 0) occ_start[V + 1] = np;
         }
     }
 
@@ -576,14 +591,12 @@ ctc_lattice_kernel(const CtcParams p) {
         const bool vec = a15_0 == 0 && a15_step == 0 && (V & 3) == 0 && ((p.gst | p.gsb) & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0;
         const int ncols = vec ? V >> 2 : V;  // work items: groups of 4 columns, or columns
-        // bit j of `present`: my j-th item (lane + 32 j) has label states (or is the blank column)
+        // scalar path: bit j of `present` = my j-th column (lane + 32 j) carries posterior mass
         unsigned present = 0;
-        {
+        if (!vec) {
             int j = 0;
-            for (int it = lane; it < ncols; it += 32, ++j) {
-                const int c0 = vec ? 4 * it : it, c1 = vec ? c0 + 4 : c0 + 1;
-                if (j < 32 && (occ_start[c1] > occ_start[c0] || (p.blank >= c0 && p.blank < c1))) present |= 1u << j;
-            }
+            for (int cc = lane; cc < V; cc += 32, ++j)
+                if (j < 32 && (occ_start[cc + 1] > occ_start[cc] || cc == p.blank)) present |= 1u << j;
         }
         auto label_mass = [&](int cc, const float *w, int slot) {  // posterior mass of column cc at this frame
             float rsum = 0.f;
@@ -607,20 +620,21 @@ ctc_lattice_kernel(const CtcParams p) {
                 const unsigned char *rowb = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
                 float *grow = grow_chunk + (int64_t)f * grow_step;
                 if (vec) {
+                    // dense pass: exp(lp) for every column, 128-bit loads and stores, no divergence
                     const float4 *row4 = reinterpret_cast<const float4 *>(rowb);
                     float4 *g4 = reinterpret_cast<float4 *>(grow);
-                    int j = 0;
-                    for (int it = lane; it < ncols; it += 32, ++j) {
+                    for (int it = lane; it < ncols; it += 32) {
                         const float4 x = row4[it];
-                        float4 v = make_float4(ex2_approx(x.x * kLog2e), ex2_approx(x.y * kLog2e),
-                                               ex2_approx(x.z * kLog2e), ex2_approx(x.w * kLog2e));
-                        if (j >= 32 || ((present >> j) & 1u)) {
-                            v.x -= label_mass(4 * it, w, slot);
-                            v.y -= label_mass(4 * it + 1, w, slot);
-                            v.z -= label_mass(4 * it + 2, w, slot);
-                            v.w -= label_mass(4 * it + 3, w, slot);
-                        }
-                        g4[it] = make_float4(v.x * gs, v.y * gs, v.z * gs, v.w * gs);
+                        g4[it] = make_float4(ex2_approx(x.x * kLog2e) * gs, ex2_approx(x.y * kLog2e) * gs,
+                                             ex2_approx(x.z * kLog2e) * gs, ex2_approx(x.w * kLog2e) * gs);
+                    }
+                    __syncwarp();  // orders the dense stores before the overwrites below (same warp)
+                    // sparse pass: the few columns that carry posterior mass, one per lane
+                    const float *row = reinterpret_cast<const float *>(rowb);
+                    const int np = occ_start[V + 1];
+                    for (int i = lane; i < np; i += 32) {
+                        const int cc = cursor[i];
+                        grow[cc] = (ex2_approx(row[cc] * kLog2e) - label_mass(cc, w, slot)) * gs;
                     }
                 } else {
                     const float *row = reinterpret_cast<const float *>(rowb);

@@ -166,3 +166,13 @@ def test_align_full_size_properties():
         assert ((sc[b, :Lb] > 0) & (sc[b, :Lb] <= 1.0 + 1e-6)).all()
     idx = [0, 17, 63]
     _check_batch(em[idx], toks[idx], el[idx], tl[idx], res=None, tag="C5 spot")
+
+
+def test_align_long_audio_cluster_sized_labels():
+    """Config C3 shape at reduced duration: L ~ 8000 tokens (16 states per lane x 16 warps) and L ~ 3000
+    (8 per lane), bit-exact against the oracle.  The full 10-minute T=30000 case is timed by tools/run_align.py."""
+    from ssak_b200.synth import align_batch
+    em, toks, el, tl = align_batch(2, 8600, 50, 7700, 8000, 51, Tmin=8400)
+    assert _check_batch(em, toks, el, tl, tag="L8000") == 2
+    em, toks, el, tl = align_batch(2, 4000, 50, 2800, 3100, 52, Tmin=3800, kind="tie")
+    _check_batch(em, toks, el, tl, tag="L3000 tie")

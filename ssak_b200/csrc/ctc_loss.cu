@@ -128,10 +128,12 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     // other-direction rows (backward): chunks of 2 rows, as many stages as the budget allows (>= 8 rows
     // of look-ahead when they fit: one row is consumed per frame and a bulk copy takes ~1-2 us)
     const int budget = few ? 96 * 1024 : 40 * 1024;
-    c->or_chunk = 2;
-    int ost = budget / (2 * row_bytes);
-    if (ost < 2) { c->or_chunk = 1; ost = budget / row_bytes; }
-    c->or_stages = ost < 2 ? 2 : (ost > 8 ? 8 : ost);
+    // few CTAs (one per SM): big chunks (fewer barrier probes on the critical path); many CTAs: 2-row chunks
+    int oc = few ? 8 : 2;
+    while (oc > 1 && oc * 3 * row_bytes > budget) oc >>= 1;
+    int ost = budget / (oc * row_bytes);
+    c->or_chunk = oc;
+    c->or_stages = ost < 2 ? 2 : (ost > (few ? 3 : 8) ? (few ? 3 : 8) : ost);
     c->G = env_int("SSAK_CTC_G", c->G);
     if (c->G > c->chunk) c->G = c->chunk;
     c->or_chunk = env_int("SSAK_CTC_OR_CHUNK", c->or_chunk);

@@ -38,7 +38,8 @@ struct AlignParams {
     const float *col0;   // caller's column 0 (first_as_garbage) or nullptr
     float *col0_eff;     // [B][Tmax] column 0 of trellis rows 1..T_b incl. the +inf sentinel (workspace)
     uint32_t *bp;        // [B][Tmax][W][2K] decision bits: per warp K words "changed>stayed", K words "<"
-    unsigned char *rec;  // [B][Tmax] decision flags of the frames on the path
+    uint32_t *rec;       // [B][Tmax] (token index << 2) | decision flags of the frames on the path
+    float *prob;         // [B][Tmax] per-frame probability of the path (workspace)
     int32_t *starts, *ends, *t_start, *status;
     double *scores;
     float *dump;
@@ -301,8 +302,12 @@ __global__ void __launch_bounds__(K == 16 ? 544 : 1024, 1) align_forward_kernel(
     if (ownsL) p.t_start[b] = best_t;
 }
 
-__global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams p) {
-    __shared__ int s_status;
+// Back-trace (:79-123) + merge_repeats (:141-157).  Warp 0 walks the decision bits from (t_start, L): each
+// lane fetches the 64-state window of one frame, 32 frames per round trip, and the fetch for the next 32
+// frames is issued before the current 32 are walked (the window [j-63, j] covers wherever the walk ends).
+// Then the whole CTA computes the per-frame probabilities (:106-112) in parallel and the per-token means.
+__global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams p) {
+    __shared__ int s_status, s_first;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     int Tb = p.em_len[b];
@@ -311,7 +316,8 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int NW = p.cfg.NW, KK = p.cfg.K;
     const uint32_t *bp_b = p.bp + (int64_t)b * p.Tmax * 2 * NW;
-    unsigned char *rec = p.rec + (int64_t)b * p.Tmax;
+    uint32_t *rec = p.rec + (int64_t)b * p.Tmax;   // (token index << 2) | (changed>stayed) | (changed<stayed) << 1
+    float *prob = p.prob + (int64_t)b * p.Tmax;
     int32_t *st_b = p.starts + (int64_t)b * p.Lmax;
     int32_t *en_b = p.ends + (int64_t)b * p.Lmax;
     double *sc_b = p.scores + (int64_t)b * p.Lmax;
@@ -320,24 +326,34 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
     if (warp == 0) {
         int t = t_start, j = L;
         bool done = false;
-        while (t > 0 && !done) {
-            // lane i holds the 32-state window [base, base+32) of trellis row t-i
-            const int base = max(j - 31, 0);
-            const int i0 = base >> 5, sh = base & 31;
-            // 32-state group g lives at word (g / K) * 2K + (g % K) ("changed > stayed"), +K ("<")
-            const int w0 = (i0 / KK) * 2 * KK + (i0 % KK), w1 = ((i0 + 1) / KK) * 2 * KK + ((i0 + 1) % KK);
-            uint32_t g0 = 0, g1 = 0, l0 = 0, l1 = 0;
-            const int rr = t - lane;
-            if (rr >= 1) {
-                const uint32_t *rowp = bp_b + (int64_t)(rr - 1) * 2 * NW;
-                g0 = __ldg(rowp + w0);
-                l0 = __ldg(rowp + w0 + KK);
-                if (i0 + 1 < NW) {
-                    g1 = __ldg(rowp + w1);
-                    l1 = __ldg(rowp + w1 + KK);
+        uint32_t cg[3], cl[3], ng[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
+        int cgrp = 0, ngrp = 0;
+        auto fetch = [&](int tt, int jj, uint32_t *g, uint32_t *l, int &grp0) {
+            // words of trellis row tt-lane covering the states [jj-63, jj]; 32-state group g lives at
+            // word (g / K) * 2K + (g % K) ("changed > stayed") and + K ("changed < stayed")
+            grp0 = max(jj - 63, 0) >> 5;
+            const int rr = tt - lane;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                g[q] = 0;
+                l[q] = 0;
+                const int grp = grp0 + q;
+                if (rr >= 1 && grp < NW) {
+                    const uint32_t *w = bp_b + (int64_t)(rr - 1) * 2 * NW + (grp / KK) * 2 * KK + (grp % KK);
+                    g[q] = __ldg(w);
+                    l[q] = __ldg(w + KK);
                 }
             }
-            const uint32_t wg = __funnelshift_r(g0, g1, sh), wl = __funnelshift_r(l0, l1, sh);
+        };
+        if (t > 0) fetch(t, j, cg, cl, cgrp);
+        while (t > 0 && !done) {
+            if (t > 32) fetch(t - 32, j, ng, nl, ngrp);  // next 32 frames, issued before the walk
+            const int base = max(j - 31, 0);
+            const int off = base - (cgrp << 5);          // 0 <= off < 64
+            const int sh = off & 31;
+            const bool hi = off >= 32;
+            const uint32_t wg = __funnelshift_r(hi ? cg[1] : cg[0], hi ? cg[2] : cg[1], sh);
+            const uint32_t wl = __funnelshift_r(hi ? cl[1] : cl[0], hi ? cl[2] : cl[1], sh);
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
                 if (t - i < 1) break;
@@ -345,14 +361,17 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
                 const int bit = j - base;
                 const uint32_t gt = (gi >> bit) & 1u, lt = (li >> bit) & 1u;
                 const int frame = t - i - 1;
-                if (lane == 0) rec[frame] = (unsigned char)(gt | (lt << 1));
+                if (lane == 0) rec[frame] = ((uint32_t)(j - 1) << 2) | gt | (lt << 1);
                 if (gt) {  // :117 changed > stayed -> previous token
                     if (lane == 0) st_b[j - 1] = frame;
                     --j;
-                    if (j == 0) { done = true; break; }  // :119-120
+                    if (j == 0) { done = true; s_first = frame; break; }  // :119-120
                 }
             }
             t -= 32;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { cg[q] = ng[q]; cl[q] = nl[q]; }
+            cgrp = ngrp;
         }
         if (lane == 0) {
             s_status = done ? 0 : 1;  // :121-122 "Failed to align"
@@ -361,18 +380,35 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
     }
     __syncthreads();
     const bool ok = s_status == 0;
+    const int first = ok ? s_first : 0, last = ok ? t_start : 0;   // path frames: [first, last)
     int32_t *ptok = p.path_token ? p.path_token + (int64_t)b * p.Tmax : nullptr;
     float *pprob = p.path_prob ? p.path_prob + (int64_t)b * p.Tmax : nullptr;
-    if (ptok || pprob) {  // frames off the path (before the first token, after t_start, failures)
-        const int lo = ok ? st_b[0] : 0, hi = ok ? t_start : 0;
-        for (int f = tid; f < (int)p.Tmax; f += blockDim.x)
-            if (f < lo || f >= hi) {
-                if (ptok) ptok[f] = -1;
-                if (pprob) pprob[f] = 0.f;
-            }
-    }
     const float *em_b = p.em + (int64_t)b * p.sb;
     const int32_t *tk = p.tokens + (int64_t)b * p.tok_stride;
+    // per-frame probability of the path (:106-112), one thread per frame
+    for (int f = tid; f < (int)p.Tmax; f += blockDim.x) {
+        float pr = 0.f;
+        int ti = -1;
+        if (f >= first && f < last) {
+            const uint32_t rc = rec[f];
+            ti = (int)(rc >> 2);
+            int tkn = tk[ti];
+            tkn = tkn < 0 ? 0 : (tkn >= p.V ? p.V - 1 : tkn);
+            const bool gt = rc & 1u, lt = rc & 2u;
+            const float *r0 = em_b + (int64_t)f * p.st;
+            if (lt && f + 1 < Tb) {  // hard-coded vocabulary index 0, next frame's token (:108)
+                const float x = r0[0], y = r0[p.st + tkn];
+                pr = expf(fmaxf(x, y));
+            } else {
+                pr = expf(r0[gt ? tkn : 0]);  // :112
+            }
+            prob[f] = pr;
+        }
+        if (ptok) ptok[f] = ti;
+        if (pprob) pprob[f] = pr;
+    }
+    __syncthreads();
+    // merge_repeats (:141-157): span of token i and the mean of its per-frame probabilities
     for (int i = tid; i < p.Lmax; i += blockDim.x) {
         if (!ok || i >= L) {
             st_b[i] = -1;
@@ -380,27 +416,10 @@ __global__ void __launch_bounds__(128) align_backtrace_kernel(const AlignParams 
             sc_b[i] = 0.0;
             continue;
         }
-        // merge_repeats (:141-157): span of token i and the mean of its per-frame scores
         const int s = st_b[i];
         const int e = i + 1 < L ? st_b[i + 1] : t_start;
-        int tkn = tk[i];
-        tkn = tkn < 0 ? 0 : (tkn >= p.V ? p.V - 1 : tkn);
         double sum = 0.0;
-        for (int f = s; f < e; ++f) {
-            const unsigned fl = rec[f];
-            const bool gt = fl & 1u, lt = fl & 2u;
-            const float *r0 = em_b + (int64_t)f * p.st;
-            float pr;
-            if (lt && f + 1 < Tb) {  // :106-108 (hard-coded vocabulary index 0, next frame's token)
-                const float x = r0[0], y = r0[p.st + tkn];
-                pr = expf(fmaxf(x, y));
-            } else {
-                pr = expf(r0[gt ? tkn : 0]);  // :112
-            }
-            sum += (double)pr;
-            if (ptok) ptok[f] = i;
-            if (pprob) pprob[f] = pr;
-        }
+        for (int f = s; f < e; ++f) sum += (double)prob[f];
         en_b[i] = e;
         sc_b[i] = sum / (double)(e - s);
     }
@@ -418,7 +437,7 @@ extern "C" size_t ssak_align_workspace_bytes(int64_t B, int64_t Tmax, int64_t Lm
     AlignCfg c;
     if (B <= 0 || Tmax < 0 || Lmax < 0 || !choose_align_cfg(Lmax, B, 64, &c)) return 0;
     return align_up((size_t)B * (size_t)Tmax * 2 * c.NW * sizeof(uint32_t), 256) +
-           align_up((size_t)B * (size_t)Tmax, 256) + align_up((size_t)B * (size_t)Tmax * sizeof(float), 256) + 256;
+           3 * align_up((size_t)B * (size_t)Tmax * sizeof(float), 256) + 256;
 }
 
 extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax, int64_t V,
@@ -449,8 +468,10 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     char *ws = reinterpret_cast<char *>(workspace);
     p.bp = reinterpret_cast<uint32_t *>(ws);
     const size_t bp_bytes = align_up((size_t)B * (size_t)Tmax * 2 * p.cfg.NW * sizeof(uint32_t), 256);
-    p.rec = reinterpret_cast<unsigned char *>(ws + bp_bytes);
-    p.col0_eff = reinterpret_cast<float *>(ws + bp_bytes + align_up((size_t)B * (size_t)Tmax, 256));
+    const size_t bt_bytes = align_up((size_t)B * (size_t)Tmax * sizeof(float), 256);
+    p.rec = reinterpret_cast<uint32_t *>(ws + bp_bytes);
+    p.prob = reinterpret_cast<float *>(ws + bp_bytes + bt_bytes);
+    p.col0_eff = reinterpret_cast<float *>(ws + bp_bytes + 2 * bt_bytes);
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     p.starts = starts; p.ends = ends; p.scores = scores; p.t_start = t_start; p.status = status;
     p.dump = trellis_dump; p.path_token = path_token; p.path_prob = path_prob;
@@ -483,6 +504,6 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
 #undef SSAK_LAUNCH2
     rc = check_launch();
     if (rc != SSAK_OK) return rc;
-    align_backtrace_kernel<<<(unsigned)B, 128, 0, s>>>(p);
+    align_backtrace_kernel<<<(unsigned)B, 256, 0, s>>>(p);
     return check_launch();
 }

@@ -6,9 +6,13 @@
 
 #include "common.cuh"
 
+constexpr int kMaxSub = 4;  // utterance sub-batches pipelined on separate streams (copy/compute overlap)
+
 struct ssak_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t sub[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
     char *scratch = nullptr;
     size_t scratch_bytes = 0;
 };
@@ -63,6 +67,12 @@ extern "C" int ssak_context_create(int device, ssak_context_t **out) {
         delete ctx;
         return cuda_fail(e);
     }
+    for (int i = 0; i < kMaxSub; ++i) {
+        e = cudaStreamCreateWithFlags(&ctx->sub[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) { ssak_context_destroy(ctx); return cuda_fail(e); }
+    }
+    e = cudaEventCreateWithFlags(&ctx->ready, cudaEventDisableTiming);
+    if (e != cudaSuccess) { ssak_context_destroy(ctx); return cuda_fail(e); }
     *out = ctx;
     return SSAK_OK;
 }
@@ -74,6 +84,12 @@ extern "C" void ssak_context_destroy(ssak_context_t *ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    for (int i = 0; i < kMaxSub; ++i)
+        if (ctx->sub[i]) {
+            cudaStreamSynchronize(ctx->sub[i]);
+            cudaStreamDestroy(ctx->sub[i]);
+        }
+    if (ctx->ready) cudaEventDestroy(ctx->ready);
     if (ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
 }
@@ -88,55 +104,81 @@ extern "C" int ssak_ctc_loss_host(ssak_context_t *ctx, const float *log_probs_ho
         !nll_host || T < 0 || B <= 0 || V <= 0 || Smax < 0)
         return SSAK_ERR_INVALID_ARGUMENT;
     SSAK_CUDA(cudaSetDevice(ctx->device));
-    int64_t Lmax = 0;
-    for (int64_t b = 0; b < B; ++b) {
+    for (int64_t b = 0; b < B; ++b)
         if (input_lengths_host[b] < 0 || input_lengths_host[b] > T || target_lengths_host[b] < 0 ||
             target_lengths_host[b] > Smax)
             return SSAK_ERR_INVALID_ARGUMENT;
-        Lmax = std::max<int64_t>(Lmax, target_lengths_host[b]);
-    }
     const bool want_grad = grad_host != nullptr;
+    // Utterance sub-batches on separate streams: the host->device copy of sub-batch i+1, the kernels of
+    // sub-batch i and the device->host copy of sub-batch i-1 overlap (utterances are independent).
+    const int NS = B >= 32 ? kMaxSub : (B >= 8 ? 2 : 1);
+    int64_t b0s[kMaxSub + 1], lmaxs[kMaxSub];
+    size_t wsb[kMaxSub], ws_total = 0;
+    for (int i = 0; i <= NS; ++i) b0s[i] = B * i / NS;
+    for (int i = 0; i < NS; ++i) {
+        int64_t lm = 0;
+        for (int64_t b = b0s[i]; b < b0s[i + 1]; ++b) lm = std::max<int64_t>(lm, target_lengths_host[b]);
+        lmaxs[i] = lm;
+        wsb[i] = ssak_ctc_loss_workspace_bytes(T, b0s[i + 1] - b0s[i], lm, want_grad);
+        if (wsb[i] == 0) return SSAK_ERR_UNSUPPORTED;
+        ws_total += align_up(wsb[i], 256);
+    }
     const size_t n_lp = (size_t)T * B * V;
-    const size_t ws_bytes = ssak_ctc_loss_workspace_bytes(T, B, Lmax, want_grad);
-    if (ws_bytes == 0) return SSAK_ERR_UNSUPPORTED;
     Arena a;
     const size_t o_lp = a.take(n_lp * 4), o_grad = a.take(want_grad ? n_lp * 4 : 0),
                  o_tg = a.take((size_t)B * std::max<int64_t>(Smax, 1) * 4), o_off = a.take((size_t)B * 8),
                  o_il = a.take((size_t)B * 4), o_tl = a.take((size_t)B * 4), o_nll = a.take((size_t)B * 4),
-                 o_go = a.take((size_t)B * 4), o_ws = a.take(ws_bytes);
+                 o_go = a.take((size_t)B * 4), o_ws = a.take(ws_total);
     int rc = ensure_scratch(ctx, a.off);
     if (rc != SSAK_OK) return rc;
     char *d = ctx->scratch;
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s0 = ctx->stream;
     std::vector<int64_t> offs((size_t)B);
-    for (int64_t b = 0; b < B; ++b) offs[(size_t)b] = b * Smax;
     std::vector<float> ones;
     if (want_grad && !grad_out_host) ones.assign((size_t)B, 1.0f);
-    SSAK_CUDA(cudaMemcpyAsync(d + o_lp, log_probs_host, n_lp * 4, cudaMemcpyHostToDevice, s));
+    // small arrays first, on the context stream
     if (Smax > 0)
-        SSAK_CUDA(cudaMemcpyAsync(d + o_tg, targets_host, (size_t)B * Smax * 4, cudaMemcpyHostToDevice, s));
-    SSAK_CUDA(cudaMemcpyAsync(d + o_off, offs.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
-    SSAK_CUDA(cudaMemcpyAsync(d + o_il, input_lengths_host, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-    SSAK_CUDA(cudaMemcpyAsync(d + o_tl, target_lengths_host, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+        SSAK_CUDA(cudaMemcpyAsync(d + o_tg, targets_host, (size_t)B * Smax * 4, cudaMemcpyHostToDevice, s0));
+    SSAK_CUDA(cudaMemcpyAsync(d + o_il, input_lengths_host, (size_t)B * 4, cudaMemcpyHostToDevice, s0));
+    SSAK_CUDA(cudaMemcpyAsync(d + o_tl, target_lengths_host, (size_t)B * 4, cudaMemcpyHostToDevice, s0));
     if (want_grad)
         SSAK_CUDA(cudaMemcpyAsync(d + o_go, grad_out_host ? grad_out_host : ones.data(), (size_t)B * 4,
-                                  cudaMemcpyHostToDevice, s));
-    rc = ssak_ctc_loss_forward((const float *)(d + o_lp), T, B, V, B * V, V, (const int32_t *)(d + o_tg),
-                               (const int64_t *)(d + o_off), (const int32_t *)(d + o_il),
-                               (const int32_t *)(d + o_tl), Lmax, blank, want_grad ? 1 : 0,
-                               (float *)(d + o_nll), d + o_ws, ws_bytes, s);
-    if (rc != SSAK_OK) return rc;
-    if (want_grad) {
-        rc = ssak_ctc_loss_backward((const float *)(d + o_go), (const float *)(d + o_lp), T, B, V, B * V, V,
-                                    (const int32_t *)(d + o_tg), (const int64_t *)(d + o_off),
-                                    (const int32_t *)(d + o_il), (const int32_t *)(d + o_tl), Lmax, blank,
-                                    zero_infinity, (const float *)(d + o_nll), (float *)(d + o_grad), B * V,
-                                    V, d + o_ws, ws_bytes, s);
+                                  cudaMemcpyHostToDevice, s0));
+    // target offsets are relative to each sub-batch's first row of the padded target matrix
+    for (int i = 0; i < NS; ++i)
+        for (int64_t b = b0s[i]; b < b0s[i + 1]; ++b) offs[(size_t)b] = (b - b0s[i]) * Smax;
+    SSAK_CUDA(cudaMemcpyAsync(d + o_off, offs.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s0));
+    SSAK_CUDA(cudaEventRecord(ctx->ready, s0));
+    const size_t pitch = (size_t)B * V * 4;
+    size_t ws_off = o_ws;
+    for (int i = 0; i < NS; ++i) {
+        cudaStream_t s = ctx->sub[i];
+        const int64_t b0 = b0s[i], nb = b0s[i + 1] - b0s[i];
+        SSAK_CUDA(cudaStreamWaitEvent(s, ctx->ready, 0));
+        // [T, nb, V] slice of the [T, B, V] host tensor: T rows of nb*V floats
+        SSAK_CUDA(cudaMemcpy2DAsync(d + o_lp + (size_t)b0 * V * 4, pitch, log_probs_host + b0 * V, pitch,
+                                    (size_t)nb * V * 4, (size_t)T, cudaMemcpyHostToDevice, s));
+        const float *lp = (const float *)(d + o_lp) + b0 * V;
+        rc = ssak_ctc_loss_forward(lp, T, nb, V, B * V, V, (const int32_t *)(d + o_tg) + b0 * std::max<int64_t>(Smax, 1),
+                                   (const int64_t *)(d + o_off) + b0, (const int32_t *)(d + o_il) + b0,
+                                   (const int32_t *)(d + o_tl) + b0, lmaxs[i], blank, want_grad ? 1 : 0,
+                                   (float *)(d + o_nll) + b0, d + ws_off, wsb[i], s);
         if (rc != SSAK_OK) return rc;
-        SSAK_CUDA(cudaMemcpyAsync(grad_host, d + o_grad, n_lp * 4, cudaMemcpyDeviceToHost, s));
+        if (want_grad) {
+            float *g = (float *)(d + o_grad) + b0 * V;
+            rc = ssak_ctc_loss_backward((const float *)(d + o_go) + b0, lp, T, nb, V, B * V, V,
+                                        (const int32_t *)(d + o_tg) + b0 * std::max<int64_t>(Smax, 1),
+                                        (const int64_t *)(d + o_off) + b0, (const int32_t *)(d + o_il) + b0,
+                                        (const int32_t *)(d + o_tl) + b0, lmaxs[i], blank, zero_infinity,
+                                        (const float *)(d + o_nll) + b0, g, B * V, V, d + ws_off, wsb[i], s);
+            if (rc != SSAK_OK) return rc;
+            SSAK_CUDA(cudaMemcpy2DAsync(grad_host + b0 * V, pitch, g, pitch, (size_t)nb * V * 4, (size_t)T,
+                                        cudaMemcpyDeviceToHost, s));
+        }
+        SSAK_CUDA(cudaMemcpyAsync(nll_host + b0, (float *)(d + o_nll) + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+        ws_off += align_up(wsb[i], 256);
     }
-    SSAK_CUDA(cudaMemcpyAsync(nll_host, d + o_nll, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    SSAK_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < NS; ++i) SSAK_CUDA(cudaStreamSynchronize(ctx->sub[i]));
     if (zero_infinity)
         for (int64_t b = 0; b < B; ++b)
             if (!(nll_host[b] < 3.0e38f)) nll_host[b] = 0.f;

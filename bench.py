@@ -18,7 +18,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import torch
@@ -44,35 +43,46 @@ def make_batch(name, seed):
     return lp, tg, il, tl, cells
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under the benchmark's load (one background
+    `nvidia-smi -lms 20` process, as in B200_PROFILING.md; started before the timed region, stopped after)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.proc, self.samples = index, None, []
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6 and f[0].replace(".", "").isdigit():
+                self.samples.append(f)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        sm = sorted(float(s[0]) for s in self.samples)
+        busy = [x for x in sm if x > 0.5 * sm[-1]] or sm   # samples taken while the kernels were running
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
 
 
 def peaks():
@@ -222,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t_e2e = time.perf_counter() - t0
     if rank == 0:
-        sampler.stop_flag.set()
+        sampler.stop()
     # parity gate on the timed configuration: the host-ABI result equals the torch-facing one
     _, g = step()
     torch.cuda.synchronize()

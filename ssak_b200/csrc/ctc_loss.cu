@@ -359,7 +359,7 @@ ctc_lattice_kernel(const CtcParams p) {
             const int pp = pbase + k * 32;
             if (GRAD) {
                 ab[k] = fin[pp];
-                al[k] = fin[lab_pos + k * 32];
+                al[k] = lab_off[k] == c.slot_bytes - 16 ? kNeg : fin[lab_pos + k * 32];  // states beyond 2L+1
             } else {
                 ab[k] = pp == (dir ? L : 0) ? 0.f : kNeg;
                 al[k] = kNeg;
@@ -452,11 +452,10 @@ ctc_lattice_kernel(const CtcParams p) {
             float *x_out = xchg + 1 + warp;
             // row pointers: pair (pbase + 32k) -> blank at [pbase+32k], label at [P_pad+1-DIR+pbase+32k]
             const bool save = !GRAD && p.rows != nullptr;
-            unsigned char *st_ptr =
-                save ? reinterpret_cast<unsigned char *>(p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase) : nullptr;
-            const int64_t st_step_b = st_step * 4;
             const int lab_delta = P_pad + 1 - DIR;
-            const int lab_delta_b = lab_delta * 4, spare_b = (DIR ? 2 * P_pad : P_pad) * 4, off_b = (2 * P_pad + 2) * 4;
+            float *sb = save ? p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase : nullptr;  // my blank states
+            float *sl = sb + lab_delta;                                                                // my label states
+            double *soff = reinterpret_cast<double *>(sb - pbase + 2 * P_pad + 2);                    // the row's offset
             const unsigned char *or_row = or_slots;
             int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
             unsigned char *wl_bytes = reinterpret_cast<unsigned char *>(wlab);
@@ -465,10 +464,98 @@ ctc_lattice_kernel(const CtcParams p) {
             int remaining = nsteps;
             bool first_chunk = true;
             int chunk_idx = 0;
+            float xfix = 0.f;
+            double base_d = 0.0;
+            int pbuf = 0;
+            // one frame; `n` is the number of frames of the current chunk (a constant CH on the fast path)
+            auto frame = [&](const int f, const int n) {
+                // the bulk copy lands the row (addr & 15) bytes into its slot; raw natural-log values
+                const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
+                const float eb2 = fmaxf(*reinterpret_cast<const float *>(row + blank_off) * kLog2e, kNeg);
+                float el2[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    el2[k] = fmaxf(*reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
+                float xin = x_in[(f & 1) * 18];
+                if (f == 0) xin -= xfix;
+                float r[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float seamv = DIR ? (k == K - 1 ? xin : r[k < K - 1 ? k + 1 : k])
+                                            : (k == 0 ? xin : r[k > 0 ? k - 1 : 0]);
+                    const float carry = sel(seam_m, seamv, r[k]);
+                    const float A = lse2(ab[k], carry);
+                    const float oth = sel(skip_m[k], A, ab[k]);
+                    const float nlab = lse2(al[k], oth) + el2[k];
+                    ab[k] = A + eb2;
+                    al[k] = nlab;
+                }
+                if (is_out) x_out[((f & 1) ^ 1) * 18] = DIR ? al[0] : al[K - 1];
+                if (f == CH - 1) {  // publish the row maximum for the next chunk's re-centring
+                    float mx = kNeg;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
+                    mx = warp_max(mx);
+                    if (lane == 0) wmax[warp] = mx;
+                }
+                if (!GRAD) {
+                    if (save) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            sb[k * 32] = ab[k];
+                            sl[k * 32] = al[k];
+                        }
+                        if (tid == 0) *soff = off_mine;
+                        sb += st_step;
+                        sl += st_step;
+                        soff += st_step / 2;  // row_elems is even
+                    }
+                } else {
+                    // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
+                    if (or_left == 0) {
+                        mbar_wait(&or_full[ostage], (uint32_t)ophase);
+                        or_left = Co;
+                    }
+                    const float *orow = reinterpret_cast<const float *>(or_row) + pbase;
+                    const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
+                    const float bracket = (float)(base_d + ooff);
+                    const float cb = bracket - eb2;
+                    unsigned char *wl = wl_bytes + (pbuf + f) * (WL * 4);
+                    float sbl = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        sbl += ex2_approx(ab[k] + orow[k * 32] + cb);
+                        *reinterpret_cast<float *>(wl + wl_off[k]) =
+                            ex2_approx(al[k] + orow[lab_delta + k * 32] + (bracket - el2[k]));
+                    }
+                    const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
+                    const unsigned tot = __reduce_add_sync(FULL, fx);
+                    __syncwarp();
+                    if (lane == 0) {
+                        atomicAdd(&blank_acc[pbuf + f], tot);
+                        mbar_arrive(&post_full[pbuf + f]);  // release: this warp's posteriors of the frame
+                    }
+                    or_row += row_bytes;
+                    if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
+                    if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
+                        or_left = 0;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&or_empty[ostage]);
+                        if (++ostage == No) { ostage = 0; ophase ^= 1; }
+                    }
+                }
+                if (f == n - 1) {  // release the emission stage before the barrier
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+                }
+                named_bar_sync(1, nbar);
+            };
             while (remaining > 0) {
                 const int n = remaining < CH ? remaining : CH;
                 mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
-                float xfix = 0.f;  // correction for the seam value written before the re-centring
+                xfix = 0.f;  // correction for the seam value written before the re-centring
                 if (!first_chunk) {
                     // re-centre on the row maximum published at the end of the previous chunk
                     float mx = wmax[0];
@@ -481,98 +568,16 @@ ctc_lattice_kernel(const CtcParams p) {
                     }
                 }
                 first_chunk = false;
-                const double base_d = off_mine + nll2;
+                base_d = off_mine + nll2;
                 if (GRAD && chunk_idx >= 2)  // the gradient warps must be done with this posterior buffer
                     mbar_wait(&post_empty[chunk_idx & 1], (uint32_t)(((chunk_idx >> 1) - 1) & 1));
-                const int pbuf = (chunk_idx & 1) * CH;
+                pbuf = (chunk_idx & 1) * CH;
+                if (n == CH) {  // fast path: full chunk, every per-frame test folds at compile time
 #pragma unroll
-                for (int f = 0; f < CH; ++f) {
-                    if (f >= n) break;
-                    // the bulk copy lands the row (addr & 15) bytes into its slot; raw natural-log values
-                    const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
-                    const float eb2 = fmaxf(*reinterpret_cast<const float *>(row + blank_off) * kLog2e, kNeg);
-                    float el2[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        el2[k] = fmaxf(*reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
-                    float xin = x_in[(f & 1) * 18];
-                    if (f == 0) xin -= xfix;
-                    float r[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float seamv = DIR ? (k == K - 1 ? xin : r[k < K - 1 ? k + 1 : k])
-                                                : (k == 0 ? xin : r[k > 0 ? k - 1 : 0]);
-                        const float carry = sel(seam_m, seamv, r[k]);
-                        const float A = lse2(ab[k], carry);
-                        const float oth = sel(skip_m[k], A, ab[k]);
-                        const float nlab = lse2(al[k], oth) + el2[k];
-                        ab[k] = A + eb2;
-                        al[k] = nlab;
-                    }
-                    if (is_out) x_out[((f & 1) ^ 1) * 18] = DIR ? al[0] : al[K - 1];
-                    if (f == CH - 1) {  // publish the row maximum for the next chunk's re-centring
-                        float mx = kNeg;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
-                        mx = warp_max(mx);
-                        if (lane == 0) wmax[warp] = mx;
-                    }
-                    if (!GRAD) {
-                        if (save) {
-                            float *sb = reinterpret_cast<float *>(st_ptr);
-                            float *sl = reinterpret_cast<float *>(st_ptr + lab_delta_b);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                sb[k * 32] = ab[k];
-                                sl[k * 32] = al[k];
-                            }
-                            if (tid == 0) {
-                                *reinterpret_cast<float *>(st_ptr + spare_b) = kNeg;  // the label slot this direction skips
-                                *reinterpret_cast<double *>(st_ptr + off_b) = off_mine;
-                            }
-                            st_ptr += st_step_b;
-                        }
-                    } else {
-                        // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
-                        if (or_left == 0) {
-                            mbar_wait(&or_full[ostage], (uint32_t)ophase);
-                            or_left = Co;
-                        }
-                        const float *orow = reinterpret_cast<const float *>(or_row) + pbase;
-                        const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
-                        const float bracket = (float)(base_d + ooff);
-                        const float cb = bracket - eb2;
-                        unsigned char *wl = wl_bytes + (pbuf + f) * (WL * 4);
-                        float sbl = 0.f;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            sbl += ex2_approx(ab[k] + orow[k * 32] + cb);
-                            *reinterpret_cast<float *>(wl + wl_off[k]) =
-                                ex2_approx(al[k] + orow[lab_delta + k * 32] + (bracket - el2[k]));
-                        }
-                        const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
-                        const unsigned tot = __reduce_add_sync(FULL, fx);
-                        __syncwarp();
-                        if (lane == 0) {
-                            atomicAdd(&blank_acc[pbuf + f], tot);
-                            mbar_arrive(&post_full[pbuf + f]);  // release: this warp's posteriors of the frame
-                        }
-                        or_row += row_bytes;
-                        if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
-                        if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
-                            or_left = 0;
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&or_empty[ostage]);
-                            if (++ostage == No) { ostage = 0; ophase ^= 1; }
-                        }
-                    }
-                    if (f == n - 1) {  // release the emission stage before the barrier
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&em_empty[em_stage]);
-                    }
-                    named_bar_sync(1, nbar);
+                    for (int f = 0; f < CH; ++f) frame(f, CH);
+                } else {
+#pragma unroll 1
+                    for (int f = 0; f < n; ++f) frame(f, n);
                 }
                 remaining -= n;
                 ++chunk_idx;
@@ -671,10 +676,7 @@ ctc_lattice_kernel(const CtcParams p) {
                 fin[k * 32] = ab[k];
                 fin[P_pad + 1 - dir + k * 32] = al[k];
             }
-            if (tid == 0) {
-                fin[dir ? 2 * P_pad : P_pad] = kNeg;
-                *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = off_mine;
-            }
+            if (tid == 0) *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = off_mine;
         }
     } else if (dir == 0) {
         const int nthr = n_consumers * 32, me = compute ? tid : tid - 32 * NPROD;  // every warp but the producers

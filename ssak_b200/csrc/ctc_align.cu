@@ -61,6 +61,7 @@ static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
         while (K < 8 && (P + 32 * K - 1) / (32 * K) > wtarget) K *= 2;
     }
     if (K != 1 && K != 2 && K != 4 && K != 8 && K != 16) return false;
+    if (K < 8 && (P + 32 * K - 1) / (32 * K) > 15) K = 8;     // K <= 4 kernels are built for <= 15 recursion warps
     if (K < 16 && (P + 32 * K - 1) / (32 * K) > 31) K = 16;  // one warp of the CTA is the producer
     const int64_t W = (P + 32 * K - 1) / (32 * K);
     if (W > (K == 16 ? 16 : 31)) return false;  // L <= 8191
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(32) align_col0_kernel(const AlignParams p) {
 
 // Warp roles: [0, W) recursion, W producer (bulk copies of the emission rows, mbarriers only).
 template <int K, int CH>
-__global__ void __launch_bounds__(K == 16 ? 544 : 1024, 1) align_forward_kernel(const AlignParams p) {
+__global__ void __launch_bounds__(K == 16 ? 544 : (K == 8 ? 1024 : 512), 1)
+align_forward_kernel(const AlignParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const AlignCfg &c = p.cfg;
     const int b = blockIdx.x;
@@ -222,55 +224,52 @@ __global__ void __launch_bounds__(K == 16 ? 544 : 1024, 1) align_forward_kernel(
     float *dump_row = p.dump ? p.dump + ((int64_t)b * (p.Tmax + 1) + 1) * (p.Lmax + 1) + jbase : nullptr;
     const unsigned char *em_base = ring.slots, *em_chunk = em_base;
     int em_stage = 0, em_phase = 0, remaining = Tb, t = 0;
-    float c0n[CH];  // column-0 values of the next chunk (thread 0), fetched one chunk ahead
-#pragma unroll
-    for (int f = 0; f < CH; ++f) c0n[f] = (tid == 0 && f < Tb) ? __ldg(c0_ptr + f) : 0.f;
+    // column-0 values: lane f of warp 0 fetches the value of frame f of the NEXT chunk (one chunk ahead);
+    // thread 0 picks its frame's value with a shuffle
+    float c0n = (warp == 0 && lane < CH && lane < Tb) ? __ldg(c0_ptr + lane) : 0.f;
 
     while (remaining > 0) {
         const int n = remaining < CH ? remaining : CH;
-        float c0[CH];
-#pragma unroll
-        for (int f = 0; f < CH; ++f) {
-            c0[f] = c0n[f];
-            c0n[f] = (tid == 0 && t + CH + f < Tb) ? __ldg(c0_ptr + t + CH + f) : 0.f;
-        }
+        const float c0cur = c0n;
+        c0n = (warp == 0 && lane < CH && t + CH + lane < Tb) ? __ldg(c0_ptr + t + CH + lane) : 0.f;
         mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
-#pragma unroll
+        constexpr int kUnroll = K >= 8 ? 1 : CH;  // many states per lane: the frame body is big enough
+#pragma unroll kUnroll
         for (int f = 0; f < CH; ++f) {
             if (f >= n) break;
             const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
             const float eb = *reinterpret_cast<const float *>(row + blank_off);
-            float e[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) e[k] = *reinterpret_cast<const float *>(row + tok_off[k]);
             const float xin = x_in[(f & 1) * 34];
-            float r[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, v[k], (lane + 31) & 31);
-            uint32_t words[2 * K];
+            // states in ascending order; the neighbour of state k is the OLD value of the previous state:
+            // shuffle v[k] before overwriting it, keep the previous shuffle for the warp seam (lane 0).
+            // Decision words are stored as soon as four of a kind are complete (few live registers).
+            float rprev = xin;
+            uint32_t wg[4], wl[4];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const float prev = sel(seam_m, k == 0 ? xin : r[k > 0 ? k - 1 : 0], r[k]);
+                const float rk = __shfl_sync(FULL, v[k], (lane + 31) & 31);
+                const float prev = sel(seam_m, rprev, rk);
+                rprev = rk;
+                const float ek = *reinterpret_cast<const float *>(row + tok_off[k]);
                 const float stayb = v[k] + eb;             // :48
-                const float stayt = v[k] + e[k];           // :49
-                const float chg = prev + e[k];             // :51
+                const float stayt = v[k] + ek;             // :49
+                const float chg = prev + ek;               // :51
                 const float stayed = fmaxf(stayb, stayt);  // what backtrack recomputes (:96-99)
                 float nv = fmaxf(stayed, chg);
-                if (k == 0) nv = sel(zero_m, c0[f], nv);   // column 0 (:37 / :39 / :42), never read back as a decision
+                if (k == 0) nv = sel(zero_m, __shfl_sync(FULL, c0cur, f), nv);  // column 0 (:37 / :39 / :42)
                 v[k] = nv;
-                words[k] = __ballot_sync(FULL, chg > stayed);
-                words[K + k] = __ballot_sync(FULL, chg < stayed);
-            }
-            if (lane == 31) x_out[((f & 1) ^ 1) * 34] = v[K - 1];
-            if (lane == 0) {
+                wg[k & 3] = __ballot_sync(FULL, chg > stayed);
+                wl[k & 3] = __ballot_sync(FULL, chg < stayed);
                 if (K == 1) {
-                    *reinterpret_cast<uint2 *>(bp_ptr) = make_uint2(words[0], words[1]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 2 * K; q += 4)
-                        *reinterpret_cast<uint4 *>(bp_ptr + q) = make_uint4(words[q], words[q + 1], words[q + 2], words[q + 3]);
+                    if (lane == 0) *reinterpret_cast<uint2 *>(bp_ptr) = make_uint2(wg[0], wl[0]);
+                } else if (K == 2) {
+                    if (k == 1 && lane == 0) *reinterpret_cast<uint4 *>(bp_ptr) = make_uint4(wg[0], wg[1], wl[0], wl[1]);
+                } else if ((k & 3) == 3 && lane == 0) {
+                    *reinterpret_cast<uint4 *>(bp_ptr + (k - 3)) = make_uint4(wg[0], wg[1], wg[2], wg[3]);
+                    *reinterpret_cast<uint4 *>(bp_ptr + K + (k - 3)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
                 }
             }
+            if (lane == 31) x_out[((f & 1) ^ 1) * 34] = v[K - 1];
             bp_ptr += 2 * NW;
             if (ownsL) {
                 float vl = v[0];

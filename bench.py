@@ -323,19 +323,34 @@ def extra_numbers(lib, dev, flush):
                                                "align_c2shape": (64, 1500, 50, 200, 400, 1200)}.items():
         try:
             em, toks, el, tl = align_batch(B, T, V, Lmin, Lmax, 5, Tmin=Tmin)
-            em_d = em.to(dev)
+            em_d, toks_d, el_d, tl_d = em.to(dev), toks.to(dev), el.to(dev), tl.to(dev)
             ts = []
-            for i in range(5):
+            for i in range(6):
                 flush.add_(1)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                r = ssak_b200.forced_align(em_d, toks, el, tl)
+                r = ssak_b200.forced_align(em_d, toks_d, el_d, tl_d)
                 b.record()
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b) * 1e-3)
             cells = int((el.long() * (tl.long() + 1)).sum())
             t = statistics.mean(ts[1:])
-            res[name] = {"cells_per_s": cells / t, "ms": t * 1e3, "aligned": int((r.status == 0).sum())}
+            alg_bytes = 4.0 * float(el.sum()) * V + 4.0 * float((el.long() * (tl.long() + 1)).sum()) / 8 * 2
+            res[name] = {"cells_per_s": cells / t, "ms": t * 1e3, "aligned": int((r.status == 0).sum()),
+                         "hbm_frac_algorithmic": alg_bytes / t / 1e9 / peaks()[0]}
+            if name == "align_c5":   # greedy decode of the same emissions: frames/s and fraction of the HBM roofline
+                ts = []
+                for i in range(6):
+                    flush.add_(1)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    ids, out, lens = ssak_b200.greedy_ids(em_d, el_d, 0)
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b) * 1e-3)
+                t = statistics.mean(ts[1:])
+                res["greedy_c5"] = {"frames_per_s": B * T / t, "ms": t * 1e3,
+                                    "hbm_frac": (4.0 * B * T * V + 8.0 * B * T) / t / 1e9 / peaks()[0]}
             del em_d
         except Exception as e:
             res[name] = {"error": repr(e)}

@@ -57,6 +57,10 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline()   # nvidia-smi needs ~1 s to start: wait for its first sample
+            f = [x.strip() for x in first.split(",")]
+            if len(f) >= 6 and f[0].replace(".", "").isdigit():
+                self.samples.append(f)
         except OSError:
             self.proc = None
 
@@ -82,7 +86,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "window": "timed steps + 0.3 s of the same step (soak) + e2e loop"}
 
 
 def peaks():
@@ -210,6 +214,14 @@ def run_ours(args, rank, world, local_rank):
         evs.append((a, b))
     barrier()
     t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    # the timed region lasts a few ms, shorter than nvidia-smi's sampling period: keep the same work running
+    # for ~0.3 s more so that the clock / throttle samples are taken under this load
+    if rank == 0:
+        t_soak = time.perf_counter()
+        while time.perf_counter() - t_soak < 0.3:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
     # ---- end to end through the host-buffer C ABI: pinned host log-probs in, nll + gradient out
     ctx = C.c_void_p()
     assert lib.ssak_context_create(local_rank, C.byref(ctx)) == 0

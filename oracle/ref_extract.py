@@ -17,8 +17,9 @@ import os
 
 REFERENCE_ROOT = os.environ.get("SSAK_REFERENCE_ROOT", "/root/reference")
 _ALIGN_PY = os.path.join(REFERENCE_ROOT, "ssak", "utils", "align_transcriptions.py")
-_WANTED_DEFS = {"get_trellis", "backtrack", "merge_repeats", "merge_words", "Point", "Segment"}
-_WANTED_ASSIGNS = {"USE_MAX", "USE_CHAR_REPEATED"}
+_WANTED_DEFS = {"get_trellis", "backtrack", "merge_repeats", "merge_words", "Point", "Segment",
+                "loose_get_char_index"}
+_WANTED_ASSIGNS = {"USE_MAX", "USE_CHAR_REPEATED", "MISSING_LABELS"}
 _ns = None
 
 
@@ -42,7 +43,13 @@ def namespace() -> dict:
                     isinstance(t, ast.Name) and t.id in _WANTED_ASSIGNS for t in node.targets):
                 keep.append(node)
         mod = ast.Module(body=keep, type_ignores=[])
-        ns = {"torch": torch, "dataclass": dataclass}
+        import unicodedata
+
+        def transliterate(c):  # ssak/utils/text_basic.py:191-196 (one line, needed by loose_get_char_index)
+            return unicodedata.normalize("NFKD", c).encode("ascii", "ignore").decode("ascii")
+
+        ns = {"torch": torch, "dataclass": dataclass, "transliterate": transliterate,
+              "hashmd5": lambda d: str(sorted(d.items()))}
         exec(compile(mod, _ALIGN_PY, "exec"), ns)
         missing = (_WANTED_DEFS | _WANTED_ASSIGNS) - set(ns)
         if missing:

@@ -8,8 +8,9 @@ Public API (same call signatures as the reference's call sites, see each module)
 The compute lives in libssak_b200.so (C ABI: include/ssak_b200.h); there is no CPU fallback.
 """
 from ._lib import LIB_PATH, SsakB200Error, lib  # noqa: F401
-from .align import (AlignResult, Point, Segment, Trellis, backtrack, forced_align, get_trellis,  # noqa: F401
-                    merge_repeats, merge_words, segments_from_result)
+from .align import (AlignResult, Point, Segment, Trellis, backtrack, compute_alignment_from_emission,  # noqa: F401
+                    compute_alignments, forced_align, get_trellis, loose_get_char_index, merge_repeats, merge_words,
+                    segments_from_result)
 from .greedy import argmax_ids, ctc_greedy_decode, greedy_ids, hf_collapse  # noqa: F401
 from .loss import ctc_loss, ctc_neg_log_likelihood, install, sb_ctc_loss, uninstall  # noqa: F401
 

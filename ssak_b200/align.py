@@ -210,3 +210,125 @@ def segments_from_result(res: AlignResult, b: int, transcript: str) -> List[Segm
     n = len(transcript)
     st, en, sc = res.starts[b, :n].tolist(), res.ends[b, :n].tolist(), res.scores[b, :n].tolist()
     return [Segment(transcript[i], st[i], en[i], sc[i]) for i in range(n)]
+
+
+# --------------------------------------------------------------------------------------------------
+# compute_alignment (align_transcriptions.py:294-402) from the emission onwards, one utterance or a batch
+# (SURVEY.md section 8 f-2).  The acoustic-model front end (emission, labels, blank_id) stays with the
+# reference: ssak.infer.general.compute_log_probas / get_model_vocab.
+# --------------------------------------------------------------------------------------------------
+def _ascii_fold(c: str) -> str:
+    """Closest ASCII equivalent of a character (ssak/utils/text_basic.py:191-196)."""
+    import unicodedata
+    return unicodedata.normalize("NFKD", c).encode("ascii", "ignore").decode("ascii")
+
+
+_MISSING_LABELS = set()
+
+
+def loose_get_char_index(dictionary, c, default):
+    """Vocabulary index of character `c` with the reference's fall-backs (:406-423): exact, lower / upper
+    case, ASCII-folded (and its cases); otherwise `default` (warned once per character)."""
+    i = dictionary.get(c)
+    if i is not None:
+        return i
+    folded = _ascii_fold(c)
+    for c2 in (c.lower(), c.upper(), folded, folded.lower(), folded.upper()):
+        i = dictionary.get(c2)
+        if i is not None:
+            return i
+    if c not in _MISSING_LABELS:
+        _MISSING_LABELS.add(c)
+        print("WARNING: cannot find label " + c)
+    return default
+
+
+def _prepare_transcript(transcript, labels, blank_id, add_before_after):
+    if isinstance(transcript, str):
+        chars, words = transcript, None
+    else:
+        assert isinstance(transcript, list), f"Got unexpected transcript (of type {type(transcript)})"
+        for w in transcript:
+            assert isinstance(w, str), f"Got unexpected type {type(w)} (not a string)"
+        chars, words = " ".join(transcript), transcript
+    space_id = labels.index(" ") if " " in labels else blank_id          # :332-334
+    if add_before_after:                                                 # :336-339
+        assert len(add_before_after) == 1 and add_before_after in labels
+        chars = add_before_after + chars + add_before_after
+    dictionary = {c: i for i, c in enumerate(labels)}
+    tokens = [loose_get_char_index(dictionary, c, space_id) for c in chars]
+    return chars, words, [t for t in tokens if t is not None]
+
+
+def _segments_to_words(char_segments, chars, words, add_before_after):
+    """:363-387: strip the sentinel characters, then group characters into words."""
+    if add_before_after:
+        assert char_segments[0].label == add_before_after and char_segments[-1].label == add_before_after
+        char_segments = char_segments[1:-1]
+        chars = chars[1:-1]
+    if words is None:
+        return char_segments, merge_words(char_segments)
+    punct = _punctuation()
+    out, i2 = [], -1
+    for word in words:
+        i1 = i2 + 1
+        i2 = i1 + len(word)
+        segs1 = char_segments[i1:i2]
+        assert "".join(s.label for s in segs1) == word
+        segs = [s for s in segs1 if s.label != " " and s.label not in punct] or segs1   # :381-385
+        out.append(_word_from(segs, word))
+    return char_segments, out
+
+
+def compute_alignments(emissions, transcripts, labels, blank_id, add_before_after=None, first_as_garbage=False):
+    """Batched compute_alignment: B utterances, ONE launch.
+
+    emissions: list of [T_i, V] CUDA tensors (or a padded [B,Tmax,V] tensor with `emission_lengths` given as a
+    second element of a tuple); transcripts: list of str or list[str] (words).  Returns a list with, per
+    utterance, (char_segments, word_segments) or None where the reference raises "Failed to align"."""
+    lengths = None
+    if isinstance(emissions, tuple):
+        emissions, lengths = emissions
+    if isinstance(emissions, (list, tuple)):
+        lengths = [int(e.shape[0]) for e in emissions]
+        Tmax, V = max(lengths), emissions[0].shape[1]
+        em = emissions[0].new_zeros((len(emissions), Tmax, V))
+        for i, e in enumerate(emissions):
+            em[i, : e.shape[0]] = e
+    else:
+        em = emissions
+        if lengths is None:
+            lengths = [em.shape[1]] * em.shape[0]
+    labels = list(labels)[: em.shape[2]]                                 # :341
+    prepared = [_prepare_transcript(t, labels, blank_id, add_before_after) for t in transcripts]
+    Lmax = max((len(p[2]) for p in prepared), default=0)
+    toks = torch.zeros((len(prepared), max(Lmax, 1)), dtype=torch.int32)
+    for i, p in enumerate(prepared):
+        toks[i, : len(p[2])] = torch.tensor(p[2], dtype=torch.int32)
+    res = forced_align(em, toks[:, :Lmax] if Lmax else toks[:, :0], torch.tensor(lengths, dtype=torch.int32),
+                       torch.tensor([len(p[2]) for p in prepared], dtype=torch.int32), blank_id=blank_id,
+                       first_as_garbage=first_as_garbage)
+    status = res.status.cpu().tolist()
+    st, en, sc = res.starts.cpu(), res.ends.cpu(), res.scores.cpu()
+    out = []
+    for i, (chars, words, tk) in enumerate(prepared):
+        if status[i] != 0:
+            out.append(None)
+            continue
+        n = len(tk)
+        segs = [Segment(chars[j], int(st[i, j]), int(en[i, j]), float(sc[i, j])) for j in range(n)]
+        out.append(_segments_to_words(segs, chars, words, add_before_after))
+    return out
+
+
+def compute_alignment_from_emission(emission, transcript, labels, blank_id, add_before_after=None,
+                                    first_as_garbage=False):
+    """compute_alignment (:294-402) after `emission = compute_log_probas(model, audio)`:
+    -> (labels, emission, trellis, char_segments, word_segments); raises the reference's RuntimeError."""
+    out = compute_alignments([emission], [transcript], labels, blank_id, add_before_after, first_as_garbage)[0]
+    if out is None:
+        raise RuntimeError("Failed to align (not enough tokens for the duration?)")
+    char_segments, word_segments = out
+    n_tok = len(char_segments) + (2 if add_before_after else 0)
+    trellis = Trellis(emission.shape[0], n_tok - (2 if add_before_after else 0), None)   # :367 drops the sentinels
+    return list(labels)[: emission.shape[1]], emission, trellis, char_segments, word_segments

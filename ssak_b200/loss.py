@@ -211,16 +211,73 @@ def sb_ctc_loss(log_probs, targets, input_lens, target_lens, blank_index, reduct
 
 
 _torch_ctc_loss = None
+_aten_lib = None
 
 
-def install() -> None:
-    """Route torch.nn.functional.ctc_loss to the sm_100a kernels for CUDA inputs (HF, SpeechBrain
-    and NeMo all end up there).  CPU tensors keep going to torch's own CPU kernel."""
-    global _torch_ctc_loss
+def _aten_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, zero_infinity=False):
+    """aten::_ctc_loss on CUDA -> (neg_log_likelihood[B], opaque workspace handed back as `log_alpha`)."""
+    lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, list(input_lengths), list(target_lengths),
+                                                       blank)
+    L = _lib.lib()
+    T, B, V = lp.shape
+    ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, lmax, 1)
+    if ws_bytes == 0:
+        raise _lib.SsakB200Error(f"ctc_loss: shape not supported (T={T}, B={B}, max target length={lmax})")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lp.device)
+    nll = torch.empty(B, dtype=torch.float32, device=lp.device)
+    with torch.cuda.device(lp.device):
+        rc = L.ssak_ctc_loss_forward(lp.data_ptr(), T, B, V, lp.stride(0), lp.stride(1), tg.data_ptr(),
+                                     tgt_off.data_ptr(), in_len.data_ptr(), tgt_len.data_ptr(), lmax, int(blank), 1,
+                                     nll.data_ptr(), ws.data_ptr(), ws_bytes,
+                                     torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ssak_ctc_loss_forward")
+    return nll, ws
+
+
+def _aten_ctc_loss_backward(grad, log_probs, targets, input_lengths, target_lengths, neg_log_likelihood, log_alpha,
+                            blank, zero_infinity=False):
+    """aten::_ctc_loss_backward on CUDA; `log_alpha` is the workspace `_aten_ctc_loss` returned."""
+    lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, list(input_lengths), list(target_lengths),
+                                                       blank)
+    L = _lib.lib()
+    T, B, V = lp.shape
+    g = grad.to(torch.float32).expand(B).contiguous()
+    out = torch.empty((T, B, V), dtype=torch.float32, device=lp.device)
+    with torch.cuda.device(lp.device):
+        rc = L.ssak_ctc_loss_backward(g.data_ptr(), lp.data_ptr(), T, B, V, lp.stride(0), lp.stride(1), tg.data_ptr(),
+                                      tgt_off.data_ptr(), in_len.data_ptr(), tgt_len.data_ptr(), lmax, int(blank),
+                                      int(zero_infinity), neg_log_likelihood.data_ptr(), out.data_ptr(),
+                                      out.stride(0), out.stride(1), log_alpha.data_ptr(), log_alpha.numel(),
+                                      torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ssak_ctc_loss_backward")
+    return out
+
+
+def install(mode: str = "functional") -> None:
+    """Route CTC-loss calls on CUDA tensors to the sm_100a kernels.
+
+    mode="functional": replace torch.nn.functional.ctc_loss (HF, SpeechBrain and NeMo all end up there); lengths
+        stay on the device, the reduction is fused.  CPU tensors keep going to torch's own CPU kernel.
+    mode="aten": register CUDA implementations of aten::_ctc_loss / aten::_ctc_loss_backward through
+        torch.library, below autograd: every caller (including C++ ones) is covered and ATen's composite
+        ctc_loss keeps applying `reduction` / `zero_infinity`.  Cannot be undone within the process."""
+    global _torch_ctc_loss, _aten_lib
     import torch.nn.functional as F
+    _lib.lib()  # fail now if the library is missing
+    if mode == "aten":
+        if _aten_lib is None:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")   # "Overriding a previously registered kernel"
+                lib_ = torch.library.Library("aten", "IMPL")
+                lib_.impl("_ctc_loss", _aten_ctc_loss, "CUDA")
+                lib_.impl("_ctc_loss_backward", _aten_ctc_loss_backward, "CUDA")
+            _aten_lib = lib_
+        return
+    if mode != "functional":
+        raise ValueError(mode)
     if _torch_ctc_loss is not None:
         return
-    _lib.lib()  # fail now if the library is missing
     _torch_ctc_loss = F.ctc_loss
 
     def patched(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean",

@@ -176,3 +176,50 @@ def test_align_long_audio_cluster_sized_labels():
     assert _check_batch(em, toks, el, tl, tag="L8000") == 2
     em, toks, el, tl = align_batch(2, 4000, 50, 2800, 3100, 52, Tmin=3800, kind="tie")
     _check_batch(em, toks, el, tl, tag="L3000 tie")
+
+
+def test_compute_alignments_batched_front_end():
+    """compute_alignment from the emission onwards (align_transcriptions.py:310-402), batched: character ->
+    token mapping with the loose fall-backs, sentinel character, word regrouping and score aggregation."""
+    import ssak_b200
+    labels = ["<pad>", "<s>", "</s>", "<unk>", " "] + list("abcdefghijklmnopqrstuvwxyz'-") + list("àâéèêëîïôùûç")
+    V, blank = len(labels), 0
+    dic = {c: i for i, c in enumerate(labels)}
+    texts = ["bonjour à tous", ["c'est", "pas", "plus", "mal,", "euh"], "OUI Élise", ["allô", "allô"]]
+    g = torch.Generator().manual_seed(77)
+    ems, toks_all = [], []
+    for tx in texts:
+        chars = tx if isinstance(tx, str) else " ".join(tx)
+        toks = [ssak_b200.loose_get_char_index(dic, c, dic[" "]) for c in chars]
+        T = 3 * len(toks) + int(torch.randint(5, 40, (1,), generator=g))
+        from ssak_b200.synth import planted_emissions
+        ems.append(planted_emissions(T, V, toks, g, blank))
+        toks_all.append(toks)
+    out = ssak_b200.compute_alignments([e.cuda() for e in ems], texts, labels, blank)
+    punct = set('!"#$%&()*+,./:;<=>?@[\\]^_`{|}~')
+    for tx, e, toks, res in zip(texts, ems, toks_all, out):
+        assert res is not None
+        chars = tx if isinstance(tx, str) else " ".join(tx)
+        rc, ss, se, sc, _ = O.align(e.numpy(), toks, blank, False)
+        assert rc == 0
+        char_segments, word_segments = res
+        assert [(s.label, s.start, s.end) for s in char_segments] == [(chars[i], int(ss[i]), int(se[i])) for i in range(len(toks))]
+        np.testing.assert_allclose([s.score for s in char_segments], sc, rtol=1e-6)
+        # words: split on the space segments (:159-173) or by the given word list (:373-387)
+        words = tx.split(" ") if isinstance(tx, str) else tx
+        pos = 0
+        assert [w.label for w in word_segments] == words
+        for w, seg in zip(words, word_segments):
+            idx = list(range(pos, pos + len(w)))
+            keep = [i for i in idx if chars[i] != " " and chars[i] not in punct] if not isinstance(tx, str) else idx
+            keep = keep or idx
+            assert (seg.start, seg.end) == (int(ss[keep[0]]), int(se[keep[-1]]))
+            lens = np.array([se[i] - ss[i] for i in keep], dtype=np.float64)
+            assert abs(seg.score - float((sc[keep] * lens).sum() / lens.sum())) <= 1e-6
+            pos += len(w) + 1
+    # sentinel character on both ends (:336-339, :363-368) and the single-utterance wrapper
+    lab2, em2, trellis, cs, ws = ssak_b200.compute_alignment_from_emission(ems[0].cuda(), texts[0], labels, blank,
+                                                                              add_before_after=" ")
+    assert "".join(s.label for s in cs) == texts[0] and trellis.size(0) == ems[0].shape[0] + 1
+    with pytest.raises(RuntimeError, match="Failed to align"):
+        ssak_b200.compute_alignment_from_emission(ems[0][:5].cuda(), texts[0], labels, blank)

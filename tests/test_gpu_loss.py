@@ -209,3 +209,29 @@ def test_loss_full_size_c2(planted):
     assert rowsum < 2e-3
     for b in (0, 21, 63):
         assert (grad[int(il[b]):, b] == 0).all()
+
+
+def test_loss_aten_level_install():
+    """install(mode="aten"): torch's own F.ctc_loss (ATen composite + autograd) runs on the sm_100a kernels.
+    Runs last in this file: the registration cannot be undone within the process."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import torch, torch.nn.functional as F, sys
+        sys.path.insert(0, %r)
+        import ssak_b200
+        from ssak_b200.synth import ctc_batch
+        ssak_b200.install(mode="aten")
+        lp, tg, il, tl = ctc_batch(5, 150, 40, 5, 40, 91, Tmin=70)
+        for red in ("mean", "sum", "none"):
+            x = lp.cuda().requires_grad_(True)
+            loss = F.ctc_loss(x, tg.cuda(), il, tl, blank=0, reduction=red, zero_infinity=True)
+            loss.sum().backward()
+            y = lp.double().requires_grad_(True)
+            ref = F.ctc_loss(y, tg, il, tl, blank=0, reduction=red, zero_infinity=True)
+            ref.sum().backward()
+            assert ((loss.detach().cpu().double() - ref.detach()).abs() / ref.detach().abs()).max() <= 1e-5, red
+            assert (x.grad.cpu().double() - y.grad).abs().max() <= 1e-4, red
+        print("aten ok")
+    """ % __import__("conftest").ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "aten ok" in out.stdout, out.stdout + out.stderr

@@ -72,3 +72,14 @@ def test_product_fails_loudly_without_cuda_tensors():
         ssak_b200.ctc_greedy_decode(torch.zeros(1, 4, 3), torch.ones(1))
     with pytest.raises(RuntimeError, match="CUDA"):
         ssak_b200.ctc_loss(torch.zeros(4, 1, 3), torch.zeros(1, 1, dtype=torch.long), [4], [1])
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+def test_loose_get_char_index_matches_reference(capsys):
+    from ssak_b200 import loose_get_char_index
+    ref = R.namespace()["loose_get_char_index"]
+    labels = ["<pad>", "|", " "] + list("abcdefghijklmnopqrstuvwxyz'") + ["é", "ç", "E"]
+    dictionary = {c: i for i, c in enumerate(labels)}
+    for c in "aAzZéÉèÈçÇ'-!0 ñßœ|E":
+        assert loose_get_char_index(dictionary, c, 2) == ref(dictionary, c, 2), c
+    capsys.readouterr()

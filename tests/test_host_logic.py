@@ -78,7 +78,9 @@ def test_product_fails_loudly_without_cuda_tensors():
 def test_loose_get_char_index_matches_reference(capsys):
     from ssak_b200 import loose_get_char_index
     ref = R.namespace()["loose_get_char_index"]
-    labels = ["<pad>", "|", " "] + list("abcdefghijklmnopqrstuvwxyz'") + ["é", "ç", "E"]
+    # The reference tries its fall-backs in the iteration order of a Python set (:410-414), which is arbitrary
+    # when several fall-backs hit different labels; use a vocabulary where at most one of them can match.
+    labels = ["<pad>", "|", " "] + list("abcdefghijklmnopqrstuvwxyz'")
     dictionary = {c: i for i, c in enumerate(labels)}
     for c in "aAzZéÉèÈçÇ'-!0 ñßœ|E":
         assert loose_get_char_index(dictionary, c, 2) == ref(dictionary, c, 2), c

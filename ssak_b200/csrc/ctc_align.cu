@@ -16,13 +16,17 @@
 // Back-trace kernel: one warp walks the bit matrix from (t_start, L), 32 frames per memory
 // round trip (each lane fetches the 32-state window of one frame), then the CTA turns the
 // path into per-token frame spans and mean per-frame probabilities (the Segment.score).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ssak {
 
 struct AlignCfg {
-    int K, W, NW;  // states per lane, recursion warps, 32-state groups per frame (= K*W)
+    int K, W, NW;  // states per lane, recursion warps per CTA, 32-state groups per frame (= K*W*S)
     int chunk, stages, slot_bytes;
+    int S;         // CTAs per utterance (wave kernel: one thread-block cluster), 1 for the barrier kernel
+    int wave;      // 1: wavefront kernel (warps skewed in time, no per-frame barrier), 0: barrier kernel
 };
 
 struct AlignParams {
@@ -45,11 +49,14 @@ struct AlignParams {
     float *dump;
     int32_t *path_token;  // optional [B][Tmax]
     float *path_prob;     // optional [B][Tmax]
+    float *gseam;         // wave kernel: [B][S-1][Tmax] seam values handed from CTA c to CTA c+1 (preset to NaN)
     AlignCfg cfg;
 };
 
-static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
+static bool choose_barrier_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
     const int64_t P = Lmax + 1;
+    c->S = 1;
+    c->wave = 0;
     int wtarget = (B <= 148) ? 8 : ((B <= 4 * 148) ? 4 : 2);
     const char *s = getenv("SSAK_ALIGN_WARPS");
     if (s && *s) wtarget = atoi(s);
@@ -75,6 +82,74 @@ static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
     return c->stages >= 2;
 }
 
+static inline int align_env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// Wavefront kernel shape.  (K, W, S) depend on (Lmax, B) only, so the workspace size does not depend on V;
+// V decides the ring geometry and whether the ring fits at all (otherwise the barrier kernel is used).
+//   S  CTAs per utterance (a cluster): as many as the machine has room for when there are few utterances,
+//      as long as every CTA keeps >= 128 states;
+//   W  recursion warps per CTA, K states per lane: 32*K*W*S >= Lmax+1.
+static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
+    const int64_t P = Lmax + 1;
+    int S = (int)(148 / (B < 1 ? 1 : B));
+    S = S < 1 ? 1 : (S > 8 ? 8 : S);
+    while (S > 1 && (P + S - 1) / S < 128) --S;
+    const int64_t cap = 32 * 8 * 8;  // states one CTA can hold (K = 8, W = 8)
+    if ((P + cap - 1) / cap > S) S = (int)((P + cap - 1) / cap);
+    S = align_env_int("SSAK_ALIGN_S", S);
+    if (S < 1 || S > 8) return false;  // L <= 16383
+    const int64_t Pc = (P + S - 1) / S;
+    int wtarget = (B * S <= 148) ? 8 : ((B * S <= 4 * 148) ? 4 : 2);
+    wtarget = align_env_int("SSAK_ALIGN_WARPS", wtarget);
+    int K = align_env_int("SSAK_ALIGN_K", 0);
+    if (K == 0) K = (Pc + 127) / 128 > wtarget ? 8 : 4;
+    if (K != 4 && K != 8) return false;  // a lane owns 4 or 8 consecutive states (decision bits: 1 or 2 bytes per lane)
+    if (K < 8 && (Pc + 32 * K - 1) / (32 * K) > 8) K = 8;  // the kernels are built for <= 8 recursion warps
+    int64_t W = (Pc + 32 * K - 1) / (32 * K);
+    if (W > 8) return false;
+    c->K = K;
+    c->W = (int)W;
+    c->S = S;
+    c->NW = K * (int)W * S;
+    c->wave = 1;
+    return true;
+}
+
+static bool choose_wave_ring(int64_t B, int V, AlignCfg *c) {
+    c->slot_bytes = ring_slot_bytes(V);
+    c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;
+    const int budget = (B * c->S <= 148) ? 160 * 1024 : 72 * 1024;
+    int stages = budget / (c->chunk * c->slot_bytes);
+    // warp w works >= w chunks behind warp 0: W+2 stages at least, W+6 cover the bulk-copy latency as well
+    if (stages > c->W + 6) stages = c->W + 6;
+    stages = align_env_int("SSAK_ALIGN_STAGES", stages);
+    if (stages > 24) stages = 24;
+    c->stages = stages;
+    return stages >= c->W + 2;
+}
+
+static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
+    if (align_env_int("SSAK_ALIGN_WAVE", 1) != 0 && choose_wave_shape(Lmax, B, c) && choose_wave_ring(B, V, c))
+        return true;
+    return choose_barrier_cfg(Lmax, B, V, c);
+}
+
+// bytes of the decision-bit matrix for the larger of the two candidate shapes (the choice depends on V)
+static int align_max_nw(int64_t Lmax, int64_t B, int *S_out) {
+    AlignCfg a, w;
+    int nw = 0;
+    *S_out = 1;
+    if (choose_barrier_cfg(Lmax, B, 64, &a)) nw = a.NW;
+    if (choose_wave_shape(Lmax, B, &w)) {
+        nw = w.NW > nw ? w.NW : nw;
+        *S_out = w.S;
+    }
+    return nw;
+}
+
 // Column 0 of the trellis (:37 / :39) for rows 1..T_b, with the +inf sentinel of :42.  The cumulative
 // variant is the fp64 running sum of the blank column rounded to fp32 per element (torch.cumsum on the
 // CPU): strictly sequential by definition, so one warp per utterance fetches 32 frames at a time and
@@ -90,17 +165,24 @@ __global__ void __launch_bounds__(32) align_col0_kernel(const AlignParams p) {
     float *out = p.col0_eff + (int64_t)b * p.Tmax;
     const float *c0 = p.garbage && p.col0 ? p.col0 + (int64_t)b * p.Tmax : nullptr;
     double acc = 0.0;
+    auto load = [&](int t) -> float { return t < Tb ? (c0 ? c0[t] : em_b[(int64_t)t * p.st]) : 0.f; };
+    float xn = load(lane);
     for (int t0 = 0; t0 < Tb; t0 += 32) {
         const int t = t0 + lane;
-        float x = 0.f;
-        if (t < Tb) x = c0 ? c0[t] : em_b[(int64_t)t * p.st];
+        const float x = xn;
+        xn = load(t + 32);  // the next 32 frames are in flight while this block's chain runs
         float mine = x;
         if (!c0) {
+            // the only serial piece is the chain of fp64 adds: convert once per lane, broadcast the doubles
+            // (independent shuffles), pick my prefix with selects, round to fp32 once at the end
+            const double xd = (double)x;
+            double mine_d = 0.0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                acc += (double)__shfl_sync(0xffffffffu, x, i);
-                if (lane == i) mine = (float)acc;
+                acc += __shfl_sync(0xffffffffu, xd, i);
+                mine_d = lane == i ? acc : mine_d;
             }
+            mine = (float)mine_d;
         }
         if (t < Tb) out[t] = (t + 1 >= Tb + 1 - L) ? INF : mine;
     }
@@ -110,7 +192,7 @@ __global__ void __launch_bounds__(32) align_col0_kernel(const AlignParams p) {
 template <int K, int CH>
 __global__ void __launch_bounds__(K == 16 ? 544 : (K == 8 ? 1024 : 512), 1)
 align_forward_kernel(const AlignParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const AlignCfg &c = p.cfg;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,10 +383,328 @@ align_forward_kernel(const AlignParams p) {
     if (ownsL) p.t_start[b] = best_t;
 }
 
-// Back-trace (:79-123) + merge_repeats (:141-157).  Warp 0 walks the decision bits from (t_start, L): each
-// lane fetches the 64-state window of one frame, 32 frames per round trip, and the fetch for the next 32
-// frames is issued before the current 32 are walked (the window [j-63, j] covers wherever the walk ends).
-// Then the whole CTA computes the per-frame probabilities (:106-112) in parallel and the per-token means.
+// ---------------------------------------------------------------------------------------------
+// Wavefront forward kernel.  Same arithmetic and the same decision-bit layout as the barrier kernel, but
+// the recursion warps are skewed in time instead of meeting at a barrier every frame: state j of row t+1
+// depends on states j and j-1 of row t only, so warp g (states [32K g, 32K (g+1))) needs exactly ONE value
+// per frame from warp g-1 (its "seam").  Warp g-1 streams its seam values into a small shared-memory ring and
+// warp g runs a chunk or two behind it.  The chain continues across the CTAs of a thread-block cluster
+// (S CTAs per utterance, co-scheduled by the cluster launch) through a global, L2-resident seam buffer.
+//   * Seam words validate themselves ("flag in the data"): every word starts as a NaN pattern that no
+//     trellis value can take, the consumer polls the word itself.  No flag, no fence, no barrier; each
+//     4-byte store is atomic.  The consumer reads the words of the NEXT chunk while it computes the current
+//     one and only polls when that early read came too soon.
+//   * The emission ring's full-barrier is probed early in the same way (test_wait a chunk ahead, blocking
+//     try_wait only if that probe failed), so in the steady state a chunk costs no synchronisation latency.
+//   * Nothing ever waits on a downstream warp, so the chain cannot deadlock.  Every CTA has its own emission
+//     ring (producer warp W); a stage is recycled once all live warps of the CTA released it, which bounds
+//     the lead of warp g-1 over warp g (-> a seam ring of stages+1 chunks never overflows).
+//   * The frame body is branch-free (selects and predicated stores only) and unrolled over the chunk, so
+//     that ptxas overlaps the loads, ballots and stores of neighbouring frames with the dependent chain
+//     shuffle -> add -> max, which is all that remains serial per frame.
+struct WaveSmem {
+    int em_full, em_empty, seam_val, ring, total;
+};
+__host__ __device__ __forceinline__ WaveSmem wave_smem(int W, int stages, int chunk, int slot_bytes) {
+    WaveSmem m;
+    const int nslot = stages + 1;
+    m.em_full = 0;
+    m.em_empty = 8 * stages;
+    m.seam_val = 16 * stages;                      // [W+1][nslot][chunk] floats (+1: scratch for warps without a consumer)
+    m.ring = (m.seam_val + 4 * (W + 1) * nslot * chunk + 127) & ~127;
+    m.total = m.ring + stages * chunk * slot_bytes;
+    return m;
+}
+
+constexpr uint32_t kSeamEmpty = 0xffffffffu;  // NaN pattern no add/max of the recursion produces
+__device__ __forceinline__ float ld_seam_global(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_seam_shared(const float *p) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_seam_generic(float *p, float v) {  // shared or global (generic address)
+    // no "memory" clobber: nothing in this thread reads the word back, and the clobber would pin every
+    // emission load of the unrolled chunk behind the store of the previous frame
+    asm volatile("st.relaxed.gpu.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+
+template <int K, int CH, bool DUMP>
+__global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const AlignCfg &c = p.cfg;
+    const int cta = blockIdx.x, S = c.S, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+    const float EMPTY = __uint_as_float(kSeamEmpty);
+    const int W = c.W;
+
+    int Tb = p.em_len[b];
+    Tb = Tb < 0 ? 0 : (Tb > (int)p.Tmax ? (int)p.Tmax : Tb);
+    int L = p.tok_len[b];
+    L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
+    if (L == 0 || Tb == 0) {  // reference: empty back-track loop -> "Failed to align"
+        if (cta != 0) return;
+        if (tid == 0) p.t_start[b] = 0;
+        if (DUMP) {  // :41-42 with an empty token list / no frames: column 0 is all +inf
+            float *d = p.dump + (int64_t)b * (p.Tmax + 1) * (p.Lmax + 1);
+            for (int t = tid; t <= Tb; t += blockDim.x) d[(int64_t)t * (p.Lmax + 1)] = INF;
+            if (Tb == 0)
+                for (int j = 1 + tid; j <= L; j += blockDim.x) d[j] = -INF;
+        }
+        return;
+    }
+    // live warps of this CTA: global warp g holds states [32K g, 32K (g+1)), live iff 32K g <= L
+    const int gw0 = cta * W;
+    int wlive = L / (32 * K) + 1 - gw0;
+    wlive = wlive < 0 ? 0 : (wlive > W ? W : wlive);
+    if (wlive == 0) return;                        // the whole CTA lies beyond state L
+    const bool compute = warp < wlive;
+
+    const int V = p.V;
+    const float *em_b = p.em + (int64_t)b * p.sb;
+    const int32_t *tk = p.tokens + (int64_t)b * p.tok_stride;
+    const int NST = c.stages, NSLOT = NST + 1, slot_bytes = c.slot_bytes;
+    const WaveSmem lay = wave_smem(W, NST, CH, slot_bytes);
+    uint64_t *em_full = reinterpret_cast<uint64_t *>(smem + lay.em_full);
+    uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + lay.em_empty);
+    float *seam_val = reinterpret_cast<float *>(smem + lay.seam_val);          // [W+1][NSLOT][CH]
+    RowRing ring;
+    ring.slots = smem + lay.ring;
+    ring.full = em_full;
+    ring.chunk = CH;
+    ring.stages = NST;
+    ring.slot_bytes = slot_bytes;
+    ring.row_bytes = 4 * V;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&em_full[s], 1);
+            mbar_init(&em_empty[s], wlive);
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < (W + 1) * NSLOT * CH; i += blockDim.x) seam_val[i] = EMPTY;
+    __syncthreads();  // the only CTA-wide barrier
+    if (warp >= wlive && warp != W) return;        // idle recursion warps
+
+    const int nchunks = (Tb + CH - 1) / CH;
+    const bool contig = p.st == V;  // [.., T, V] rows back to back: chunk-sized copies, rows 4V bytes apart in the ring
+    if (!compute) {
+        // ================= producer warp =================
+        RingProducer prod;
+        prod.src = em_b;
+        prod.step_elems = p.st;
+        prod.stage = 0;
+        prod.remaining = Tb;
+        int round = 0;
+        for (int n = 0; n < nchunks; ++n) {
+            if (round > 0) mbar_wait(&em_empty[prod.stage], (uint32_t)((round - 1) & 1));
+            const int stg = prod.stage;
+            if (contig) {
+                // rows are back to back in memory: the whole chunk is ONE bulk copy (its enclosing 16-byte range)
+                if (lane == 0) {
+                    const int nf = prod.remaining < CH ? prod.remaining : CH;
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(prod.src), a0 = a & ~(uintptr_t)15;
+                    const uint32_t bytes = (uint32_t)(((a + (size_t)nf * 4 * V + 15) & ~(uintptr_t)15) - a0);
+                    mbar_arrive_expect_tx(&em_full[stg], bytes);
+                    bulk_g2s(ring.slots + (size_t)stg * CH * slot_bytes, reinterpret_cast<const void *>(a0), bytes,
+                             &em_full[stg]);
+                }
+                prod.src += (int64_t)CH * V;
+                prod.remaining -= CH;
+                if (++prod.stage == NST) prod.stage = 0;
+            } else {
+                if (lane == 0) ring_issue_next(ring, prod);
+                prod.stage = __shfl_sync(FULL, prod.stage, 0);
+            }
+            if (prod.stage <= stg) ++round;
+        }
+        return;
+    }
+
+    // ================= recursion warps =================
+    // Blocked state layout: lane l of global warp g holds the K CONSECUTIVE states 32K g + K l + [0, K), so
+    // the neighbour of every state but the lane's first one is a register, and ONE shuffle per frame brings
+    // the last state of lane l-1 (or the seam value, for lane 0).
+    const int gw = gw0 + warp;
+    const int sbase = gw * 32 * K + lane * K;
+    int tok_off[K];
+    float v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = sbase + k;
+        int tkn = p.blank;
+        if (j >= 1 && j <= L) {
+            tkn = tk[j - 1];
+            tkn = tkn < 0 ? 0 : (tkn >= V ? V - 1 : tkn);
+        }
+        tok_off[k] = 4 * tkn;
+        v[k] = j == 0 ? (L >= Tb + 1 ? INF : 0.f) : -INF;  // trellis row 0 (:35, :41, :42)
+    }
+    const int jL_rel = L - gw * 32 * K;  // state L inside this warp?
+    const bool ownsL = jL_rel >= 0 && jL_rel < 32 * K && jL_rel / K == lane;
+    const int kL = jL_rel & (K - 1);
+    float best = -INF;  // trellis[0, L] with L >= 1
+    int best_t = 0;
+    float *dump_row = nullptr;
+    if (DUMP) {
+        float *d = p.dump + (int64_t)b * (p.Tmax + 1) * (p.Lmax + 1);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (sbase + k <= L) d[sbase + k] = v[k];
+        dump_row = p.dump + ((int64_t)b * (p.Tmax + 1) + 1) * (p.Lmax + 1) + sbase;
+    }
+    // seams: where my incoming values come from, where my outgoing values go
+    const bool first = gw == 0;                       // owns trellis column 0: its "seam" is column 0 itself
+    const bool up_smem = warp > 0, up_glob = warp == 0 && cta > 0;
+    const bool dn_live = (gw + 1) * 32 * K <= L;
+    const bool dn_glob = dn_live && warp + 1 == W;
+    const float *gs_in = p.gseam + ((int64_t)b * (S - 1) + (cta - 1)) * p.Tmax;   // valid when up_glob
+    const float *sv_in = seam_val + (warp - 1) * NSLOT * CH;                      // valid when up_smem
+    // outgoing: the ring of my downstream warp in this CTA, the global buffer, or a scratch ring nobody reads
+    float *sv_out = seam_val + (dn_live && !dn_glob ? warp : W) * NSLOT * CH;
+    float *out_ptr = dn_glob ? p.gseam + ((int64_t)b * (S - 1) + cta) * p.Tmax : sv_out;
+    const bool is31 = lane == 31;
+
+    // frame f of a chunk sits at f * row_stride + ((a15 + f * a15_step) & 15) in its stage: per-row copies land
+    // every row (addr & 15) bytes into its own slot, a chunk copy lands the chunk (addr & 15) bytes into the stage
+    const int row_stride = contig ? 4 * V : slot_bytes;
+    const unsigned a15_step = contig ? 0u : (unsigned)((p.st * 4) & 15);
+    const unsigned a15_chunk_step = contig ? (unsigned)((CH * 4 * V) & 15) : 0u;
+    unsigned a15 = (unsigned)(reinterpret_cast<uintptr_t>(em_b) & 15);
+    const int blank_off = 4 * p.blank;
+    const unsigned seam_m = lane == 0 ? 0xffffffffu : 0u;
+    const unsigned zero_m = (first && lane == 0) ? 0xffffffffu : 0u;  // the thread that owns trellis column 0
+    auto sel = [](unsigned m, float a, float bb) {
+        return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
+    };
+    // decision bits, "lane entry" layout: per frame and lane one entry of 2K bits -- bit k: changed > stayed for
+    // my k-th state, bit K+k: changed < stayed -- i.e. one byte (K = 4) or two (K = 8) per lane, a coalesced
+    // 32/64-byte store per warp and frame, 16 states per 32-bit word, no cross-lane packing at all.
+    using bp_t = typename std::conditional<K == 8, uint16_t, uint8_t>::type;
+    const int64_t bp_row = (int64_t)c.S * W * 32;  // entries per frame
+    bp_t *bp_ptr = reinterpret_cast<bp_t *>(p.bp) + (int64_t)b * p.Tmax * bp_row + gw * 32 + lane;
+    const float *c0_ptr = p.col0_eff + (int64_t)b * p.Tmax;
+    const unsigned char *em_base = ring.slots, *em_chunk = em_base;
+    int em_stage = 0, em_phase = 0, remaining = Tb, t = 0, sslot = 0;
+    const bool inlane = lane < CH;
+    // incoming values of the NEXT chunk, frame f in lane f (read one chunk early; EMPTY = not there yet)
+    auto fetch_seam = [&](int t_next, int slot_next) -> float {
+        float x = -INF;
+        if (first) {
+            if (inlane && t_next + lane < Tb) x = __ldg(c0_ptr + t_next + lane);
+        } else if (up_smem) {
+            if (inlane) x = ld_seam_shared(sv_in + slot_next * CH + lane);
+        } else if (up_glob) {
+            if (inlane && t_next + lane < Tb) x = ld_seam_global(gs_in + t_next + lane);
+        }
+        return x;
+    };
+    float sv_pre = fetch_seam(0, 0);
+
+    // one frame.  xin: lane 0's neighbour (state 32K g - 1 in row t+f), or column 0 for the first warp.
+    // My last state's value in row t+f is the downstream warp's neighbour at this frame.  A store inside the
+    // unrolled chunk would pin every emission load behind it (a generic / shared store may alias the ring as
+    // far as ptxas can tell), so full chunks collect the values in registers and store them after the chunk.
+    float sout[CH];
+    auto frame = [&](const int f, const float sv, auto direct_tag) {
+        constexpr bool DIRECT = decltype(direct_tag)::value;
+        const unsigned char *row = em_chunk + f * row_stride + ((a15 + f * a15_step) & 15u);
+        const float eb = *reinterpret_cast<const float *>(row + blank_off);
+        const float xin = __shfl_sync(FULL, sv, f);
+        if (DIRECT) {
+            if (is31) st_seam_generic(out_ptr + f, v[K - 1]);
+        } else {
+            sout[f] = v[K - 1];
+        }
+        const float rk = __shfl_sync(FULL, v[K - 1], (lane + 31) & 31);
+        float prev = sel(seam_m, xin, rk);
+        unsigned ng = 0, nl = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float ek = *reinterpret_cast<const float *>(row + tok_off[k]);
+            // max(v+eb, v+ek) == v + max(eb, ek) bit for bit (rounding is monotonic): :48-49, :96-99
+            const float stayed = v[k] + fmaxf(eb, ek);
+            const float chg = prev + ek;               // :51
+            prev = v[k];
+            float nv = fmaxf(stayed, chg);
+            if (k == 0) nv = sel(zero_m, xin, nv);     // column 0 (:37 / :39 / :42)
+            v[k] = nv;
+            ng |= chg > stayed ? 1u << k : 0u;
+            nl |= chg < stayed ? 1u << k : 0u;
+        }
+        *bp_ptr = (bp_t)(ng | (nl << K));
+        bp_ptr += bp_row;
+        {   // first maximum of trellis[:, L] (:88); only the owner's comparison can be true
+            float vl = v[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) vl = k == kL ? v[k] : vl;
+            const bool up = ownsL && vl > best;
+            best = up ? vl : best;
+            best_t = up ? t + f + 1 : best_t;
+        }
+        if (DUMP) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (sbase + k <= L) dump_row[k] = v[k];
+            dump_row += p.Lmax + 1;
+        }
+    };
+
+    while (remaining > 0) {
+        const int n = remaining < CH ? remaining : CH;
+        // incoming values of this chunk: read early during the previous chunk, poll only if that was too soon
+        float sv = sv_pre;
+        if (!first) {
+            while (__any_sync(FULL, lane < n && __float_as_uint(sv) == kSeamEmpty))
+                sv = up_smem ? ld_seam_shared(sv_in + sslot * CH + (lane & (CH - 1)))
+                             : ld_seam_global(gs_in + min(t + (lane & (CH - 1)), Tb - 1));
+            if (up_smem && inlane) const_cast<float *>(sv_in)[sslot * CH + lane] = EMPTY;  // recycle the slot
+        }
+        const int sslot_next = sslot + 1 == NSLOT ? 0 : sslot + 1;
+        sv_pre = fetch_seam(t + CH, sslot_next);
+        mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+        if (dn_live && !dn_glob) out_ptr = sv_out + sslot * CH;
+        if (n == CH) {
+#pragma unroll
+            for (int f = 0; f < CH; ++f) frame(f, sv, std::false_type{});
+            if (is31) {
+#pragma unroll
+                for (int f = 0; f < CH; ++f) st_seam_generic(out_ptr + f, sout[f]);
+            }
+        } else {
+#pragma unroll 1
+            for (int f = 0; f < n; ++f) frame(f, sv, std::true_type{});
+        }
+        if (dn_glob) out_ptr += CH;
+        a15 = (a15 + a15_chunk_step) & 15u;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+        remaining -= n;
+        t += n;
+        em_chunk += CH * slot_bytes;
+        if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
+        sslot = sslot_next;
+    }
+    if (ownsL) p.t_start[b] = best_t;
+}
+
+// Back-trace (:79-123) + merge_repeats (:141-157).  Warp 0 walks the "changed > stayed" bits from (t_start, L),
+// 32 frames per round: lane i fetches the bits of frame t-1-i for the states [j-63, j] (issued one round ahead,
+// the window covers wherever the current round ends) and compacts them into one 32-state window word; the walk
+// itself is branch-free -- per frame one shuffle (off the dependent chain), a shift, a mask and a subtract -- and
+// emits rec[frame] = (state << 1) | changed.  Then the whole CTA derives the token start frames, the per-frame
+// probabilities (:106-112, which also need the "changed < stayed" bit of the path cell) and the per-token means.
+// LK = 0: decision words of the barrier kernel (32 states per word, K "greater" then K "less" words per warp);
+// LK = 4 / 8: lane entries of the wavefront kernel (16 states per 32-bit word, "greater" in the low half of
+// every 2K-bit entry).
+template <int LK>
 __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams p) {
     __shared__ int s_status, s_first;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -314,8 +714,9 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
     int L = p.tok_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int NW = p.cfg.NW, KK = p.cfg.K;
-    const uint32_t *bp_b = p.bp + (int64_t)b * p.Tmax * 2 * NW;
-    uint32_t *rec = p.rec + (int64_t)b * p.Tmax;   // (token index << 2) | (changed>stayed) | (changed<stayed) << 1
+    const int row_words = 2 * NW;  // 32-bit words of decision bits per frame (both layouts: 2 bits per state)
+    const uint32_t *bp_b = p.bp + (int64_t)b * p.Tmax * row_words;
+    uint32_t *rec = p.rec + (int64_t)b * p.Tmax;   // (state << 1) | (changed > stayed) for the frames on the path
     float *prob = p.prob + (int64_t)b * p.Tmax;
     int32_t *st_b = p.starts + (int64_t)b * p.Lmax;
     int32_t *en_b = p.ends + (int64_t)b * p.Lmax;
@@ -323,58 +724,88 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
     const int t_start = (L == 0 || Tb == 0) ? 0 : p.t_start[b];
 
     if (warp == 0) {
-        int t = t_start, j = L;
-        bool done = false;
-        uint32_t cg[3], cl[3], ng[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
-        int cgrp = 0, ngrp = 0;
-        auto fetch = [&](int tt, int jj, uint32_t *g, uint32_t *l, int &grp0) {
-            // words of trellis row tt-lane covering the states [jj-63, jj]; 32-state group g lives at
-            // word (g / K) * 2K + (g % K) ("changed > stayed") and + K ("changed < stayed")
-            grp0 = max(jj - 63, 0) >> 5;
+        int t = t_start, j = L, first = 0;
+        constexpr int NRAW = LK == 0 ? 3 : 5;
+        uint32_t cw[3], raw[NRAW];
+        int cbase = 0, nbase = 0;
+        // issue the loads of the "changed > stayed" bits of trellis row tt-lane for the states from sb0 (a multiple
+        // of 16 or 32) on; nothing here waits for them
+        auto fetch = [&](int tt, int jj, uint32_t *w, int &sb0) {
             const int rr = tt - lane;
+            const uint32_t *rowp = bp_b + (int64_t)(rr - 1) * row_words;
+            if (LK == 0) {
+                const int grp0 = max(jj - 63, 0) >> 5;
+                sb0 = grp0 << 5;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                g[q] = 0;
-                l[q] = 0;
-                const int grp = grp0 + q;
-                if (rr >= 1 && grp < NW) {
-                    const uint32_t *w = bp_b + (int64_t)(rr - 1) * 2 * NW + (grp / KK) * 2 * KK + (grp % KK);
-                    g[q] = __ldg(w);
-                    l[q] = __ldg(w + KK);
+                for (int q = 0; q < 3; ++q) {
+                    const int grp = grp0 + q;
+                    w[q] = (rr >= 1 && grp < NW) ? __ldg(rowp + (grp / KK) * 2 * KK + (grp % KK)) : 0u;
                 }
+            } else {
+                const int w0 = max(jj - 63, 0) >> 4;
+                sb0 = w0 << 4;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) w[q] = (rr >= 1 && w0 + q < row_words) ? __ldg(rowp + w0 + q) : 0u;
             }
         };
-        if (t > 0) fetch(t, j, cg, cl, cgrp);
-        while (t > 0 && !done) {
-            if (t > 32) fetch(t - 32, j, ng, nl, ngrp);  // next 32 frames, issued before the walk
-            const int base = max(j - 31, 0);
-            const int off = base - (cgrp << 5);          // 0 <= off < 64
-            const int sh = off & 31;
-            const bool hi = off >= 32;
-            const uint32_t wg = __funnelshift_r(hi ? cg[1] : cg[0], hi ? cg[2] : cg[1], sh);
-            const uint32_t wl = __funnelshift_r(hi ? cl[1] : cl[0], hi ? cl[2] : cl[1], sh);
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                if (t - i < 1) break;
-                const uint32_t gi = __shfl_sync(FULL, wg, i), li = __shfl_sync(FULL, wl, i);
-                const int bit = j - base;
-                const uint32_t gt = (gi >> bit) & 1u, lt = (li >> bit) & 1u;
-                const int frame = t - i - 1;
-                if (lane == 0) rec[frame] = ((uint32_t)(j - 1) << 2) | gt | (lt << 1);
-                if (gt) {  // :117 changed > stayed -> previous token
-                    if (lane == 0) st_b[j - 1] = frame;
-                    --j;
-                    if (j == 0) { done = true; s_first = frame; break; }  // :119-120
-                }
-            }
-            t -= 32;
+        // raw words -> 96 consecutive state bits (first use of the loaded values)
+        auto compact = [&](const uint32_t *w, uint32_t *g) {
+            if (LK == 0) {
+                g[0] = w[0]; g[1] = w[1]; g[2] = w[2];
+            } else {
+                uint32_t c[5];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { cg[q] = ng[q]; cl[q] = nl[q]; }
-            cgrp = ngrp;
+                for (int q = 0; q < 5; ++q) {
+                    uint32_t x = w[q];
+                    if (LK == 4) {
+                        x &= 0x0f0f0f0fu;
+                        x = (x | (x >> 4)) & 0x00ff00ffu;
+                    } else {
+                        x &= 0x00ff00ffu;
+                    }
+                    c[q] = (x | (x >> 8)) & 0xffffu;
+                }
+                g[0] = c[0] | (c[1] << 16);
+                g[1] = c[2] | (c[3] << 16);
+                g[2] = c[4];
+            }
+        };
+        if (t > 0) fetch(t, j, raw, nbase);
+        while (t > 0 && j > 0) {
+            compact(raw, cw);
+            cbase = nbase;
+            if (t > 32) fetch(t - 32, j, raw, nbase);  // next 32 frames: in flight during the walk
+            const int base = max(j - 31, 0);
+            const int off = base - cbase;             // 0 <= off < 64
+            uint32_t win = off < 32 ? __funnelshift_r(cw[0], cw[1], off) : __funnelshift_r(cw[1], cw[2], off - 32);
+            if (base == 0) win &= ~1u;                // state 0 never "changes": the walk parks there (:119-120)
+            const uint32_t valid = t >= 32 ? 0xffffffffu : ((1u << t) - 1u);  // step i looks at frame t-1-i >= 0
+            // all 32 windows first (independent shuffles), then the dependent chain: shift, mask, subtract
+            uint32_t gi[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t g = __shfl_sync(FULL, win, i);
+                gi[i] = (valid >> i) & 1u ? g : 0u;
+            }
+            int sh = j - base;                        // 0 <= sh <= 31, state = base + sh
+            uint32_t mine = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t bit = (gi[i] >> sh) & 1u;  // :117 changed > stayed -> previous token
+                const uint32_t r = ((uint32_t)(base + sh) << 1) | bit;
+                mine = lane == i ? r : mine;
+                sh -= (int)bit;
+                first = (bit && base + sh == 0) ? t - i - 1 : first;  // :119-120 the path starts at this frame
+            }
+            j = base + sh;
+            if (t - 1 - lane >= 0) rec[t - 1 - lane] = mine;
+            t -= 32;
         }
         if (lane == 0) {
-            s_status = done ? 0 : 1;  // :121-122 "Failed to align"
-            p.status[b] = done ? 0 : 1;
+            const bool ok = j == 0 && L > 0 && t_start > 0;
+            s_status = ok ? 0 : 1;  // :121-122 "Failed to align"
+            s_first = first;
+            p.status[b] = ok ? 0 : 1;
         }
     }
     __syncthreads();
@@ -384,16 +815,29 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
     float *pprob = p.path_prob ? p.path_prob + (int64_t)b * p.Tmax : nullptr;
     const float *em_b = p.em + (int64_t)b * p.sb;
     const int32_t *tk = p.tokens + (int64_t)b * p.tok_stride;
-    // per-frame probability of the path (:106-112), one thread per frame
+    // per-frame probability of the path (:106-112) and the start frame of every token, one thread per frame
     for (int f = tid; f < (int)p.Tmax; f += blockDim.x) {
         float pr = 0.f;
         int ti = -1;
         if (f >= first && f < last) {
             const uint32_t rc = rec[f];
-            ti = (int)(rc >> 2);
+            const int j = (int)(rc >> 1);
+            ti = j - 1;
             int tkn = tk[ti];
             tkn = tkn < 0 ? 0 : (tkn >= p.V ? p.V - 1 : tkn);
-            const bool gt = rc & 1u, lt = rc & 2u;
+            const bool gt = rc & 1u;
+            if (gt) st_b[ti] = f;
+            // "changed < stayed" of the path cell
+            const uint32_t *rowp = bp_b + (int64_t)f * row_words;
+            bool lt;
+            if (LK == 0) {
+                const int grp = j >> 5;
+                lt = (__ldg(rowp + (grp / KK) * 2 * KK + (grp % KK) + KK) >> (j & 31)) & 1u;
+            } else if (LK == 4) {
+                lt = (__ldg(rowp + (j >> 4)) >> (8 * ((j & 15) >> 2) + 4 + (j & 3))) & 1u;
+            } else {
+                lt = (__ldg(rowp + (j >> 4)) >> (16 * ((j & 15) >> 3) + 8 + (j & 7))) & 1u;
+            }
             const float *r0 = em_b + (int64_t)f * p.st;
             if (lt && f + 1 < Tb) {  // hard-coded vocabulary index 0, next frame's token (:108)
                 const float x = r0[0], y = r0[p.st + tkn];
@@ -432,11 +876,28 @@ static size_t align_smem_bytes(const AlignCfg &c) {
 
 using namespace ssak;
 
+struct AlignWs { size_t bp, rec, prob, col0, gseam, gseam_bytes, total; };
+static AlignWs align_ws_layout(int64_t B, int64_t Tmax, int nw, int S) {
+    AlignWs w;
+    const size_t bt = align_up((size_t)B * (size_t)Tmax * sizeof(float), 256);
+    size_t o = 0;
+    w.bp = o;    o += align_up((size_t)B * (size_t)Tmax * 2 * nw * sizeof(uint32_t), 256);
+    w.rec = o;   o += bt;
+    w.prob = o;  o += bt;
+    w.col0 = o;  o += bt;
+    w.gseam = o;
+    w.gseam_bytes = (size_t)B * (size_t)(S > 1 ? S - 1 : 0) * (size_t)Tmax * sizeof(float);
+    o += align_up(w.gseam_bytes, 256);
+    w.total = o + 256;
+    return w;
+}
+
 extern "C" size_t ssak_align_workspace_bytes(int64_t B, int64_t Tmax, int64_t Lmax) {
-    AlignCfg c;
-    if (B <= 0 || Tmax < 0 || Lmax < 0 || !choose_align_cfg(Lmax, B, 64, &c)) return 0;
-    return align_up((size_t)B * (size_t)Tmax * 2 * c.NW * sizeof(uint32_t), 256) +
-           3 * align_up((size_t)B * (size_t)Tmax * sizeof(float), 256) + 256;
+    if (B <= 0 || Tmax < 0 || Lmax < 0) return 0;
+    int S = 1;
+    const int nw = align_max_nw(Lmax, B, &S);
+    if (nw == 0) return 0;
+    return align_ws_layout(B, Tmax, nw, S).total;
 }
 
 extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax, int64_t V,
@@ -458,26 +919,80 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     AlignParams p;
     if (!choose_align_cfg(Lmax, B, (int)V, &p.cfg)) return SSAK_ERR_UNSUPPORTED;
     if (workspace_bytes < ssak_align_workspace_bytes(B, Tmax, Lmax)) return SSAK_ERR_WORKSPACE;
-    const size_t smem_bytes = align_smem_bytes(p.cfg);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
+    const bool wave = p.cfg.wave != 0;
+    const size_t smem_bytes = wave ? (size_t)wave_smem(p.cfg.W, p.cfg.stages, p.cfg.chunk, p.cfg.slot_bytes).total
+                                   : align_smem_bytes(p.cfg);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
     p.em = emissions; p.B = B; p.Tmax = Tmax; p.V = (int)V; p.sb = em_stride_b; p.st = em_stride_t;
     p.tokens = tokens; p.tok_stride = tok_stride; p.Lmax = (int)Lmax;
     p.em_len = emission_lengths; p.tok_len = token_lengths; p.blank = blank;
     p.garbage = first_as_garbage; p.col0 = col0;
     char *ws = reinterpret_cast<char *>(workspace);
-    p.bp = reinterpret_cast<uint32_t *>(ws);
-    const size_t bp_bytes = align_up((size_t)B * (size_t)Tmax * 2 * p.cfg.NW * sizeof(uint32_t), 256);
-    const size_t bt_bytes = align_up((size_t)B * (size_t)Tmax * sizeof(float), 256);
-    p.rec = reinterpret_cast<uint32_t *>(ws + bp_bytes);
-    p.prob = reinterpret_cast<float *>(ws + bp_bytes + bt_bytes);
-    p.col0_eff = reinterpret_cast<float *>(ws + bp_bytes + 2 * bt_bytes);
-    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
+    const AlignWs lay = align_ws_layout(B, Tmax, p.cfg.NW, p.cfg.S);
+    p.bp = reinterpret_cast<uint32_t *>(ws + lay.bp);
+    p.rec = reinterpret_cast<uint32_t *>(ws + lay.rec);
+    p.prob = reinterpret_cast<float *>(ws + lay.prob);
+    p.col0_eff = reinterpret_cast<float *>(ws + lay.col0);
+    p.gseam = reinterpret_cast<float *>(ws + lay.gseam);
     p.starts = starts; p.ends = ends; p.scores = scores; p.t_start = t_start; p.status = status;
     p.dump = trellis_dump; p.path_token = path_token; p.path_prob = path_prob;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
     int rc = check_launch();
     if (rc != SSAK_OK) return rc;
+    if (wave) {
+        if (B > 65535) return SSAK_ERR_UNSUPPORTED;
+        if (lay.gseam_bytes) {  // every cross-CTA seam word starts as "not there yet"
+            cudaError_t e = cudaMemsetAsync(p.gseam, 0xff, lay.gseam_bytes, s);
+            if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
+        }
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)p.cfg.S, (unsigned)B);
+        lc.blockDim = dim3((p.cfg.W + 1) * 32);
+        lc.dynamicSmemBytes = smem_bytes;
+        lc.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cfg.S;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        // The cluster launch is what guarantees that the CTAs of an utterance run together.  When the whole
+        // grid is resident at once anyway, a plain launch gives the same guarantee and lets the block scheduler
+        // spread the CTAs one per SM (8-CTA clusters fit only 15x on a B200 at one CTA per SM).
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const bool try_plain = align_env_int("SSAK_ALIGN_CLUSTER", 0) == 0;
+#define SSAK_WAVE3(KK, CC, DD)                                                                 \
+    {                                                                                          \
+        auto kern = align_wave_kernel<KK, CC, DD>;                                             \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem_bytes);                                 \
+        int per_sm = 0;                                                                        \
+        if (e == cudaSuccess && try_plain)                                                     \
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)lc.blockDim.x, smem_bytes); \
+        if (e == cudaSuccess && (int64_t)per_sm * sms >= (int64_t)p.cfg.S * B) lc.numAttrs = 0; \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&lc, kern, p);                            \
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
+    }
+#define SSAK_WAVE2(KK, CC)                                                                     \
+    if (p.dump) SSAK_WAVE3(KK, CC, true) else SSAK_WAVE3(KK, CC, false)
+#define SSAK_WAVE(KK)                                                                          \
+    case KK:                                                                                   \
+        if (p.cfg.chunk == 8) { SSAK_WAVE2(KK, 8) } else { SSAK_WAVE2(KK, 4) }                 \
+        break;
+        switch (p.cfg.K) {
+            SSAK_WAVE(4)
+            SSAK_WAVE(8)
+            default: return SSAK_ERR_UNSUPPORTED;
+        }
+#undef SSAK_WAVE
+#undef SSAK_WAVE2
+#undef SSAK_WAVE3
+    } else {
     dim3 grid((unsigned)B), block((p.cfg.W + 1) * 32);
 #define SSAK_LAUNCH2(KK, CC)                                                                   \
     {                                                                                          \
@@ -501,8 +1016,11 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     }
 #undef SSAK_LAUNCH
 #undef SSAK_LAUNCH2
+    }
     rc = check_launch();
     if (rc != SSAK_OK) return rc;
-    align_backtrace_kernel<<<(unsigned)B, 256, 0, s>>>(p);
+    if (!wave) align_backtrace_kernel<0><<<(unsigned)B, 256, 0, s>>>(p);
+    else if (p.cfg.K == 4) align_backtrace_kernel<4><<<(unsigned)B, 256, 0, s>>>(p);
+    else align_backtrace_kernel<8><<<(unsigned)B, 256, 0, s>>>(p);
     return check_launch();
 }

@@ -178,6 +178,31 @@ def test_align_long_audio_cluster_sized_labels():
     _check_batch(em, toks, el, tl, tag="L3000 tie")
 
 
+@pytest.mark.parametrize("mode", ["barrier", "S1K4", "S2K4", "S4K4", "S8K4", "S3K8", "S1K8", "stages", "cluster"])
+def test_align_kernel_shapes_agree(mode, monkeypatch):
+    """Every launch shape of the forward kernels gives the same bits: the per-frame-barrier kernel, and the
+    wavefront kernel for 1..8 CTAs per utterance (cluster), 4 or 8 states per lane, minimal ring depth."""
+    from ssak_b200.synth import align_batch
+    env = {"barrier": {"SSAK_ALIGN_WAVE": "0"}, "S1K4": {"SSAK_ALIGN_S": "1", "SSAK_ALIGN_K": "4"},
+           "S2K4": {"SSAK_ALIGN_S": "2", "SSAK_ALIGN_K": "4"}, "S4K4": {"SSAK_ALIGN_S": "4", "SSAK_ALIGN_K": "4"},
+           "S8K4": {"SSAK_ALIGN_S": "8", "SSAK_ALIGN_K": "4"}, "S3K8": {"SSAK_ALIGN_S": "3", "SSAK_ALIGN_K": "8"},
+           "S1K8": {"SSAK_ALIGN_S": "1", "SSAK_ALIGN_K": "8"},
+           "stages": {"SSAK_ALIGN_S": "2", "SSAK_ALIGN_K": "4", "SSAK_ALIGN_STAGES": "5"},
+           "cluster": {"SSAK_ALIGN_S": "4", "SSAK_ALIGN_K": "4", "SSAK_ALIGN_CLUSTER": "1"}}[mode]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for seed, kind in ((61, "planted"), (62, "tie")):
+        em, toks, el, tl = align_batch(3, 700, 50, 150, 520, seed, Tmin=500, kind=kind)
+        tl[0] = 520
+        tl[1] = 33          # most warps / CTAs of this utterance are idle
+        _check_batch(em, toks, el, tl, tag=f"{mode}/{kind}")
+    # T not a multiple of the chunk, T < chunk, first_as_garbage through the cross-CTA seam
+    em, toks, el, tl = align_batch(4, 301, 20, 130, 290, 63, Tmin=5, kind="tie")
+    el[0], tl[0] = 3, 2
+    el[1], tl[1] = 301, 290
+    _check_batch(em, toks, el, tl, fag=True, tag=f"{mode}/ragged")
+
+
 def test_compute_alignments_batched_front_end():
     """compute_alignment from the emission onwards (align_transcriptions.py:310-402), batched: character ->
     token mapping with the loose fall-backs, sentinel character, word regrouping and score aggregation."""

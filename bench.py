@@ -312,6 +312,24 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(out))
 
 
+def _timed_ms(fn, flush, n=7, warm=3):
+    """median device time of fn() over n calls (CUDA events, L2 flushed before each), after `warm` untimed calls
+    (the first calls of a kernel pay its lazy module load)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        flush.add_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
 def extra_numbers(lib, dev, flush):
     """Other configurations of BASELINE.json, device-resident, kernels only (informational)."""
     import ssak_b200
@@ -331,36 +349,59 @@ def extra_numbers(lib, dev, flush):
             del lp_d
         except Exception as e:  # keep the headline line even if an extra shape fails
             res[f"loss_{name}"] = {"error": repr(e)}
+    # f-1: log_softmax + ctc_loss (+ both backwards) against the single logits entry point, C5 shape, torch-facing API
+    try:
+        B, T, V, Lmin, Lmax, Tmin = WORKLOADS["c5"]
+        lp, tg, il, tl, cells = make_batch("c5", 99)
+        logits = (lp * 1.5 + 2.0).to(dev)
+        tg_d, il_d, tl_d = tg.to(dev, torch.int32), il.to(dev, torch.int32), tl.to(dev, torch.int32)
+        del lp
+
+        def unfused():
+            x = logits.detach().requires_grad_(True)
+            ssak_b200.ctc_loss(torch.log_softmax(x, -1), tg_d, il_d, tl_d, 0, "mean", True).backward()
+
+        def fused():
+            x = logits.detach().requires_grad_(True)
+            ssak_b200.ctc_loss_from_logits(x, tg_d, il_d, tl_d, 0, "mean", True).backward()
+
+        tms = {}
+        for nm, fn in (("log_softmax_then_ctc_ms", unfused), ("from_logits_ms", fused)):
+            tms[nm] = _timed_ms(fn, flush)
+        tms["cells_per_s_from_logits"] = cells / (tms["from_logits_ms"] * 1e-3)
+        res["loss_c5_logits"] = tms
+        del logits
+    except Exception as e:
+        res["loss_c5_logits"] = {"error": repr(e)}
     for name, (B, T, V, Lmin, Lmax, Tmin) in {"align_c5": (512, 750, 1024, 100, 200, 600),
-                                               "align_c2shape": (64, 1500, 50, 200, 400, 1200)}.items():
+                                               "align_c2shape": (64, 1500, 50, 200, 400, 1200),
+                                               "align_c3": (16, 30000, 50, 7600, 8000, 30000)}.items():
         try:
             em, toks, el, tl = align_batch(B, T, V, Lmin, Lmax, 5, Tmin=Tmin)
             em_d, toks_d, el_d, tl_d = em.to(dev), toks.to(dev), el.to(dev), tl.to(dev)
-            ts = []
-            for i in range(6):
-                flush.add_(1)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                r = ssak_b200.forced_align(em_d, toks_d, el_d, tl_d)
-                b.record()
-                torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b) * 1e-3)
+            keep = {}
+
+            def run_align():
+                keep["r"] = ssak_b200.forced_align(em_d, toks_d, el_d, tl_d)
+
+            t = _timed_ms(run_align, flush) * 1e-3
+            r = keep["r"]
             cells = int((el.long() * (tl.long() + 1)).sum())
-            t = statistics.mean(ts[1:])
             alg_bytes = 4.0 * float(el.sum()) * V + 4.0 * float((el.long() * (tl.long() + 1)).sum()) / 8 * 2
             res[name] = {"cells_per_s": cells / t, "ms": t * 1e3, "aligned": int((r.status == 0).sum()),
                          "hbm_frac_algorithmic": alg_bytes / t / 1e9 / peaks()[0]}
+            if name == "align_c2shape":   # the CPU port (oracle C, one core) on a bounded sample of the same batch
+                from oracle import oracle as O
+                t0, n_cpu, c_cpu = time.perf_counter(), 0, 0
+                while n_cpu < B and time.perf_counter() - t0 < 5.0:
+                    Tb, Lb = int(el[n_cpu]), int(tl[n_cpu])
+                    O.align(em[n_cpu, :Tb].numpy(), toks[n_cpu, :Lb].tolist(), 0, False)
+                    c_cpu += Tb * (Lb + 1)
+                    n_cpu += 1
+                res[name]["cpu_port"] = {"cells_per_s": c_cpu / (time.perf_counter() - t0), "cores": 1,
+                                         "sample": f"{n_cpu} utterances of this batch, oracle/ssak_oracle.c"}
             if name == "align_c5":   # greedy decode of the same emissions: frames/s and fraction of the HBM roofline
-                ts = []
-                for i in range(6):
-                    flush.add_(1)
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    ids, out, lens = ssak_b200.greedy_ids(em_d, el_d, 0)
-                    b.record()
-                    torch.cuda.synchronize()
-                    ts.append(a.elapsed_time(b) * 1e-3)
-                t = statistics.mean(ts[1:])
+                t = _timed_ms(lambda: ssak_b200.greedy_ids(em_d, el_d, 0), flush) * 1e-3
                 res["greedy_c5"] = {"frames_per_s": B * T / t, "ms": t * 1e3,
                                     "hbm_frac": (4.0 * B * T * V + 8.0 * B * T) / t / 1e9 / peaks()[0]}
             del em_d

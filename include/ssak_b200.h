@@ -105,6 +105,28 @@ SSAK_API int ssak_ctc_loss_backward(const float *grad_out, const float *log_prob
                                     int64_t g_stride_t, int64_t g_stride_b, void *workspace,
                                     size_t workspace_bytes, ssak_stream_t stream);
 
+/* Same pair on RAW LOGITS (the step before the path): replaces
+ *   log_probs = log_softmax(logits, dim=-1) followed by ctc_loss(log_probs, ...)
+ *   (site-packages/transformers/models/wav2vec2/modeling_wav2vec2.py:1725-1736, ssak/infer/general.py:99-101,
+ *    ssak/train/speechbrain/wav2vec_train.py:54).  The log-probabilities are never written to memory: one
+ *   kernel computes the row normalisers [T,B] into the workspace, the lattice kernels form
+ *   x - logsumexp(x) on the fly, and `grad` is d loss / d logits (the a-7 formula is that gradient).
+ *   Arguments, workspace (ssak_ctc_loss_workspace_bytes) and error codes as above. */
+SSAK_API int ssak_ctc_logits_forward(const float *logits, int64_t T, int64_t B, int64_t V,
+                                     int64_t stride_t, int64_t stride_b, const int32_t *targets,
+                                     const int64_t *target_offsets, const int32_t *input_lengths,
+                                     const int32_t *target_lengths, int64_t max_target_len, int32_t blank,
+                                     int32_t save_for_backward, float *neg_log_likelihood, void *workspace,
+                                     size_t workspace_bytes, ssak_stream_t stream);
+
+SSAK_API int ssak_ctc_logits_backward(const float *grad_out, const float *logits, int64_t T, int64_t B,
+                                      int64_t V, int64_t stride_t, int64_t stride_b, const int32_t *targets,
+                                      const int64_t *target_offsets, const int32_t *input_lengths,
+                                      const int32_t *target_lengths, int64_t max_target_len, int32_t blank,
+                                      int32_t zero_infinity, const float *neg_log_likelihood, float *grad,
+                                      int64_t g_stride_t, int64_t g_stride_b, void *workspace,
+                                      size_t workspace_bytes, ssak_stream_t stream);
+
 /* Reduction of aten::ctc_loss (site-packages/torch/nn/functional.py:3042-3115) fused into one launch:
  *   reduction 0 'none' (loss_out[B]), 1 'mean' = mean_b(nll_b / clamp(L_b,1)), 2 'sum',
  *   3 'mean_volume' = sum_b nll_b / sum_b L_b (NeMo, ssak/train/nemo/yamls/model.yaml:3);

@@ -2,6 +2,7 @@
 
 Public API (same call signatures as the reference's call sites, see each module):
     ctc_loss, sb_ctc_loss, install            -- torch.nn.functional.ctc_loss replacement
+    ctc_loss_from_logits                      -- log_softmax + ctc_loss in one (no log-probs in memory)
     forced_align, get_trellis, backtrack,
     merge_repeats, merge_words, Point, Segment -- ssak/utils/align_transcriptions.py
     ctc_greedy_decode, argmax_ids             -- greedy CTC collapse
@@ -12,6 +13,6 @@ from .align import (AlignResult, Point, Segment, Trellis, backtrack, compute_ali
                     compute_alignments, forced_align, get_trellis, loose_get_char_index, merge_repeats, merge_words,
                     segments_from_result)
 from .greedy import argmax_ids, ctc_greedy_decode, greedy_ids, hf_collapse  # noqa: F401
-from .loss import ctc_loss, ctc_neg_log_likelihood, install, sb_ctc_loss, uninstall  # noqa: F401
+from .loss import ctc_loss, ctc_loss_from_logits, ctc_neg_log_likelihood, install, sb_ctc_loss, uninstall  # noqa: F401
 
 __version__ = "0.1.0"

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(32) align_col0_kernel(const AlignParams p) {
             }
             mine = (float)mine_d;
         }
-        if (t < Tb) out[t] = (t + 1 >= Tb + 1 - L) ? INF : mine;
+        if (t < Tb) out[t] = (t + 1 >= Tb + 1 - L) ? INF : mine + 0.0f;  // (+0.0f: a -0.0 becomes +0.0)
     }
 }
 
@@ -625,7 +625,13 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
         }
         const float rk = __shfl_sync(FULL, v[K - 1], (lane + 31) & 31);
         float prev = sel(seam_m, xin, rk);
+        // Decision bits without predicates (FSETP -> SEL pairs serialise on the 7 predicate registers): the sign of
+        // chg - stayed is "changed < stayed", the sign of stayed - chg is "changed > stayed"; a tie gives +0 both
+        // ways and (-inf) - (-inf) gives the positive canonical NaN, i.e. no bit, exactly like the comparisons.
+        // One funnel shift pushes a sign bit into the entry.  (A -0.0 could only enter through a caller-supplied
+        // column 0; the col0 kernel turns it into +0.0.)
         unsigned ng = 0, nl = 0;
+        float stayed_k[K], chg_k[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float ek = *reinterpret_cast<const float *>(row + tok_off[k]);
@@ -636,8 +642,13 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
             float nv = fmaxf(stayed, chg);
             if (k == 0) nv = sel(zero_m, xin, nv);     // column 0 (:37 / :39 / :42)
             v[k] = nv;
-            ng |= chg > stayed ? 1u << k : 0u;
-            nl |= chg < stayed ? 1u << k : 0u;
+            stayed_k[k] = stayed;
+            chg_k[k] = chg;
+        }
+#pragma unroll
+        for (int k = K - 1; k >= 0; --k) {
+            ng = __funnelshift_l(__float_as_uint(stayed_k[k] - chg_k[k]), ng, 1);
+            nl = __funnelshift_l(__float_as_uint(chg_k[k] - stayed_k[k]), nl, 1);
         }
         *bp_ptr = (bp_t)(ng | (nl << K));
         bp_ptr += bp_row;

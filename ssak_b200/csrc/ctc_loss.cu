@@ -79,6 +79,7 @@ struct CtcParams {
     double *nll2;   // [B]    -log2 P (fp64: sum of the offsets + joined frontier)
     float *finals;  // [B][2][row_elems] frontier rows
     float *rows;    // [B][T][row_elems] half lattices (saved for backward)
+    float *zl;      // [T][B] -log2(sum_v exp(x[t,b,v])) when the input holds raw logits, else nullptr
     float *nll;     // [B] out / in
     const float *grad_out;
     float *grad;
@@ -156,7 +157,7 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
 
 // ------------------------------------------------------------------------------ kernel
 // Warp roles: [0, W) recursion; W emission producer; backward only: W+1 lattice-row producer, then G gradient warps.
-template <int K, bool GRAD, int CH>
+template <int K, bool GRAD, int CH, bool LOGITS>
 __global__ void __launch_bounds__(K == 8 ? (GRAD ? 704 : 544) : (GRAD ? 576 : 288), 1)
 ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -467,15 +468,28 @@ ctc_lattice_kernel(const CtcParams p) {
             float xfix = 0.f;
             double base_d = 0.0;
             int pbuf = 0;
+            // raw logits: the row normaliser -log2 sum exp of frame f of the chunk sits in lane f, fetched one
+            // chunk ahead; emissions are x * log2(e) + zl
+            const float *z_ptr = LOGITS ? p.zl + (int64_t)t_first * p.B + b : nullptr;
+            const int64_t z_step = (int64_t)dt * p.B;
+            auto z_fetch = [&](int step0) -> float {
+                const int sidx = step0 + lane;
+                return (LOGITS && lane < CH && sidx < nsteps) ? __ldg(z_ptr + (int64_t)sidx * z_step) : 0.f;
+            };
+            float zv = 0.f, zv_next = z_fetch(0);
+            int step0 = 0;
             // one frame; `n` is the number of frames of the current chunk (a constant CH on the fast path)
             auto frame = [&](const int f, const int n) {
                 // the bulk copy lands the row (addr & 15) bytes into its slot; raw natural-log values
                 const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
-                const float eb2 = fmaxf(*reinterpret_cast<const float *>(row + blank_off) * kLog2e, kNeg);
+                const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
+                const float eb2 = fmaxf(LOGITS ? fmaf(*reinterpret_cast<const float *>(row + blank_off), kLog2e, zl)
+                                               : *reinterpret_cast<const float *>(row + blank_off) * kLog2e, kNeg);
                 float el2[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k)
-                    el2[k] = fmaxf(*reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
+                    el2[k] = fmaxf(LOGITS ? fmaf(*reinterpret_cast<const float *>(row + lab_off[k]), kLog2e, zl)
+                                          : *reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
                 float xin = x_in[(f & 1) * 18];
                 if (f == 0) xin -= xfix;
                 float r[K];
@@ -554,6 +568,11 @@ ctc_lattice_kernel(const CtcParams p) {
             };
             while (remaining > 0) {
                 const int n = remaining < CH ? remaining : CH;
+                if (LOGITS) {
+                    zv = zv_next;
+                    step0 += CH;
+                    zv_next = z_fetch(step0);
+                }
                 mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
                 xfix = 0.f;  // correction for the seam value written before the re-centring
                 if (!first_chunk) {
@@ -616,12 +635,24 @@ ctc_lattice_kernel(const CtcParams p) {
             return rsum;
         };
         int remaining = nsteps, chunk_idx = 0;
+        const float *z_ptr = LOGITS ? p.zl + (int64_t)t_first * p.B + b : nullptr;
+        const int64_t z_step = (int64_t)dt * p.B;
+        auto z_fetch = [&](int step0) -> float {
+            const int sidx = step0 + lane;
+            return (LOGITS && lane < CH && sidx < nsteps) ? __ldg(z_ptr + (int64_t)sidx * z_step) : 0.f;
+        };
+        float zv = 0.f, zv_next = z_fetch(0);
         while (remaining > 0) {
             const int n = remaining < CH ? remaining : CH;
+            if (LOGITS) {
+                zv = zv_next;
+                zv_next = z_fetch((chunk_idx + 1) * CH);
+            }
             mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
             const int pbuf = (chunk_idx & 1) * CH;
             for (int f = gwarp; f < n; f += G) {
                 const int slot = pbuf + f;
+                const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
                 mbar_wait(&post_full[slot], (uint32_t)((chunk_idx >> 1) & 1));
                 const float *w = wlab + slot * WL;
                 const unsigned char *rowb = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
@@ -632,8 +663,8 @@ ctc_lattice_kernel(const CtcParams p) {
                     float4 *g4 = reinterpret_cast<float4 *>(grow);
                     for (int it = lane; it < ncols; it += 32) {
                         const float4 x = row4[it];
-                        g4[it] = make_float4(ex2_approx(x.x * kLog2e) * gs, ex2_approx(x.y * kLog2e) * gs,
-                                             ex2_approx(x.z * kLog2e) * gs, ex2_approx(x.w * kLog2e) * gs);
+                        g4[it] = make_float4(ex2_approx(fmaf(x.x, kLog2e, zl)) * gs, ex2_approx(fmaf(x.y, kLog2e, zl)) * gs,
+                                             ex2_approx(fmaf(x.z, kLog2e, zl)) * gs, ex2_approx(fmaf(x.w, kLog2e, zl)) * gs);
                     }
                     __syncwarp();  // orders the dense stores before the overwrites below (same warp)
                     // sparse pass: the few columns that carry posterior mass, one per lane
@@ -641,13 +672,13 @@ ctc_lattice_kernel(const CtcParams p) {
                     const int np = occ_start[V + 1];
                     for (int i = lane; i < np; i += 32) {
                         const int cc = cursor[i];
-                        grow[cc] = (ex2_approx(row[cc] * kLog2e) - label_mass(cc, w, slot)) * gs;
+                        grow[cc] = (ex2_approx(fmaf(row[cc], kLog2e, zl)) - label_mass(cc, w, slot)) * gs;
                     }
                 } else {
                     const float *row = reinterpret_cast<const float *>(rowb);
                     int j = 0;
                     for (int cc = lane; cc < V; cc += 32, ++j) {
-                        float val = ex2_approx(row[cc] * kLog2e);
+                        float val = ex2_approx(fmaf(row[cc], kLog2e, zl));
                         if (j >= 32 || ((present >> j) & 1u)) val -= label_mass(cc, w, slot);
                         grow[cc] = val * gs;
                     }
@@ -782,6 +813,47 @@ __global__ void __launch_bounds__(256) ctc_reduce_kernel(const float *nll, const
         }
 }
 
+// Row normalisers for the logits entry points (the step before the path, SURVEY 8 f-1: F.log_softmax at
+// modeling_wav2vec2.py:1725 / ssak/infer/general.py:99-101): zl[t,b] = -log2 sum_v exp(x[t,b,v]) for t < T_b.
+// One warp per row, tiles of 256 columns, running (max, sum) merged per tile: one MUFU per element.  The log-probs
+// themselves are never written: the lattice kernels form x * log2(e) + zl on the fly.
+__global__ void __launch_bounds__(256) ctc_row_lse_kernel(const CtcParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= p.T * p.B) return;
+    const int64_t t = row / p.B, b = row % p.B;
+    int Tb = p.in_len[b];
+    Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
+    if (t >= Tb) {
+        if (lane == 0) p.zl[row] = 0.f;
+        return;
+    }
+    const float *x = p.lp + t * p.st + b * p.sb;
+    const int V = p.V;
+    float m = kNeg, s = 0.f;  // running max (log2 domain) and sum of 2^(x log2e - m)
+    for (int v0 = 0; v0 < V; v0 += 256) {
+        float xv[8];
+        float tm = kNeg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int v = v0 + i * 32 + lane;
+            xv[i] = v < V ? fmaxf(__ldg(x + v) * kLog2e, kNeg) : kNeg;
+            tm = fmaxf(tm, xv[i]);
+        }
+        const float nm = fmaxf(m, tm);
+        float ts = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ts += ex2_approx(xv[i] - nm);
+        s = s * ex2_approx(m - nm) + ts;
+        m = nm;
+    }
+    const float M = warp_max(m);
+    s *= ex2_approx(m - M);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) p.zl[row] = -(M + lg2_approx(s));
+}
+
 // ---------------------------------------------------------------------------- launchers
 template <bool GRAD>
 static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
@@ -789,17 +861,19 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     const size_t smem_bytes = smem_bytes_for(c, p.V, p.Lmax, GRAD);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
     dim3 grid((unsigned)p.B, 2), block((c.W + (GRAD ? 2 + c.G : 1)) * 32);
-#define SSAK_LAUNCH2(KK, CC)                                                                   \
+#define SSAK_LAUNCH3(KK, CC, ZZ)                                                               \
     {                                                                                          \
-        auto kern = ctc_lattice_kernel<KK, GRAD, CC>;                                          \
+        auto kern = ctc_lattice_kernel<KK, GRAD, CC, ZZ>;                                      \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem_bytes);                                 \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
         kern<<<grid, block, smem_bytes, stream>>>(p);                                          \
     }
+#define SSAK_LAUNCH2(KK, CC)                                                                   \
+    if (p.zl) SSAK_LAUNCH3(KK, CC, true) else SSAK_LAUNCH3(KK, CC, false)
 #define SSAK_LAUNCH(KK)                                                                        \
     case KK:                                                                                   \
-        if (c.chunk == 8) SSAK_LAUNCH2(KK, 8) else SSAK_LAUNCH2(KK, 4)                         \
+        if (c.chunk == 8) { SSAK_LAUNCH2(KK, 8) } else { SSAK_LAUNCH2(KK, 4) }                 \
         break;
     switch (c.K) {
         SSAK_LAUNCH(1)
@@ -808,17 +882,19 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
         SSAK_LAUNCH(8)
         default: return SSAK_ERR_UNSUPPORTED;
     }
+#undef SSAK_LAUNCH3
 #undef SSAK_LAUNCH2
 #undef SSAK_LAUNCH
     return check_launch();
 }
 
-struct WsLayout { size_t nll2, finals, rows, total; };
+struct WsLayout { size_t nll2, finals, zl, rows, total; };
 static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
     WsLayout w;
     size_t o = 0;
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
+    w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
     w.rows = o;   if (saved) o += align_up((size_t)B * (size_t)T * row_elems * sizeof(float), 256);
     w.total = o + 256;
     return w;
@@ -827,7 +903,7 @@ static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
 static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t B, int64_t V,
                        int64_t st, int64_t sb, const int32_t *targets, const int64_t *tgt_off,
                        const int32_t *in_len, const int32_t *tgt_len, int64_t Lmax, int32_t blank,
-                       void *workspace, size_t workspace_bytes, bool saved) {
+                       void *workspace, size_t workspace_bytes, bool saved, bool logits) {
     if (!log_probs || !targets || !tgt_off || !in_len || !tgt_len || !workspace)
         return SSAK_ERR_INVALID_ARGUMENT;
     if (T < 0 || B <= 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V || T > 0x7ffffff0 ||
@@ -844,6 +920,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->nll2 = reinterpret_cast<double *>(ws + w.nll2);
     p->finals = reinterpret_cast<float *>(ws + w.finals);
     p->rows = saved ? reinterpret_cast<float *>(ws + w.rows) : nullptr;
+    p->zl = logits ? reinterpret_cast<float *>(ws + w.zl) : nullptr;
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
     return SSAK_OK;
@@ -860,6 +937,46 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
     return ws_layout(T, B, c.row_elems, save_for_backward != 0).total;
 }
 
+static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,
+                        const int32_t *targets, const int64_t *target_offsets, const int32_t *input_lengths,
+                        const int32_t *target_lengths, int64_t max_target_len, int32_t blank,
+                        int32_t save_for_backward, float *neg_log_likelihood, void *workspace,
+                        size_t workspace_bytes, ssak_stream_t stream, bool logits) {
+    CtcParams p;
+    if (!neg_log_likelihood) return SSAK_ERR_INVALID_ARGUMENT;
+    int rc = fill_params(&p, x, T, B, V, st, sb, targets, target_offsets, input_lengths, target_lengths,
+                         max_target_len, blank, workspace, workspace_bytes, save_for_backward != 0, logits);
+    if (rc != SSAK_OK) return rc;
+    p.nll = neg_log_likelihood;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (logits && T > 0) {
+        ctc_row_lse_kernel<<<(unsigned)((T * B + 7) / 8), 256, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != SSAK_OK) return rc;
+    }
+    rc = launch_lattice<false>(p, s);
+    if (rc != SSAK_OK) return rc;
+    ctc_join_kernel<<<(unsigned)B, 256, 0, s>>>(p);
+    return check_launch();
+}
+
+static int backward_impl(const float *grad_out, const float *x, int64_t T, int64_t B, int64_t V, int64_t st,
+                         int64_t sb, const int32_t *targets, const int64_t *target_offsets,
+                         const int32_t *input_lengths, const int32_t *target_lengths, int64_t max_target_len,
+                         int32_t blank, int32_t zero_infinity, const float *neg_log_likelihood, float *grad,
+                         int64_t g_stride_t, int64_t g_stride_b, void *workspace, size_t workspace_bytes,
+                         ssak_stream_t stream, bool logits) {
+    CtcParams p;
+    if (!grad_out || !neg_log_likelihood || !grad) return SSAK_ERR_INVALID_ARGUMENT;
+    int rc = fill_params(&p, x, T, B, V, st, sb, targets, target_offsets, input_lengths, target_lengths,
+                         max_target_len, blank, workspace, workspace_bytes, true, logits);
+    if (rc != SSAK_OK) return rc;
+    p.nll = const_cast<float *>(neg_log_likelihood);
+    p.grad_out = grad_out; p.grad = grad; p.gst = g_stride_t; p.gsb = g_stride_b;
+    p.zero_inf = zero_infinity;
+    return launch_lattice<true>(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t B, int64_t V,
                                      int64_t lp_stride_t, int64_t lp_stride_b,
                                      const int32_t *targets, const int64_t *target_offsets,
@@ -868,18 +985,9 @@ extern "C" int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t 
                                      int32_t save_for_backward, float *neg_log_likelihood,
                                      void *workspace, size_t workspace_bytes,
                                      ssak_stream_t stream) {
-    CtcParams p;
-    if (!neg_log_likelihood) return SSAK_ERR_INVALID_ARGUMENT;
-    int rc = fill_params(&p, log_probs, T, B, V, lp_stride_t, lp_stride_b, targets, target_offsets,
-                         input_lengths, target_lengths, max_target_len, blank, workspace,
-                         workspace_bytes, save_for_backward != 0);
-    if (rc != SSAK_OK) return rc;
-    p.nll = neg_log_likelihood;
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    rc = launch_lattice<false>(p, s);
-    if (rc != SSAK_OK) return rc;
-    ctc_join_kernel<<<(unsigned)B, 256, 0, s>>>(p);
-    return check_launch();
+    return forward_impl(log_probs, T, B, V, lp_stride_t, lp_stride_b, targets, target_offsets, input_lengths,
+                        target_lengths, max_target_len, blank, save_for_backward, neg_log_likelihood, workspace,
+                        workspace_bytes, stream, false);
 }
 
 extern "C" int ssak_ctc_loss_backward(const float *grad_out, const float *log_probs, int64_t T,
@@ -891,16 +999,32 @@ extern "C" int ssak_ctc_loss_backward(const float *grad_out, const float *log_pr
                                       const float *neg_log_likelihood, float *grad,
                                       int64_t g_stride_t, int64_t g_stride_b, void *workspace,
                                       size_t workspace_bytes, ssak_stream_t stream) {
-    CtcParams p;
-    if (!grad_out || !neg_log_likelihood || !grad) return SSAK_ERR_INVALID_ARGUMENT;
-    int rc = fill_params(&p, log_probs, T, B, V, lp_stride_t, lp_stride_b, targets, target_offsets,
-                         input_lengths, target_lengths, max_target_len, blank, workspace,
-                         workspace_bytes, true);
-    if (rc != SSAK_OK) return rc;
-    p.nll = const_cast<float *>(neg_log_likelihood);
-    p.grad_out = grad_out; p.grad = grad; p.gst = g_stride_t; p.gsb = g_stride_b;
-    p.zero_inf = zero_infinity;
-    return launch_lattice<true>(p, reinterpret_cast<cudaStream_t>(stream));
+    return backward_impl(grad_out, log_probs, T, B, V, lp_stride_t, lp_stride_b, targets, target_offsets,
+                         input_lengths, target_lengths, max_target_len, blank, zero_infinity, neg_log_likelihood,
+                         grad, g_stride_t, g_stride_b, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int ssak_ctc_logits_forward(const float *logits, int64_t T, int64_t B, int64_t V,
+                                       int64_t stride_t, int64_t stride_b, const int32_t *targets,
+                                       const int64_t *target_offsets, const int32_t *input_lengths,
+                                       const int32_t *target_lengths, int64_t max_target_len, int32_t blank,
+                                       int32_t save_for_backward, float *neg_log_likelihood, void *workspace,
+                                       size_t workspace_bytes, ssak_stream_t stream) {
+    return forward_impl(logits, T, B, V, stride_t, stride_b, targets, target_offsets, input_lengths,
+                        target_lengths, max_target_len, blank, save_for_backward, neg_log_likelihood, workspace,
+                        workspace_bytes, stream, true);
+}
+
+extern "C" int ssak_ctc_logits_backward(const float *grad_out, const float *logits, int64_t T, int64_t B,
+                                        int64_t V, int64_t stride_t, int64_t stride_b, const int32_t *targets,
+                                        const int64_t *target_offsets, const int32_t *input_lengths,
+                                        const int32_t *target_lengths, int64_t max_target_len, int32_t blank,
+                                        int32_t zero_infinity, const float *neg_log_likelihood, float *grad,
+                                        int64_t g_stride_t, int64_t g_stride_b, void *workspace,
+                                        size_t workspace_bytes, ssak_stream_t stream) {
+    return backward_impl(grad_out, logits, T, B, V, stride_t, stride_b, targets, target_offsets, input_lengths,
+                         target_lengths, max_target_len, blank, zero_infinity, neg_log_likelihood, grad,
+                         g_stride_t, g_stride_b, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int ssak_ctc_loss_reduce(const float *neg_log_likelihood, const int32_t *target_lengths,

@@ -59,7 +59,7 @@ class _CTCLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity,
-                reduction):
+                reduction, from_logits=False):
         L = _lib.lib()
         T, B, V = log_probs.shape
         dev = log_probs.device
@@ -74,23 +74,24 @@ class _CTCLossFunction(torch.autograd.Function):
         loss = torch.empty(B if red == 0 else (), dtype=torch.float32, device=dev)
         gscale = torch.empty(B, dtype=torch.float32, device=dev) if save else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = L.ssak_ctc_loss_forward(log_probs.data_ptr(), T, B, V, log_probs.stride(0), log_probs.stride(1),
-                                     targets.data_ptr(), tgt_off.data_ptr(), in_len.data_ptr(),
-                                     tgt_len.data_ptr(), max_target_len, blank, int(save), nll.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, stream)
-        _lib.check(rc, "ssak_ctc_loss_forward")
+        fwd = L.ssak_ctc_logits_forward if from_logits else L.ssak_ctc_loss_forward
+        rc = fwd(log_probs.data_ptr(), T, B, V, log_probs.stride(0), log_probs.stride(1),
+                 targets.data_ptr(), tgt_off.data_ptr(), in_len.data_ptr(),
+                 tgt_len.data_ptr(), max_target_len, blank, int(save), nll.data_ptr(),
+                 ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "ssak_ctc_logits_forward" if from_logits else "ssak_ctc_loss_forward")
         rc = L.ssak_ctc_loss_reduce(nll.data_ptr(), tgt_len.data_ptr(), B, red, int(zero_infinity),
                                     loss.data_ptr(), _lib.ptr(gscale), stream)
         _lib.check(rc, "ssak_ctc_loss_reduce")
         if save:
             ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale)
-            ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes)
+            ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes, from_logits)
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
         log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale = ctx.saved_tensors
-        max_target_len, blank, zero_infinity, ws_bytes = ctx.meta
+        max_target_len, blank, zero_infinity, ws_bytes, from_logits = ctx.meta
         L = _lib.lib()
         T, B, V = log_probs.shape
         g = (gscale * grad_loss.to(torch.float32)).contiguous()   # [B]: upstream x d loss / d nll_b
@@ -101,13 +102,14 @@ class _CTCLossFunction(torch.autograd.Function):
             grad = torch.empty((T, B, V), dtype=torch.float32, device=log_probs.device)
         with torch.cuda.device(log_probs.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rc = L.ssak_ctc_loss_backward(g.data_ptr(), log_probs.data_ptr(), T, B, V, log_probs.stride(0),
-                                          log_probs.stride(1), targets.data_ptr(), tgt_off.data_ptr(),
-                                          in_len.data_ptr(), tgt_len.data_ptr(), max_target_len, blank,
-                                          int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
-                                          grad.stride(1), ws.data_ptr(), ws_bytes, stream)
-        _lib.check(rc, "ssak_ctc_loss_backward")
-        return grad, None, None, None, None, None, None, None, None
+            bwd = L.ssak_ctc_logits_backward if from_logits else L.ssak_ctc_loss_backward
+            rc = bwd(g.data_ptr(), log_probs.data_ptr(), T, B, V, log_probs.stride(0),
+                     log_probs.stride(1), targets.data_ptr(), tgt_off.data_ptr(),
+                     in_len.data_ptr(), tgt_len.data_ptr(), max_target_len, blank,
+                     int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
+                     grad.stride(1), ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "ssak_ctc_logits_backward" if from_logits else "ssak_ctc_loss_backward")
+        return grad, None, None, None, None, None, None, None, None, None
 
 
 def _prepare(log_probs, targets, input_lengths, target_lengths, blank):
@@ -185,6 +187,24 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reducti
     with torch.cuda.device(lp.device):
         out = _CTCLossFunction.apply(lp, tg, tgt_off, in_len, tgt_len, lmax, int(blank), bool(zero_infinity),
                                      reduction)
+    return out[0] if (unbatched and reduction == "none") else out
+
+
+def ctc_loss_from_logits(logits, targets, input_lengths, target_lengths, blank=0, reduction="mean",
+                         zero_infinity=False):
+    """`ctc_loss(log_softmax(logits, -1), ...)` without materialising the log-probabilities.
+
+    Replaces the pair at site-packages/transformers/models/wav2vec2/modeling_wav2vec2.py:1725-1736 (and
+    ssak/train/speechbrain/wav2vec_train.py:54 + :66): `logits` [T,B,V] fp32 (any strides in T and B), the
+    result is differentiable w.r.t. `logits`.  One extra kernel computes the [T,B] row normalisers; the lattice
+    kernels read the logits themselves, so a full write + read of the [T,B,V] log-probabilities disappears."""
+    if reduction not in _REDUCTIONS:
+        raise ValueError(f"{reduction} is not a valid value for reduction")
+    unbatched = isinstance(logits, torch.Tensor) and logits.dim() == 2
+    x, tg, tgt_off, in_len, tgt_len, lmax = _prepare(logits, targets, input_lengths, target_lengths, blank)
+    with torch.cuda.device(x.device):
+        out = _CTCLossFunction.apply(x, tg, tgt_off, in_len, tgt_len, lmax, int(blank), bool(zero_infinity),
+                                     reduction, True)
     return out[0] if (unbatched and reduction == "none") else out
 
 

@@ -17,7 +17,8 @@ def _header_symbols():
 
 def test_header_declares_expected_entry_points():
     syms = _header_symbols()
-    for name in ("ssak_ctc_loss_forward", "ssak_ctc_loss_backward", "ssak_forced_align", "ssak_ctc_greedy",
+    for name in ("ssak_ctc_loss_forward", "ssak_ctc_loss_backward", "ssak_ctc_logits_forward",
+                 "ssak_ctc_logits_backward", "ssak_forced_align", "ssak_ctc_greedy",
                  "ssak_ctc_loss_host", "ssak_forced_align_host", "ssak_ctc_greedy_host", "ssak_b200_version"):
         assert name in syms
 

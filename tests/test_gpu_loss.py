@@ -235,3 +235,38 @@ def test_loss_aten_level_install():
     """ % __import__("conftest").ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "aten ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("layout", ["tbv", "btv_view"])
+def test_loss_from_logits_matches_log_softmax_then_ctc(layout):
+    """ctc_loss_from_logits(x) == F.ctc_loss(F.log_softmax(x, -1)) (fp64 CPU truth), gradient w.r.t.
+    the LOGITS, without the log-probabilities ever being written; raw logits of any scale / offset per row."""
+    import ssak_b200
+    from ssak_b200.synth import ctc_batch
+    g = torch.Generator().manual_seed(5)
+    for seed, (B, T, V, Lmin, Lmax) in enumerate([(5, 60, 20, 0, 12), (6, 150, 50, 10, 40), (3, 70, 1024, 3, 30),
+                                                   (2, 300, 257, 100, 140)]):
+        lp, tg, il, tl = ctc_batch(B, T, V, Lmin, Lmax, 300 + seed, Tmin=T // 2)
+        # un-normalise: per-row offsets and a global scale, as an acoustic model's logits would be
+        logits = lp * 1.7 + 4.0 * torch.randn(T, B, 1, generator=g) + 3.0
+        for red, zi in (("mean", True), ("sum", False), ("none", True)):
+            if layout == "tbv":
+                x = logits.cuda().requires_grad_(True)
+                loss = ssak_b200.ctc_loss_from_logits(x, tg, il, tl, 0, red, zi)
+                loss.sum().backward()
+                grad = x.grad.cpu()
+            else:   # the HF call: [B,T,V] logits, transposed view handed to the loss
+                xb = logits.transpose(0, 1).contiguous().cuda().requires_grad_(True)
+                loss = ssak_b200.ctc_loss_from_logits(xb.transpose(0, 1), tg, il, tl, 0, red, zi)
+                loss.sum().backward()
+                grad = xb.grad.transpose(0, 1).cpu()
+            ref_x = logits.double().clone().requires_grad_(True)
+            ref = F.ctc_loss(F.log_softmax(ref_x, -1), tg, il, tl, 0, red, zi)
+            ref.sum().backward()
+            _assert_close(loss.detach().cpu(), grad, ref.detach(), ref_x.grad, f"logits {layout}/{seed}/{red}")
+            assert (grad[int(il[0]):, 0] == 0).all()
+    # agreement of the two entry points on the same normalised input (x = log-probs: normaliser ~ 0)
+    lp, tg, il, tl = ctc_batch(4, 200, 50, 20, 60, 311, Tmin=150)
+    a = ssak_b200.ctc_loss_from_logits(lp.cuda(), tg, il, tl, 0, "none", True)
+    b = ssak_b200.ctc_loss(lp.cuda(), tg, il, tl, 0, "none", True)
+    assert torch.allclose(a, b, rtol=1e-6, atol=0)

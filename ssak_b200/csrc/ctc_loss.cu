@@ -160,7 +160,7 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
 template <int K, bool GRAD, int CH, bool LOGITS>
 __global__ void __launch_bounds__(K == 8 ? (GRAD ? 704 : 544) : (GRAD ? 576 : 288), 1)
 ctc_lattice_kernel(const CtcParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const CtcCfg &c = p.cfg;
     const int b = blockIdx.x;
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (backward in time)
@@ -359,7 +359,7 @@ ctc_lattice_kernel(const CtcParams p) {
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
             if (GRAD) {
-                ab[k] = fin[pp];
+                ab[k] = pp <= L ? fin[pp] : kNeg;                                        // pairs beyond L
                 al[k] = lab_off[k] == c.slot_bytes - 16 ? kNeg : fin[lab_pos + k * 32];  // states beyond 2L+1
             } else {
                 ab[k] = pp == (dir ? L : 0) ? 0.f : kNeg;
@@ -427,11 +427,12 @@ ctc_lattice_kernel(const CtcParams p) {
     const int blank_off = 4 * p.blank;
     const unsigned a15_0 = (unsigned)(reinterpret_cast<uintptr_t>(first_row) & 15);
     const unsigned a15_step = (unsigned)((step_elems * 4) & 15);  // CH * a15_step % 16 == 0
-    unsigned skip_m[K];
+    unsigned skip_m[K], bl_m[K];  // bl_m: my k-th blank state exists (pair <= L)
     int wl_off[K];  // byte offset of my label posterior in the label-sorted buffer (backward)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         skip_m[k] = (skipmask >> k) & 1u ? 0xffffffffu : 0u;
+        bl_m[k] = pbase + k * 32 <= L ? 0xffffffffu : 0u;
         wl_off[k] = 4 * (WL - 1);  // dump slot for the states beyond 2L+1
         if (GRAD && compute) {
             const int li = dir ? pbase + k * 32 - 1 : pbase + k * 32;
@@ -540,7 +541,8 @@ ctc_lattice_kernel(const CtcParams p) {
                     float sbl = 0.f;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        sbl += ex2_approx(ab[k] + orow[k * 32] + cb);
+                        // (the other direction's row holds nothing for the pairs beyond L)
+                        sbl += ex2_approx(ab[k] + sel(bl_m[k], orow[k * 32], kNeg) + cb);
                         *reinterpret_cast<float *>(wl + wl_off[k]) =
                             ex2_approx(al[k] + orow[lab_delta + k * 32] + (bracket - el2[k]));
                     }
@@ -718,6 +720,296 @@ ctc_lattice_kernel(const CtcParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------ wavefront forward kernel
+// The forward launch (half lattices + frontier rows) without the per-frame barrier: chain element c -- the pair
+// (blank, label) number c in recursion order, i.e. pair c for alpha and pair L-c for beta -- depends on elements
+// c and c-1 of the previous frame only, so recursion warp w needs ONE value per frame from warp w-1.  Warps run
+// skewed in time: warp w-1 streams its last label state ("seam") chunk by chunk into a small shared-memory ring
+// whose words validate themselves (a NaN pattern = "not there yet", no flag / fence / barrier), warp w follows
+// a chunk or two behind.  Lanes own K CONSECUTIVE chain elements (one shuffle per frame instead of K), the frame
+// body is branch-free and unrolled over the chunk, stores to shared memory happen once per chunk.
+//   Re-centring is per warp and by INTEGER amounts (exact in fp32; offsets add up exactly in int32): every chunk a
+// warp subtracts floor(max of its states).  With the seam values travel the sender's offset and the offset of
+// the chain's first warp; the latter is the one offset stored with every saved row, values are converted on the
+// way out (v + (off_w - off_row)), so the row format is exactly what ctc_lattice_kernel<.., GRAD> and
+// ctc_join_kernel read.
+struct FwdWaveSmem {
+    int em_full, em_empty, seam, ring, total;
+};
+__host__ __device__ __forceinline__ FwdWaveSmem fwd_wave_smem(int W, int stages, int chunk, int slot_bytes) {
+    FwdWaveSmem m;
+    m.em_full = 0;
+    m.em_empty = 8 * stages;
+    m.seam = 16 * stages;                                        // [W+1][stages+1][chunk+2] words
+    m.ring = (m.seam + 4 * (W + 1) * (stages + 1) * (chunk + 2) + 127) & ~127;
+    m.total = m.ring + stages * chunk * slot_bytes;
+    return m;
+}
+constexpr uint32_t kSeamEmptyBits = 0xffffffffu;
+__device__ __forceinline__ float ld_volatile_shared_f32(const float *p) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+struct FwdWaveCfg {
+    int K, W, stages, chunk, slot_bytes;
+};
+
+template <int K, int CH, bool LOGITS, bool SAVE>
+__global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel(const CtcParams p, const FwdWaveCfg wc) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int b = blockIdx.x, dir = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int W = wc.W;
+    const float EMPTY = __uint_as_float(kSeamEmptyBits);
+
+    int Tb = p.in_len[b];
+    Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
+    int L = p.tgt_len[b];
+    L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
+    const int m = Tb >> 1;
+    const int nsteps = dir ? Tb - m : m;            // frames this direction owns in forward()
+    const int P_pad = p.cfg.P_pad, row_elems = p.cfg.row_elems;
+    const int V = p.V;
+    const float *lp_b = p.lp + (int64_t)b * p.sb;
+    const int32_t *tg = p.targets + p.tgt_off[b];
+    const int t_first = dir ? Tb - 1 : 0;
+    const int dt = dir ? -1 : 1;
+
+    int wlive = L / (32 * K) + 1;                   // chain elements 0..L
+    wlive = wlive > W ? W : wlive;
+    const bool compute = warp < wlive;
+
+    const int NST = wc.stages, NSLOT = NST + 1, slot_bytes = wc.slot_bytes, SW = CH + 2;
+    const FwdWaveSmem lay = fwd_wave_smem(W, NST, CH, slot_bytes);
+    uint64_t *em_full = reinterpret_cast<uint64_t *>(smem + lay.em_full);
+    uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + lay.em_empty);
+    float *seam = reinterpret_cast<float *>(smem + lay.seam);  // [W+1][NSLOT][SW]
+    RowRing ring;
+    ring.slots = smem + lay.ring;
+    ring.full = em_full;
+    ring.chunk = CH;
+    ring.stages = NST;
+    ring.slot_bytes = slot_bytes;
+    ring.row_bytes = 4 * V;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&em_full[s], 1);
+            mbar_init(&em_empty[s], wlive);
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < (W + 1) * NSLOT * SW; i += blockDim.x) seam[i] = EMPTY;
+    // sentinel emission log(0) for the chain elements beyond L: the last 16 bytes of a slot are never written
+    for (int i = tid; i < NST * CH * 4; i += blockDim.x)
+        *reinterpret_cast<float *>(ring.slots + (size_t)(i >> 2) * slot_bytes + slot_bytes - 16 + (i & 3) * 4) = kNeg;
+    __syncthreads();  // the only CTA-wide barrier
+    if (warp >= wlive && warp != W) return;
+
+    const int nchunks = (nsteps + CH - 1) / CH;
+    const int64_t step_elems = (int64_t)dt * p.st;
+    const float *first_row = lp_b + (int64_t)t_first * p.st;
+    if (!compute) {
+        // ================= producer warp =================
+        RingProducer prod;
+        prod.src = first_row;
+        prod.step_elems = step_elems;
+        prod.stage = 0;
+        prod.remaining = nsteps;
+        int round = 0;
+        for (int n = 0; n < nchunks; ++n) {
+            if (round > 0) mbar_wait(&em_empty[prod.stage], (uint32_t)((round - 1) & 1));
+            const int stg = prod.stage;
+            if (lane == 0) ring_issue_next(ring, prod);
+            prod.stage = __shfl_sync(FULL, prod.stage, 0);
+            if (prod.stage <= stg) ++round;
+        }
+        return;
+    }
+
+    // ================= recursion warps =================
+    // chain element c: alpha -> (blank c, label c); beta -> (blank L-c, label L-c-1)
+    const int cbase = warp * 32 * K + lane * K;
+    int lab_off[K], bpos[K], lpos[K];
+    unsigned skip_m[K];
+    float ab[K], al[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = cbase + k;
+        const int li = dir ? L - c - 1 : c;          // natural index of my label
+        int off = slot_bytes - 16;                   // sentinel word: emission log(0)
+        skip_m[k] = 0u;
+        if (c <= L && li >= 0 && li < L) {
+            int l = tg[li];
+            l = l < 0 ? 0 : (l >= V ? V - 1 : l);
+            off = 4 * l;
+            const int lo = dir ? li + 1 : li - 1;    // the label a skip transition comes from
+            if (lo >= 0 && lo < L) {
+                int l2 = tg[lo];
+                l2 = l2 < 0 ? 0 : (l2 >= V ? V - 1 : l2);
+                if (l2 != l) skip_m[k] = 0xffffffffu;
+            }
+        }
+        lab_off[k] = off;
+        // row positions; states that do not exist go to the spare word [P_pad], which nobody reads for real
+        bpos[k] = c <= L ? (dir ? L - c : c) : P_pad;
+        lpos[k] = (c <= L && li >= 0 && li < L) ? P_pad + 1 + li : P_pad;
+        ab[k] = c == 0 ? 0.f : kNeg;                 // virtual start row
+        al[k] = kNeg;
+    }
+    const bool first = warp == 0;
+    const bool dn_live = (warp + 1) * 32 * K <= L;   // a live downstream warp reads my seam
+    const float *sv_in = seam + (warp - 1) * NSLOT * SW;
+    float *sv_out = seam + (dn_live ? warp : W) * NSLOT * SW;
+    const bool is31 = lane == 31;
+    const unsigned seam_m = lane == 0 ? 0xffffffffu : 0u;
+    auto sel = [](unsigned mm, float a, float bb) {
+        return __int_as_float((__float_as_int(a) & mm) | (__float_as_int(bb) & ~mm));
+    };
+    const int blank_off = 4 * p.blank;
+    const unsigned a15_0 = (unsigned)(reinterpret_cast<uintptr_t>(first_row) & 15);
+    const unsigned a15_step = (unsigned)((step_elems * 4) & 15);
+    float *row_out = SAVE ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
+    const int64_t row_step = (int64_t)dt * row_elems;
+    const unsigned char *em_base = ring.slots, *em_chunk = em_base;
+    int em_stage = 0, em_phase = 0, remaining = nsteps, sslot = 0, step0 = 0;
+    int off_me = 0, off_row = 0;                     // integer log2 offsets: true value = state + off
+    float ds = 0.f;                                  // off_me - off_row: conversion to the stored row's offset
+    double off_row_d = 0.0;
+    const bool inlane = lane < SW;
+    auto fetch_seam = [&](int slot) -> float {
+        return (!first && inlane) ? ld_volatile_shared_f32(sv_in + slot * SW + lane) : kNeg;
+    };
+    float sv_pre = fetch_seam(0);
+    const float *z_ptr = LOGITS ? p.zl + (int64_t)t_first * p.B + b : nullptr;
+    const int64_t z_step = (int64_t)dt * p.B;
+    auto z_fetch = [&](int s0) -> float {
+        const int sidx = s0 + lane;
+        return (LOGITS && lane < CH && sidx < nsteps) ? __ldg(z_ptr + (int64_t)sidx * z_step) : 0.f;
+    };
+    float zv = 0.f, zv_next = z_fetch(0);
+
+    float sout[CH];
+    auto frame = [&](const int f, const float sv, auto direct_tag) {
+        constexpr bool DIRECT = decltype(direct_tag)::value;
+        const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
+        const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
+        const float xb = *reinterpret_cast<const float *>(row + blank_off);
+        const float eb2 = fmaxf(LOGITS ? fmaf(xb, kLog2e, zl) : xb * kLog2e, kNeg);
+        float el2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float x = *reinterpret_cast<const float *>(row + lab_off[k]);
+            el2[k] = fmaxf(LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e, kNeg);
+        }
+        const float xin = __shfl_sync(FULL, sv, f);
+        if (DIRECT) {
+            if (is31) sv_out[sslot * SW + f] = al[K - 1];
+        } else {
+            sout[f] = al[K - 1];
+        }
+        const float rk = __shfl_sync(FULL, al[K - 1], (lane + 31) & 31);
+        float carry = sel(seam_m, xin, rk);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            // both updates over ONE common maximum: the three exponentials are independent, the dependent chain per
+            // frame is one log-sum-exp long instead of two (A = lse(ab, carry) then lse(al, A)).  A term more than
+            // 2^126 below the largest of the three is dropped -- it could not change an fp32 result anyway.
+            const float M = fmaxf(fmaxf(ab[k], carry), al[k]);
+            const float e_b = ex2_approx(ab[k] - M), e_c = ex2_approx(carry - M), e_l = ex2_approx(al[k] - M);
+            const float s_a = e_b + e_c;
+            const float s_l = e_l + sel(skip_m[k], s_a, e_b);
+            carry = al[k];
+            al[k] = (M + lg2_approx(s_l)) + el2[k];
+            ab[k] = fmaxf(M + lg2_approx(s_a), kNeg) + eb2;
+        }
+        if (SAVE) {
+            float *r = row_out + (int64_t)f * row_step;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                r[bpos[k]] = ab[k] + ds;
+                r[lpos[k]] = al[k] + ds;
+            }
+            if (first && lane == 0) *reinterpret_cast<double *>(r + 2 * P_pad + 2) = off_row_d;
+        }
+    };
+
+    while (remaining > 0) {
+        const int n = remaining < CH ? remaining : CH;
+        // re-centre on floor(max of my states): exact, the offset stays an integer
+        {
+            float mx = kNeg;
+#pragma unroll
+            for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
+            mx = floorf(warp_max(mx));
+            if (mx > kNegTest && mx != 0.f) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
+                off_me += (int)mx;
+            }
+        }
+        // incoming seam of this chunk (read early during the previous chunk; poll only if that was too soon):
+        // lanes [0, n) the values, lane CH the sender's offset, lane CH+1 the row offset
+        float sv = sv_pre;
+        if (!first) {
+            while (__any_sync(FULL, (lane < n || (lane >= CH && lane < SW)) && __float_as_uint(sv) == kSeamEmptyBits))
+                sv = ld_volatile_shared_f32(sv_in + sslot * SW + (lane < SW ? lane : 0));
+            if (inlane) const_cast<float *>(sv_in)[sslot * SW + lane] = EMPTY;  // recycle the slot
+            const int off_up = (int)__shfl_sync(FULL, sv, CH);
+            off_row = (int)__shfl_sync(FULL, sv, CH + 1);
+            // the sender's values are relative to its offset: bring them to mine (lanes >= CH are not used)
+            sv += (float)(off_up - off_me);
+        } else {
+            off_row = off_me;
+        }
+        ds = (float)(off_me - off_row);
+        off_row_d = (double)off_row;
+        const int sslot_next = sslot + 1 == NSLOT ? 0 : sslot + 1;
+        sv_pre = fetch_seam(sslot_next);
+        if (LOGITS) {
+            zv = zv_next;
+            step0 += CH;
+            zv_next = z_fetch(step0);
+        }
+        mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+        if (n == CH) {
+#pragma unroll
+            for (int f = 0; f < CH; ++f) frame(f, sv, std::false_type{});
+            if (is31) {
+#pragma unroll
+                for (int f = 0; f < CH; ++f) sv_out[sslot * SW + f] = sout[f];
+            }
+        } else {
+#pragma unroll 1
+            for (int f = 0; f < n; ++f) frame(f, sv, std::true_type{});
+        }
+        if (is31) {
+            sv_out[sslot * SW + CH] = (float)off_me;
+            sv_out[sslot * SW + CH + 1] = (float)off_row;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+        remaining -= n;
+        if (SAVE) row_out += (int64_t)n * row_step;
+        em_chunk += CH * slot_bytes;
+        if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
+        sslot = sslot_next;
+    }
+    // frontier row for the join kernel / the backward call (same conversion; nsteps == 0: the virtual start row)
+    {
+        float *fin = p.finals + ((int64_t)b * 2 + dir) * row_elems;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            fin[bpos[k]] = ab[k] + ds;
+            fin[lpos[k]] = al[k] + ds;
+        }
+        if (first && lane == 0) *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = (double)off_row;
+    }
+}
+
 // Join the alpha frontier (row m-1, or the virtual start row) with the beta frontier (row m):
 //   log P = off_a + off_b + lse_s( lse(alpha[s], alpha[s-1], skip ? alpha[s-2]) + beta_m[s] )
 __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
@@ -888,6 +1180,48 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
+// The wavefront forward kernel when the shape fits it (SSAK_ERR_UNSUPPORTED -> the barrier kernel is used).
+static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
+    if (env_int("SSAK_CTC_FWD_WAVE", 1) == 0) return SSAK_ERR_UNSUPPORTED;
+    const int64_t P = (int64_t)p.Lmax + 1;
+    if (P > 1024 || p.T > 100000) return SSAK_ERR_UNSUPPORTED;   // 32 * 4 * 8 chain elements; float-exact offsets
+    FwdWaveCfg wc;
+    // A lone warp issues ~0.3 instructions per cycle whatever its ILP (measured), so latency-bound shapes want MANY
+    // thin warps: one chain element per lane up to 16 warps, then 2, then 4 per lane.
+    wc.K = env_int("SSAK_CTC_FWD_K", P <= 512 ? 1 : 4);
+    if (wc.K != 1 && wc.K != 2 && wc.K != 4) return SSAK_ERR_UNSUPPORTED;
+    wc.W = (int)((P + 32 * wc.K - 1) / (32 * wc.K));
+    if (wc.W > (wc.K == 1 ? 16 : 8)) return SSAK_ERR_UNSUPPORTED;
+    wc.slot_bytes = ring_slot_bytes(p.V);
+    wc.chunk = 8 * wc.slot_bytes <= 16384 ? 8 : 4;
+    const int budget = 2 * p.B <= 2 * 148 ? 100 * 1024 : 40 * 1024;
+    int stages = budget / (wc.chunk * wc.slot_bytes);
+    if (stages > wc.W + 6) stages = wc.W + 6;
+    stages = env_int("SSAK_CTC_FWD_STAGES", stages);
+    if (stages < wc.W + 2 || stages > 24) return SSAK_ERR_UNSUPPORTED;
+    wc.stages = stages;
+    const size_t smem_bytes = (size_t)fwd_wave_smem(wc.W, wc.stages, wc.chunk, wc.slot_bytes).total;
+    if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)p.B, 2), block((wc.W + 1) * 32);
+#define SSAK_FW4(KK, CC, ZZ, SS)                                                               \
+    {                                                                                          \
+        auto kern = ctc_forward_wave_kernel<KK, CC, ZZ, SS>;                                   \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem_bytes);                                 \
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
+        kern<<<grid, block, smem_bytes, stream>>>(p, wc);                                      \
+    }
+#define SSAK_FW3(KK, CC, ZZ) if (p.rows) SSAK_FW4(KK, CC, ZZ, true) else SSAK_FW4(KK, CC, ZZ, false)
+#define SSAK_FW2(KK, CC) if (p.zl) { SSAK_FW3(KK, CC, true) } else { SSAK_FW3(KK, CC, false) }
+#define SSAK_FW(KK) if (wc.chunk == 8) { SSAK_FW2(KK, 8) } else { SSAK_FW2(KK, 4) }
+    if (wc.K == 1) { SSAK_FW(1) } else if (wc.K == 2) { SSAK_FW(2) } else { SSAK_FW(4) }
+#undef SSAK_FW
+#undef SSAK_FW2
+#undef SSAK_FW3
+#undef SSAK_FW4
+    return check_launch();
+}
+
 struct WsLayout { size_t nll2, finals, zl, rows, total; };
 static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
     WsLayout w;
@@ -954,7 +1288,8 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         rc = check_launch();
         if (rc != SSAK_OK) return rc;
     }
-    rc = launch_lattice<false>(p, s);
+    rc = launch_forward_wave(p, s);
+    if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
     if (rc != SSAK_OK) return rc;
     ctc_join_kernel<<<(unsigned)B, 256, 0, s>>>(p);
     return check_launch();

@@ -1182,7 +1182,14 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
 
 // The wavefront forward kernel when the shape fits it (SSAK_ERR_UNSUPPORTED -> the barrier kernel is used).
 static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
-    if (env_int("SSAK_CTC_FWD_WAVE", 1) == 0) return SSAK_ERR_UNSUPPORTED;
+    // Used by default for loss-only calls (no rows saved) on few CTAs (at most one per SM: latency-bound, the
+    // wavefront is ~25 % faster).  Not for training steps: a saved row carries ONE offset, here the first warp's,
+    // and once the probability mass has left that warp the states that matter are stored as large numbers
+    // (ulp(800) = 6e-5): the C2 gradient error grows from 6e-6 to 2.6e-4.  With several CTAs per SM the barrier
+    // kernel's fatter lanes issue fewer instructions per cell (1.25 vs 1.54 ms at B = 1024).
+    // SSAK_CTC_FWD_WAVE=1 forces it (tests), =0 disables it.
+    const int mode = env_int("SSAK_CTC_FWD_WAVE", -1);
+    if (mode == 0 || (mode < 0 && (p.rows != nullptr || 2 * p.B > 2 * 148))) return SSAK_ERR_UNSUPPORTED;
     const int64_t P = (int64_t)p.Lmax + 1;
     if (P > 1024 || p.T > 100000) return SSAK_ERR_UNSUPPORTED;   // 32 * 4 * 8 chain elements; float-exact offsets
     FwdWaveCfg wc;

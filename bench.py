@@ -216,12 +216,11 @@ def run_ours(args, rank, world, local_rank):
     t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
     # the timed region lasts a few ms, shorter than nvidia-smi's sampling period: keep the same work running
     # for ~0.3 s more so that the clock / throttle samples are taken under this load
-    if rank == 0:
-        t_soak = time.perf_counter()
-        while time.perf_counter() - t_soak < 0.3:
-            for _ in range(20):
-                step()
-            torch.cuda.synchronize()
+    # (every rank runs the same fixed number of steps: the sharded step contains a collective)
+    for _ in range(30):
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
     # ---- end to end through the host-buffer C ABI: pinned host log-probs in, nll + gradient out
     ctx = C.c_void_p()
     assert lib.ssak_context_create(local_rank, C.byref(ctx)) == 0
@@ -411,6 +410,9 @@ def extra_numbers(lib, dev, flush):
 
 
 def main():
+    if os.environ.get("BENCH_WATCHDOG"):   # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

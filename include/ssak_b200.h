@@ -137,6 +137,24 @@ SSAK_API int ssak_ctc_loss_reduce(const float *neg_log_likelihood, const int32_t
                                   int64_t B, int32_t reduction, int32_t zero_infinity, float *loss_out,
                                   float *grad_scale, ssak_stream_t stream);
 
+/* Utterance-sharded loss (ssak_b200/shard.py): the three device-side pieces around the ONE all-reduce
+ * of two doubles a multi-GPU step needs (the caller does the collective, e.g. ncclAllReduce on `packed`).
+ *   ssak_ctc_shard_pack       packed[0] = local numerator (reduction 1 'mean': sum nll_b / clamp(L_b,1);
+ *                             2 'sum' and 3 'mean_volume': sum nll_b), packed[1] = local denominator part
+ *                             (B_local / 1 / sum L_b); grad_scale[b] = d numerator / d nll_b (0 where
+ *                             zero_infinity dropped the utterance)
+ *   ssak_ctc_shard_finish     loss_out[0] = packed[0] / den, inv_den_out[0] = 1 / den, den = global_batch
+ *                             ('mean'), 1 ('sum'), max(packed[1], 1) ('mean_volume')
+ *   ssak_ctc_shard_grad_scale grad_out[b] = grad_scale[b] * grad_loss[0] * inv_den[0]  (input of
+ *                             ssak_ctc_loss_backward) */
+SSAK_API int ssak_ctc_shard_pack(const float *neg_log_likelihood, const int32_t *target_lengths, int64_t B,
+                                 int32_t reduction, int32_t zero_infinity, double *packed, float *grad_scale,
+                                 ssak_stream_t stream);
+SSAK_API int ssak_ctc_shard_finish(const double *packed, int32_t reduction, int64_t global_batch, float *loss_out,
+                                   float *inv_den_out, ssak_stream_t stream);
+SSAK_API int ssak_ctc_shard_grad_scale(const float *grad_scale, const float *grad_loss, const float *inv_den,
+                                       int64_t B, float *grad_out, ssak_stream_t stream);
+
 /* =========================================================================================
  * Forced alignment.  Replaces get_trellis + backtrack + merge_repeats
  *   (ssak/utils/align_transcriptions.py:27-70, 79-123, 141-157), i.e. the reference's own

@@ -1146,6 +1146,56 @@ __global__ void __launch_bounds__(256) ctc_row_lse_kernel(const CtcParams p) {
     if (lane == 0) p.zl[row] = -(M + lg2_approx(s));
 }
 
+// Utterance-sharded reduction: the local part of [numerator, denominator] as doubles, ready for the
+// ONE all-reduce, plus d numerator / d nll_b.  reduction 1 'mean': num = sum nll_b / clamp(L_b,1), den = B_local
+// (the caller divides by the a-priori known global batch); 2 'sum': num = sum nll_b, den = 1 per rank (unused);
+// 3 'mean_volume': num = sum nll_b, den = sum L_b.
+__global__ void __launch_bounds__(256) ctc_shard_pack_kernel(const float *nll, const int32_t *tgt_len, int64_t B,
+                                                             int reduction, int zero_inf, double *packed,
+                                                             float *gscale) {
+    __shared__ double red_a[8], red_b[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a = 0.0, l = 0.0;
+    for (int64_t b = tid; b < B; b += 256) {
+        float x = nll[b];
+        const bool dropped = zero_inf && !(x < 3.0e38f);
+        if (dropped) x = 0.f;
+        const int L = tgt_len[b];
+        const float w = reduction == 1 ? 1.0f / (float)(L < 1 ? 1 : L) : 1.0f;
+        a += (double)(x * w);
+        l += (double)L;
+        gscale[b] = dropped ? 0.f : w;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        l += __shfl_xor_sync(0xffffffffu, l, d);
+    }
+    if (lane == 0) { red_a[warp] = a; red_b[warp] = l; }
+    __syncthreads();
+    if (tid == 0) {
+        double A = 0.0, Ls = 0.0;
+        for (int w = 0; w < 8; ++w) { A += red_a[w]; Ls += red_b[w]; }
+        packed[0] = A;
+        packed[1] = reduction == 1 ? (double)B : (reduction == 3 ? Ls : 1.0);
+    }
+}
+
+// After the all-reduce: loss = num / den with den = global_batch ('mean'), 1 ('sum') or the reduced sum of
+// lengths ('mean_volume'); inv_den feeds the backward scale.
+__global__ void ctc_shard_finish_kernel(const double *packed, int reduction, double global_batch, float *loss,
+                                        float *inv_den) {
+    double den = reduction == 1 ? global_batch : (reduction == 3 ? (packed[1] < 1.0 ? 1.0 : packed[1]) : 1.0);
+    loss[0] = (float)(packed[0] / den);
+    inv_den[0] = (float)(1.0 / den);
+}
+
+// grad_out[b] of the backward launch = upstream gradient x d loss / d nll_b
+__global__ void ctc_shard_grad_scale_kernel(const float *gscale, const float *grad_loss, const float *inv_den,
+                                            int64_t B, float *out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) out[b] = gscale[b] * (grad_loss[0] * inv_den[0]);
+}
+
 // ---------------------------------------------------------------------------- launchers
 template <bool GRAD>
 static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
@@ -1376,5 +1426,33 @@ extern "C" int ssak_ctc_loss_reduce(const float *neg_log_likelihood, const int32
         return SSAK_ERR_INVALID_ARGUMENT;
     ctc_reduce_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         neg_log_likelihood, target_lengths, B, reduction, zero_infinity, loss_out, grad_scale);
+    return check_launch();
+}
+
+extern "C" int ssak_ctc_shard_pack(const float *neg_log_likelihood, const int32_t *target_lengths, int64_t B,
+                                   int32_t reduction, int32_t zero_infinity, double *packed, float *grad_scale,
+                                   ssak_stream_t stream) {
+    if (!neg_log_likelihood || !target_lengths || !packed || !grad_scale || B <= 0 || reduction < 1 || reduction > 3)
+        return SSAK_ERR_INVALID_ARGUMENT;
+    ctc_shard_pack_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        neg_log_likelihood, target_lengths, B, reduction, zero_infinity, packed, grad_scale);
+    return check_launch();
+}
+
+extern "C" int ssak_ctc_shard_finish(const double *packed, int32_t reduction, int64_t global_batch, float *loss_out,
+                                     float *inv_den_out, ssak_stream_t stream) {
+    if (!packed || !loss_out || !inv_den_out || reduction < 1 || reduction > 3 || global_batch <= 0)
+        return SSAK_ERR_INVALID_ARGUMENT;
+    ctc_shard_finish_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, reduction,
+                                                                                 (double)global_batch, loss_out,
+                                                                                 inv_den_out);
+    return check_launch();
+}
+
+extern "C" int ssak_ctc_shard_grad_scale(const float *grad_scale, const float *grad_loss, const float *inv_den,
+                                         int64_t B, float *grad_out, ssak_stream_t stream) {
+    if (!grad_scale || !grad_loss || !inv_den || !grad_out || B <= 0) return SSAK_ERR_INVALID_ARGUMENT;
+    ctc_shard_grad_scale_kernel<<<(unsigned)((B + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        grad_scale, grad_loss, inv_den, B, grad_out);
     return check_launch();
 }

@@ -70,13 +70,92 @@ def reduce_loss(local_nll: torch.Tensor, local_target_lengths: torch.Tensor, red
     return (num_glob + (num_local - num_local.detach())) / den
 
 
+class _ShardedCTCFunction(torch.autograd.Function):
+    """The sharded loss on the sm_100a kernels in as few launches as the single-GPU wrapper plus the collective:
+    lattice forward + join, the fused local reduction, ONE all-reduce of [numerator, denominator], one division;
+    backward: one scale of the per-utterance weights and the lattice backward.  (The generic path below builds
+    the same value out of ~25 small autograd ops, which makes a 0.5 ms step launch-bound.)"""
+
+    @staticmethod
+    def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity,
+                reduction, global_batch, group):
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        T, B, V = log_probs.shape
+        dev = log_probs.device
+        ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, max_target_len, 1)
+        if ws_bytes == 0:
+            raise _lib.SsakB200Error(f"ctc_loss: shape not supported (T={T}, B={B}, max target length={max_target_len})")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        gscale = torch.empty(B, dtype=torch.float32, device=dev)
+        packed = torch.empty(2, dtype=torch.float64, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)      # [loss, 1/denominator]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = L.ssak_ctc_loss_forward(log_probs.data_ptr(), T, B, V, log_probs.stride(0), log_probs.stride(1),
+                                     targets.data_ptr(), tgt_off.data_ptr(), in_len.data_ptr(), tgt_len.data_ptr(),
+                                     max_target_len, blank, 1, nll.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "ssak_ctc_loss_forward")
+        code = {"mean": 1, "sum": 2, "mean_volume": 3}[reduction]
+        rc = L.ssak_ctc_shard_pack(nll.data_ptr(), tgt_len.data_ptr(), B, code, int(zero_infinity),
+                                   packed.data_ptr(), gscale.data_ptr(), stream)
+        _lib.check(rc, "ssak_ctc_shard_pack")
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        rc = L.ssak_ctc_shard_finish(packed.data_ptr(), code, int(global_batch), out.data_ptr(),
+                                     out.data_ptr() + 4, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "ssak_ctc_shard_finish")
+        ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale, out)
+        ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        from . import _lib
+        log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale, out = ctx.saved_tensors
+        max_target_len, blank, zero_infinity, ws_bytes = ctx.meta
+        L = _lib.lib()
+        T, B, V = log_probs.shape
+        gl = grad_loss if (grad_loss.dtype == torch.float32 and grad_loss.is_contiguous()) else grad_loss.float().contiguous()
+        g = torch.empty(B, dtype=torch.float32, device=log_probs.device)
+        grad = torch.empty_like(log_probs)
+        if grad.stride(2) != 1:
+            grad = torch.empty((T, B, V), dtype=torch.float32, device=log_probs.device)
+        with torch.cuda.device(log_probs.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = L.ssak_ctc_shard_grad_scale(gscale.data_ptr(), gl.data_ptr(), out.data_ptr() + 4, B, g.data_ptr(), stream)
+            _lib.check(rc, "ssak_ctc_shard_grad_scale")
+            rc = L.ssak_ctc_loss_backward(g.data_ptr(), log_probs.data_ptr(), T, B, V, log_probs.stride(0),
+                                          log_probs.stride(1), targets.data_ptr(), tgt_off.data_ptr(),
+                                          in_len.data_ptr(), tgt_len.data_ptr(), max_target_len, blank,
+                                          int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
+                                          grad.stride(1), ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "ssak_ctc_loss_backward")
+        return (grad,) + (None,) * 10
+
+
 def sharded_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean",
                      zero_infinity=False, global_batch=None, group=None, loss_fn=None):
-    """CTC loss of this rank's utterance shard, reduced over all ranks.  `loss_fn(..., reduction='none')`
-    defaults to ssak_b200.ctc_loss; the CPU tests inject a stand-in."""
+    """CTC loss of this rank's utterance shard, reduced over all ranks.
+
+    Default: the sm_100a kernels through one lean autograd node (`_ShardedCTCFunction`).  With `loss_fn`
+    (`loss_fn(..., reduction='none')`, e.g. the CPU stand-in of the gloo tests) the same value is built from
+    generic torch ops."""
     import torch.distributed as dist
+    if reduction not in ("mean", "sum", "mean_volume"):
+        raise ValueError(reduction)
     if loss_fn is None:
-        from .loss import ctc_loss as loss_fn
+        from .loss import _prepare
+        lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, input_lengths, target_lengths, blank)
+        if global_batch is None:
+            n = torch.tensor([lp.shape[1]], dtype=torch.int64, device=lp.device)
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(n, group=group)
+            global_batch = int(n.item())
+        with torch.cuda.device(lp.device):
+            return _ShardedCTCFunction.apply(lp, tg, tgt_off, in_len, tgt_len, lmax, int(blank), bool(zero_infinity),
+                                             reduction, int(global_batch), group)
     nll = loss_fn(log_probs, targets, input_lengths, target_lengths, blank=blank, reduction="none",
                   zero_infinity=zero_infinity)
     tl = torch.as_tensor(target_lengths).to(nll.device)

@@ -55,7 +55,7 @@ def test_sharded_loss_matches_single_process(reduction):
     ref.backward()
     seen = []
     for rank, mine, loss, grad in results:
-        assert abs(loss - float(ref)) <= 1e-5 * abs(float(ref))
+        assert abs(loss - float(ref)) <= 5e-5 * abs(float(ref))   # fp32 sums in a different order
         assert torch.allclose(grad, x.grad[:, mine], atol=1e-6)
         seen += mine
     assert sorted(seen) == list(range(10))

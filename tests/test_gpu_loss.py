@@ -309,3 +309,25 @@ def test_loss_forward_kernels_agree(fwd, monkeypatch):
         with torch.no_grad():
             l2 = ssak_b200.ctc_loss(lp.cuda(), tg, il, tl, 0, "none", True).cpu()
         _assert_close(l2, rg.float(), rl, rg, f"{fwd}/{seed}/no_grad")
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum", "mean_volume"])
+def test_sharded_wrapper_single_rank_equals_ctc_loss(reduction):
+    """ssak_b200.shard.sharded_ctc_loss without a process group (world size 1: the collective is skipped) is the
+    plain loss -- the lean autograd node around ssak_ctc_shard_pack / _finish / _grad_scale (N > 1: tools/check_sharded.py
+    under torchrun, and the gloo test of the host logic)."""
+    import ssak_b200
+    from ssak_b200.shard import sharded_ctc_loss
+    from ssak_b200.synth import ctc_batch
+    lp, tg, il, tl = ctc_batch(9, 120, 40, 0, 30, 77, Tmin=50)
+    tg[2, :3] = torch.tensor([7, 7, 7])
+    il[2], tl[2] = 4, 3                      # infeasible: dropped by zero_infinity
+    x = lp.cuda().requires_grad_(True)
+    loss = sharded_ctc_loss(x, tg.cuda(), il.cuda(), tl.cuda(), 0, reduction, True, global_batch=9)
+    loss.backward(torch.tensor(0.5, device="cuda"))
+    y = lp.cuda().requires_grad_(True)
+    ref = ssak_b200.ctc_loss(y, tg.cuda(), il.cuda(), tl.cuda(), 0, reduction, True)
+    ref.backward(torch.tensor(0.5, device="cuda"))
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert (x.grad - y.grad).abs().max().item() <= 1e-7
+    assert (x.grad[:, 2] == 0).all()

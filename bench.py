@@ -348,6 +348,30 @@ def extra_numbers(lib, dev, flush):
             del lp_d
         except Exception as e:  # keep the headline line even if an extra shape fails
             res[f"loss_{name}"] = {"error": repr(e)}
+    # on-box GPU comparator: torch's own CUDA ctc_loss (native kernel, cuDNN off as HF does) on the
+    # same C2 / 1k / C5 tensors, forward + backward through autograd, same event timing and L2 flush
+    import torch.nn.functional as F
+    for name in ("c2", "1k", "c5"):
+        try:
+            B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
+            lp, tg, il, tl, cells = make_batch(name, 99)
+            lp_d, tg_d, il_d, tl_d = lp.to(dev), tg.to(dev), il.to(dev), tl.to(dev)
+
+            def torch_step():
+                x = lp_d.detach().requires_grad_(True)
+                with torch.backends.cudnn.flags(enabled=False):
+                    F.ctc_loss(x, tg_d, il_d, tl_d, 0, "mean", True).backward()
+
+            def our_step():
+                x = lp_d.detach().requires_grad_(True)
+                ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, 0, "mean", True).backward()
+
+            t_torch, t_ours = _timed_ms(torch_step, flush), _timed_ms(our_step, flush)
+            res[f"torch_cuda_ctc_{name}"] = {"torch_ms": t_torch, "ours_ms": t_ours, "speedup": t_torch / t_ours,
+                                              "torch_cells_per_s": cells / (t_torch * 1e-3)}
+            del lp_d
+        except Exception as e:
+            res[f"torch_cuda_ctc_{name}"] = {"error": repr(e)}
     # f-1: log_softmax + ctc_loss (+ both backwards) against the single logits entry point, C5 shape, torch-facing API
     try:
         B, T, V, Lmin, Lmax, Tmin = WORKLOADS["c5"]

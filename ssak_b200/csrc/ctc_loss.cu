@@ -58,6 +58,7 @@ struct CtcCfg {
     int slot_bytes;
     int or_chunk;   // rows per stage of the "other direction" ring (backward)
     int or_stages;
+    int PW;         // posterior warps (backward; 0: the recursion warps compute the posteriors themselves)
 };
 // Row layout (floats): [0,P_pad) blank states | [P_pad] spare | [P_pad+1, 2P_pad+1) label states
 //                      | [2P_pad+2, 2P_pad+4) fp64 re-centring offset | pad to 2P_pad+8.
@@ -94,6 +95,7 @@ static inline int env_int(const char *name, int dflt) {
 }
 
 // Launch shape from (Lmax, B) only, so forward and backward agree on the workspace layout.
+static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad);
 static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     const int64_t P = Lmax + 1;
     // Few CTAs (latency regime): one recursion warp per SM sub-partition.  Many CTAs
@@ -140,25 +142,40 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->or_chunk = env_int("SSAK_CTC_OR_CHUNK", c->or_chunk);
     c->or_stages = env_int("SSAK_CTC_OR_STAGES", c->or_stages);
     if (c->or_stages > 8 || c->or_stages < 2 || c->or_chunk < 1) return false;
+    // Posterior warps (latency regime only): a lone warp issues ~0.3 instructions per cycle whatever its ILP, so
+    // the per-frame work of the backward is split over two warps per state group -- the recursion warp keeps the
+    // serial chain, a posterior warp (one chunk behind, through a 2-chunk state ring) multiplies with the other
+    // direction's row.  Needs W more warps (<= 22 in all) and 2*chunk*2*P_pad floats of shared memory.
+    c->PW = 0;
+    if (few && env_int("SSAK_CTC_SPLIT", 1) != 0 && K <= 4 && c->W + 2 + c->G + c->W <= 22) {
+        c->PW = c->W;
+        if (smem_bytes_for(*c, V, (int)Lmax, true) > 227 * 1024) c->PW = 0;
+    }
     return true;
 }
 
 // shared memory map (bytes)
 constexpr int kBarEmFull = 0, kBarEmEmpty = 64, kBarOrFull = 128, kBarOrEmpty = 192, kBarPostEmpty = 256, kBarPostFull = 272;
 constexpr int kSmemXchg = 400, kSmemWmax = 560, kSmemRing = 640;
+// bytes of the posterior-warp hand-over area (state ring of 2 chunk buffers, per-warp base offsets, mbarriers)
+static size_t split_bytes_for(const CtcCfg &c) {
+    return c.PW ? 2 * (size_t)c.chunk * 2 * c.P_pad * sizeof(float) + (size_t)c.PW * 2 * 8 + (size_t)c.PW * 4 * 8 : 0;
+}
 static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
     size_t o = kSmemRing + (size_t)c.stages * c.chunk * c.slot_bytes;
-    if (grad)
+    if (grad) {
         o += (size_t)c.or_stages * c.or_chunk * c.row_elems * 4 + 2 * (size_t)c.chunk * (c.P_pad + 8) * sizeof(float) +
              2 * (size_t)c.chunk * sizeof(unsigned) + ((size_t)V + 2) * sizeof(int) + (size_t)V * sizeof(int) +
              (size_t)(Lmax > 0 ? Lmax : 1) * sizeof(int);
+        o = align_up(o, 16) + split_bytes_for(c);
+    }
     return align_up(o, 16);
 }
 
 // ------------------------------------------------------------------------------ kernel
 // Warp roles: [0, W) recursion; W emission producer; backward only: W+1 lattice-row producer, then G gradient warps.
-template <int K, bool GRAD, int CH, bool LOGITS>
-__global__ void __launch_bounds__(K == 8 ? (GRAD ? 704 : 544) : (GRAD ? 576 : 288), 1)
+template <int K, bool GRAD, int CH, bool LOGITS, bool SPLIT>
+__global__ void __launch_bounds__(K == 8 ? (GRAD ? 704 : 544) : (GRAD ? (SPLIT ? 704 : 576) : 288), 1)
 ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const CtcCfg &c = p.cfg;
@@ -169,6 +186,11 @@ ctc_lattice_kernel(const CtcParams p) {
     const bool compute = warp < W;
     constexpr int NPROD = GRAD ? 2 : 1;  // producer warps
     const bool producer = warp >= W && warp < W + NPROD;
+    const int PW = (GRAD && SPLIT) ? c.PW : 0;           // posterior warps (0: the recursion warps do it)
+    const int post0 = W + NPROD + (GRAD ? c.G : 0);      // first posterior warp
+    const bool is_post = SPLIT && warp >= post0;
+    constexpr bool split = GRAD && SPLIT;
+    const int rw = is_post ? warp - post0 : warp;        // the recursion warp whose state group this warp handles
     const unsigned FULL = 0xffffffffu;
 
     int Tb = p.in_len[b];
@@ -211,6 +233,13 @@ ctc_lattice_kernel(const CtcParams p) {
     int *occ_start = reinterpret_cast<int *>(blank_acc + 2 * CH);
     int *cursor = occ_start + (V + 2);  // counting-sort cursors, then the list of columns that carry posterior mass
     int *occ_pos = cursor + V;
+    // posterior-warp hand-over (split): state ring [2*CH][2*P_pad], per-warp chunk bases, mbarriers
+    unsigned char *split_base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(occ_pos + (p.Lmax > 0 ? p.Lmax : 1)) + 15) & ~(uintptr_t)15);
+    float *sring = reinterpret_cast<float *>(split_base);
+    double *sbase = reinterpret_cast<double *>(split_base + 2 * (size_t)CH * 2 * P_pad * sizeof(float));  // [PW][2]
+    uint64_t *st_full = reinterpret_cast<uint64_t *>(sbase + 2 * (PW > 0 ? PW : 1));                       // [PW][2]
+    uint64_t *st_empty = st_full + 2 * (PW > 0 ? PW : 1);                                                  // [PW][2]
 
     // ---- gradient prologue: trivial outcomes ----
     double nll2 = 0.0;
@@ -234,7 +263,7 @@ ctc_lattice_kernel(const CtcParams p) {
         nll2 = p.nll2[b];
     }
 
-    const int n_consumers = W + (GRAD ? c.G : 0);
+    const int n_consumers = W + (GRAD ? c.G : 0) + PW;
     if (tid == 0) {
         for (int s = 0; s < c.stages; ++s) {
             mbar_init(&em_full[s], 1);
@@ -251,6 +280,10 @@ ctc_lattice_kernel(const CtcParams p) {
             }
             mbar_init(&post_empty[0], c.G);
             mbar_init(&post_empty[1], c.G);
+            for (int s = 0; s < 2 * PW; ++s) {
+                mbar_init(&st_full[s], 1);
+                mbar_init(&st_empty[s], 1);
+            }
         }
         mbar_fence_init();
     }
@@ -265,8 +298,8 @@ ctc_lattice_kernel(const CtcParams p) {
     // alpha: pair p = (blank p, label p);  beta: pair q = (label q-1, blank q)
     int lab_off[K];
     unsigned skipmask = 0;
-    const int pbase = warp * 32 * K + lane;
-    if (compute) {
+    const int pbase = rw * 32 * K + lane;
+    if (compute || is_post) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
@@ -434,7 +467,7 @@ ctc_lattice_kernel(const CtcParams p) {
         skip_m[k] = (skipmask >> k) & 1u ? 0xffffffffu : 0u;
         bl_m[k] = pbase + k * 32 <= L ? 0xffffffffu : 0u;
         wl_off[k] = 4 * (WL - 1);  // dump slot for the states beyond 2L+1
-        if (GRAD && compute) {
+        if (GRAD && (compute || is_post)) {
             const int li = dir ? pbase + k * 32 - 1 : pbase + k * 32;
             if (li >= 0 && li < L) wl_off[k] = 4 * occ_pos[li];
         }
@@ -527,6 +560,18 @@ ctc_lattice_kernel(const CtcParams p) {
                         sl += st_step;
                         soff += st_step / 2;  // row_elems is even
                     }
+                } else if (split) {
+                    // hand my states of this frame to my posterior warp (state ring, buffer of this chunk)
+                    float *sr = sring + (size_t)(pbuf + f) * 2 * P_pad + pbase;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        sr[k * 32] = ab[k];
+                        sr[P_pad + k * 32] = al[k];
+                    }
+                    if (f == n - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&st_full[warp * 2 + (chunk_idx & 1)]);
+                    }
                 } else {
                     // posteriors of my states at this frame: 2^(alpha + beta - lp - log2 P)
                     if (or_left == 0) {
@@ -590,8 +635,13 @@ ctc_lattice_kernel(const CtcParams p) {
                 }
                 first_chunk = false;
                 base_d = off_mine + nll2;
-                if (GRAD && chunk_idx >= 2)  // the gradient warps must be done with this posterior buffer
+                if (GRAD && split) {
+                    // my posterior warp must be done with this state buffer; it also needs this chunk's base
+                    if (chunk_idx >= 2) mbar_wait(&st_empty[warp * 2 + (chunk_idx & 1)], (uint32_t)(((chunk_idx >> 1) - 1) & 1));
+                    if (lane == 0) sbase[warp * 2 + (chunk_idx & 1)] = base_d;
+                } else if (GRAD && chunk_idx >= 2) {  // the gradient warps must be done with this posterior buffer
                     mbar_wait(&post_empty[chunk_idx & 1], (uint32_t)(((chunk_idx >> 1) - 1) & 1));
+                }
                 pbuf = (chunk_idx & 1) * CH;
                 if (n == CH) {  // fast path: full chunk, every per-frame test folds at compile time
 #pragma unroll
@@ -607,6 +657,86 @@ ctc_lattice_kernel(const CtcParams p) {
             }
         };
         if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
+    } else if (GRAD && is_post) {
+        // ---------------- posterior warps: one chunk behind their recursion warp ----------------
+        // posterior of a state = 2^(alpha + beta - lp - log2 P): my recursion warp's states (state ring) times
+        // the other direction's stored row (row ring), label posteriors into the label-sorted posterior ring,
+        // blank posteriors summed in fixed point.  Everything here is off the serial chain of the recursion.
+        const int lab_delta = P_pad + 1 - dir;
+        const unsigned char *or_row = or_slots;
+        int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
+        unsigned char *wl_bytes = reinterpret_cast<unsigned char *>(wlab);
+        int em_stage = 0, em_phase = 0, remaining = nsteps, chunk_idx = 0;
+        const unsigned char *em_chunk = em_base;
+        const float *z_ptr = LOGITS ? p.zl + (int64_t)t_first * p.B + b : nullptr;
+        const int64_t z_step = (int64_t)dt * p.B;
+        auto z_fetch = [&](int step0) -> float {
+            const int sidx = step0 + lane;
+            return (LOGITS && lane < CH && sidx < nsteps) ? __ldg(z_ptr + (int64_t)sidx * z_step) : 0.f;
+        };
+        float zv = 0.f, zv_next = z_fetch(0);
+        while (remaining > 0) {
+            const int n = remaining < CH ? remaining : CH;
+            if (LOGITS) {
+                zv = zv_next;
+                zv_next = z_fetch((chunk_idx + 1) * CH);
+            }
+            const int buf = chunk_idx & 1, pbuf = buf * CH;
+            mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+            mbar_wait(&st_full[rw * 2 + buf], (uint32_t)((chunk_idx >> 1) & 1));   // the chunk's states are there
+            if (chunk_idx >= 2)  // the gradient warps must be done with this posterior buffer
+                mbar_wait(&post_empty[buf], (uint32_t)(((chunk_idx >> 1) - 1) & 1));
+            const double base_d = sbase[rw * 2 + buf];
+            for (int f = 0; f < n; ++f) {
+                const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
+                const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
+                const float xb = *reinterpret_cast<const float *>(row + blank_off);
+                const float eb2 = fmaxf(LOGITS ? fmaf(xb, kLog2e, zl) : xb * kLog2e, kNeg);
+                if (or_left == 0) {
+                    mbar_wait(&or_full[ostage], (uint32_t)ophase);
+                    or_left = Co;
+                }
+                const float *orow = reinterpret_cast<const float *>(or_row) + pbase;
+                const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
+                const float bracket = (float)(base_d + ooff);
+                const float cb = bracket - eb2;
+                const float *sr = sring + (size_t)(pbuf + f) * 2 * P_pad + pbase;
+                unsigned char *wl = wl_bytes + (pbuf + f) * (WL * 4);
+                float sbl = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float x = *reinterpret_cast<const float *>(row + lab_off[k]);
+                    const float el2 = fmaxf(LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e, kNeg);
+                    sbl += ex2_approx(sr[k * 32] + sel(bl_m[k], orow[k * 32], kNeg) + cb);
+                    *reinterpret_cast<float *>(wl + wl_off[k]) =
+                        ex2_approx(sr[P_pad + k * 32] + orow[lab_delta + k * 32] + (bracket - el2));
+                }
+                const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
+                const unsigned tot = __reduce_add_sync(FULL, fx);
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(&blank_acc[pbuf + f], tot);
+                    mbar_arrive(&post_full[pbuf + f]);  // release: this warp's posteriors of the frame
+                }
+                or_row += row_bytes;
+                if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
+                if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
+                    or_left = 0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&or_empty[ostage]);
+                    if (++ostage == No) { ostage = 0; ophase ^= 1; }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&em_empty[em_stage]);
+                mbar_arrive(&st_empty[rw * 2 + buf]);
+            }
+            remaining -= n;
+            ++chunk_idx;
+            em_chunk += CH * slot_bytes;
+            if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
+        }
     } else if (GRAD) {
         // ---------------- gradient warps: consume the posterior ring, mbarriers only ----------------
         // Each gradient warp takes whole frames (frame f of a chunk goes to warp f mod G), so the
@@ -1202,17 +1332,19 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     const CtcCfg &c = p.cfg;
     const size_t smem_bytes = smem_bytes_for(c, p.V, p.Lmax, GRAD);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)p.B, 2), block((c.W + (GRAD ? 2 + c.G : 1)) * 32);
-#define SSAK_LAUNCH3(KK, CC, ZZ)                                                               \
+    dim3 grid((unsigned)p.B, 2), block((c.W + (GRAD ? 2 + c.G + c.PW : 1)) * 32);
+#define SSAK_LAUNCH4(KK, CC, ZZ, SP)                                                           \
     {                                                                                          \
-        auto kern = ctc_lattice_kernel<KK, GRAD, CC, ZZ>;                                      \
+        auto kern = ctc_lattice_kernel<KK, GRAD, CC, ZZ, SP>;                                  \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem_bytes);                                 \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
         kern<<<grid, block, smem_bytes, stream>>>(p);                                          \
     }
+#define SSAK_LAUNCH3(KK, CC, ZZ)                                                               \
+    if (GRAD && KK <= 4 && c.PW > 0) SSAK_LAUNCH4(KK, CC, ZZ, (GRAD && KK <= 4)) else SSAK_LAUNCH4(KK, CC, ZZ, false)
 #define SSAK_LAUNCH2(KK, CC)                                                                   \
-    if (p.zl) SSAK_LAUNCH3(KK, CC, true) else SSAK_LAUNCH3(KK, CC, false)
+    if (p.zl) { SSAK_LAUNCH3(KK, CC, true) } else { SSAK_LAUNCH3(KK, CC, false) }
 #define SSAK_LAUNCH(KK)                                                                        \
     case KK:                                                                                   \
         if (c.chunk == 8) { SSAK_LAUNCH2(KK, 8) } else { SSAK_LAUNCH2(KK, 4) }                 \
@@ -1224,6 +1356,7 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
         SSAK_LAUNCH(8)
         default: return SSAK_ERR_UNSUPPORTED;
     }
+#undef SSAK_LAUNCH4
 #undef SSAK_LAUNCH3
 #undef SSAK_LAUNCH2
 #undef SSAK_LAUNCH

@@ -105,9 +105,20 @@ static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
     int wtarget = (B * S <= 148) ? 8 : ((B * S <= 4 * 148) ? 4 : 2);
     wtarget = align_env_int("SSAK_ALIGN_WARPS", wtarget);
     int K = align_env_int("SSAK_ALIGN_K", 0);
-    if (K == 0) K = (Pc + 127) / 128 > wtarget ? 8 : 4;
-    if (K != 4 && K != 8) return false;  // a lane owns 4 or 8 consecutive states (decision bits: 1 or 2 bytes per lane)
-    if (K < 8 && (Pc + 32 * K - 1) / (32 * K) > 8) K = 8;  // the kernels are built for <= 8 recursion warps
+    if (K == 0) {
+        // few CTAs (latency regime): a lone warp issues ~0.3 instructions per cycle whatever its ILP, so thinner
+        // warps help -- down to 2 states per lane (measured on the C2-shaped batch: 0.26 ms at K = 2, 0.29 ms at
+        // K = 1 (longer warp chain, two more shuffles per frame) and at K = 4); many CTAs: 4 states per lane
+        // (fewest instructions per state), 8 beyond 1024 states per CTA
+        if (B * S <= 148) {
+            K = 2;
+            while (K < 8 && (Pc + 32 * K - 1) / (32 * K) > 8) K *= 2;
+        } else {
+            K = (Pc + 127) / 128 > wtarget ? 8 : 4;
+        }
+    }
+    if (K != 1 && K != 2 && K != 4 && K != 8) return false;  // consecutive states per lane
+    while (K < 8 && (Pc + 32 * K - 1) / (32 * K) > 8) K *= 2;  // the kernels are built for <= 8 recursion warps
     int64_t W = (Pc + 32 * K - 1) / (32 * K);
     if (W > 8) return false;
     c->K = K;
@@ -587,9 +598,14 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
     // decision bits, "lane entry" layout: per frame and lane one entry of 2K bits -- bit k: changed > stayed for
     // my k-th state, bit K+k: changed < stayed -- i.e. one byte (K = 4) or two (K = 8) per lane, a coalesced
     // 32/64-byte store per warp and frame, 16 states per 32-bit word, no cross-lane packing at all.
+    // K = 1, 2: the 4/K lanes that share a byte OR their bits together (1-2 xor shuffles) and the first one stores,
+    // so the layout is that of K = 4 (state s -> byte s/4, "greater" bit s%4, "less" bit 4 + s%4).
     using bp_t = typename std::conditional<K == 8, uint16_t, uint8_t>::type;
-    const int64_t bp_row = (int64_t)c.S * W * 32;  // entries per frame
-    bp_t *bp_ptr = reinterpret_cast<bp_t *>(p.bp) + (int64_t)b * p.Tmax * bp_row + gw * 32 + lane;
+    constexpr int LPB = K < 4 ? 4 / K : 1;                  // lanes per entry
+    const int64_t bp_row = (int64_t)c.S * W * (32 / LPB);  // entries per frame
+    bp_t *bp_ptr = reinterpret_cast<bp_t *>(p.bp) + (int64_t)b * p.Tmax * bp_row + gw * (32 / LPB) + lane / LPB;
+    const int ent_sh = K * (lane % LPB);                    // my bits' position inside the nibble
+    const bool ent_store = lane % LPB == 0;
     const float *c0_ptr = p.col0_eff + (int64_t)b * p.Tmax;
     const unsigned char *em_base = ring.slots, *em_chunk = em_base;
     int em_stage = 0, em_phase = 0, remaining = Tb, t = 0, sslot = 0;
@@ -650,7 +666,14 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
             ng = __funnelshift_l(__float_as_uint(stayed_k[k] - chg_k[k]), ng, 1);
             nl = __funnelshift_l(__float_as_uint(chg_k[k] - stayed_k[k]), nl, 1);
         }
-        *bp_ptr = (bp_t)(ng | (nl << K));
+        if (K >= 4) {
+            *bp_ptr = (bp_t)(ng | (nl << K));
+        } else {
+            unsigned e = (ng << ent_sh) | (nl << (4 + ent_sh));
+            e |= __shfl_xor_sync(FULL, e, 1);
+            if (K == 1) e |= __shfl_xor_sync(FULL, e, 2);
+            if (ent_store) *bp_ptr = (bp_t)e;
+        }
         bp_ptr += bp_row;
         {   // first maximum of trellis[:, L] (:88); only the owner's comparison can be true
             float vl = v[0];
@@ -996,6 +1019,8 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
         if (p.cfg.chunk == 8) { SSAK_WAVE2(KK, 8) } else { SSAK_WAVE2(KK, 4) }                 \
         break;
         switch (p.cfg.K) {
+            SSAK_WAVE(1)
+            SSAK_WAVE(2)
             SSAK_WAVE(4)
             SSAK_WAVE(8)
             default: return SSAK_ERR_UNSUPPORTED;
@@ -1031,7 +1056,7 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     rc = check_launch();
     if (rc != SSAK_OK) return rc;
     if (!wave) align_backtrace_kernel<0><<<(unsigned)B, 256, 0, s>>>(p);
-    else if (p.cfg.K == 4) align_backtrace_kernel<4><<<(unsigned)B, 256, 0, s>>>(p);
+    else if (p.cfg.K <= 4) align_backtrace_kernel<4><<<(unsigned)B, 256, 0, s>>>(p);   // K = 1, 2 write the K = 4 layout
     else align_backtrace_kernel<8><<<(unsigned)B, 256, 0, s>>>(p);
     return check_launch();
 }

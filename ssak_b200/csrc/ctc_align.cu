@@ -421,8 +421,8 @@ __host__ __device__ __forceinline__ WaveSmem wave_smem(int W, int stages, int ch
     const int nslot = stages + 1;
     m.em_full = 0;
     m.em_empty = 8 * stages;
-    m.seam_val = 16 * stages;                      // [W+1][nslot][chunk] floats (+1: scratch for warps without a consumer)
-    m.ring = (m.seam_val + 4 * (W + 1) * nslot * chunk + 127) & ~127;
+    m.seam_val = 16 * stages;                      // [W+2][nslot][chunk] floats (+ scratch ring, + column-0 ring)
+    m.ring = (m.seam_val + 4 * (W + 2) * nslot * chunk + 127) & ~127;
     m.total = m.ring + stages * chunk * slot_bytes;
     return m;
 }
@@ -445,7 +445,7 @@ __device__ __forceinline__ void st_seam_generic(float *p, float v) {  // shared 
 }
 
 template <int K, int CH, bool DUMP>
-__global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p) {
+__global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const AlignCfg &c = p.cfg;
     const int cta = blockIdx.x, S = c.S, b = blockIdx.y;
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
     const WaveSmem lay = wave_smem(W, NST, CH, slot_bytes);
     uint64_t *em_full = reinterpret_cast<uint64_t *>(smem + lay.em_full);
     uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + lay.em_empty);
-    float *seam_val = reinterpret_cast<float *>(smem + lay.seam_val);          // [W+1][NSLOT][CH]
+    float *seam_val = reinterpret_cast<float *>(smem + lay.seam_val);          // [W+2][NSLOT][CH]
     RowRing ring;
     ring.slots = smem + lay.ring;
     ring.full = em_full;
@@ -500,9 +500,51 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < (W + 1) * NSLOT * CH; i += blockDim.x) seam_val[i] = EMPTY;
+    for (int i = tid; i < (W + 2) * NSLOT * CH; i += blockDim.x) seam_val[i] = EMPTY;
     __syncthreads();  // the only CTA-wide barrier
-    if (warp >= wlive && warp != W) return;        // idle recursion warps
+    if (warp >= wlive && warp != W && !(warp == W + 1 && cta == 0)) return;  // idle recursion warps
+
+    if (warp == W + 1) {
+        // ================= column-0 warp (first CTA of the utterance) =================
+        // Column 0 of the trellis (:37 / :39 / :42) is the "seam" of global warp 0: the fp64 running sum of the
+        // blank column rounded to fp32 per element (torch.cumsum on the CPU; strictly sequential, 32 frames per
+        // round: doubles broadcast by independent shuffles, only the chain of adds is serial), or the caller's
+        // vector (first_as_garbage), with the +inf sentinel.  It is streamed into a seam ring like any other
+        // seam; a slot is written once its consumer has recycled it.
+        float *c0ring = seam_val + (W + 1) * NSLOT * CH;
+        const float *c0 = p.garbage && p.col0 ? p.col0 + (int64_t)b * p.Tmax : nullptr;
+        const float *blank_col = em_b + p.blank;
+        auto load = [&](int tt) -> float { return tt < Tb ? (c0 ? c0[tt] : blank_col[(int64_t)tt * p.st]) : 0.f; };
+        double acc = 0.0;
+        float xn = load(lane);
+        int slot = 0;
+        for (int t0 = 0; t0 < Tb; t0 += 32) {
+            const int tt = t0 + lane;
+            const float x = xn;
+            xn = load(tt + 32);
+            float mine = x;
+            if (!c0) {
+                const double xd = (double)x;
+                double mine_d = 0.0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    acc += __shfl_sync(FULL, xd, i);
+                    mine_d = lane == i ? acc : mine_d;
+                }
+                mine = (float)mine_d;
+            }
+            const float val = (tt + 1 >= Tb + 1 - L) ? INF : mine + 0.0f;  // (+0.0f: a -0.0 becomes +0.0)
+            for (int j = 0; j < 32 / CH && t0 + j * CH < Tb; ++j) {
+                float *dst = c0ring + slot * CH;
+                if (lane == 0)
+                    while (__float_as_uint(ld_seam_shared(dst)) != kSeamEmpty) __nanosleep(100);
+                __syncwarp();
+                if (lane / CH == j && tt < Tb) dst[lane % CH] = val;
+                if (++slot == NSLOT) slot = 0;
+            }
+        }
+        return;
+    }
 
     const int nchunks = (Tb + CH - 1) / CH;
     const bool contig = p.st == V;  // [.., T, V] rows back to back: chunk-sized copies, rows 4V bytes apart in the ring
@@ -573,11 +615,11 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
     }
     // seams: where my incoming values come from, where my outgoing values go
     const bool first = gw == 0;                       // owns trellis column 0: its "seam" is column 0 itself
-    const bool up_smem = warp > 0, up_glob = warp == 0 && cta > 0;
+    const bool up_smem = warp > 0 || first, up_glob = warp == 0 && cta > 0;
     const bool dn_live = (gw + 1) * 32 * K <= L;
     const bool dn_glob = dn_live && warp + 1 == W;
     const float *gs_in = p.gseam + ((int64_t)b * (S - 1) + (cta - 1)) * p.Tmax;   // valid when up_glob
-    const float *sv_in = seam_val + (warp - 1) * NSLOT * CH;                      // valid when up_smem
+    const float *sv_in = seam_val + (first ? W + 1 : warp - 1) * NSLOT * CH;     // valid when up_smem
     // outgoing: the ring of my downstream warp in this CTA, the global buffer, or a scratch ring nobody reads
     float *sv_out = seam_val + (dn_live && !dn_glob ? warp : W) * NSLOT * CH;
     float *out_ptr = dn_glob ? p.gseam + ((int64_t)b * (S - 1) + cta) * p.Tmax : sv_out;
@@ -606,16 +648,13 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
     bp_t *bp_ptr = reinterpret_cast<bp_t *>(p.bp) + (int64_t)b * p.Tmax * bp_row + gw * (32 / LPB) + lane / LPB;
     const int ent_sh = K * (lane % LPB);                    // my bits' position inside the nibble
     const bool ent_store = lane % LPB == 0;
-    const float *c0_ptr = p.col0_eff + (int64_t)b * p.Tmax;
     const unsigned char *em_base = ring.slots, *em_chunk = em_base;
     int em_stage = 0, em_phase = 0, remaining = Tb, t = 0, sslot = 0;
     const bool inlane = lane < CH;
     // incoming values of the NEXT chunk, frame f in lane f (read one chunk early; EMPTY = not there yet)
     auto fetch_seam = [&](int t_next, int slot_next) -> float {
         float x = -INF;
-        if (first) {
-            if (inlane && t_next + lane < Tb) x = __ldg(c0_ptr + t_next + lane);
-        } else if (up_smem) {
+        if (up_smem) {
             if (inlane) x = ld_seam_shared(sv_in + slot_next * CH + lane);
         } else if (up_glob) {
             if (inlane && t_next + lane < Tb) x = ld_seam_global(gs_in + t_next + lane);
@@ -695,7 +734,7 @@ __global__ void __launch_bounds__(288, 1) align_wave_kernel(const AlignParams p)
         const int n = remaining < CH ? remaining : CH;
         // incoming values of this chunk: read early during the previous chunk, poll only if that was too soon
         float sv = sv_pre;
-        if (!first) {
+        {
             while (__any_sync(FULL, lane < n && __float_as_uint(sv) == kSeamEmpty))
                 sv = up_smem ? ld_seam_shared(sv_in + sslot * CH + (lane & (CH - 1)))
                              : ld_seam_global(gs_in + min(t + (lane & (CH - 1)), Tb - 1));
@@ -972,9 +1011,12 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     p.starts = starts; p.ends = ends; p.scores = scores; p.t_start = t_start; p.status = status;
     p.dump = trellis_dump; p.path_token = path_token; p.path_prob = path_prob;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
-    int rc = check_launch();
-    if (rc != SSAK_OK) return rc;
+    int rc = SSAK_OK;
+    if (!wave) {   // (the wavefront kernel computes column 0 itself)
+        align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != SSAK_OK) return rc;
+    }
     if (wave) {
         if (B > 65535) return SSAK_ERR_UNSUPPORTED;
         if (lay.gseam_bytes) {  // every cross-CTA seam word starts as "not there yet"
@@ -983,7 +1025,7 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
         }
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned)p.cfg.S, (unsigned)B);
-        lc.blockDim = dim3((p.cfg.W + 1) * 32);
+        lc.blockDim = dim3((p.cfg.W + 2) * 32);   // recursion warps, emission producer, column-0 warp
         lc.dynamicSmemBytes = smem_bytes;
         lc.stream = s;
         cudaLaunchAttribute attr[1];

@@ -83,3 +83,72 @@ def align(emission, tokens, blank_id=0, first_as_garbage=False, want_trellis=Fal
     segs = ns["merge_repeats"](list(range(len(toks))), path)
     out["segments"] = [(s.label, s.start, s.end, s.score) for s in segs]
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# the word-packing step of tools/align_audio_transcript.py (:383-435), i.e. `add_segment` and the
+# loop that packs aligned words into cuts of at most `max_duration` seconds.  It lives inside a 300-line function
+# with heavy imports, so the block is sliced out of the source text (never copied into the repository), dedented
+# and executed on stand-in file objects; _punctuation comes from ssak/utils/text_basic.py:15-16 the same way.
+_TOOL_PY = os.path.join(REFERENCE_ROOT, "tools", "align_audio_transcript.py")
+_TEXT_BASIC_PY = os.path.join(REFERENCE_ROOT, "ssak", "utils", "text_basic.py")
+_pack_code = None
+_punct = None
+
+
+def cutter_available() -> bool:
+    return os.path.isfile(_TOOL_PY) and os.path.isfile(_TEXT_BASIC_PY)
+
+
+def reference_punctuation() -> str:
+    global _punct
+    if _punct is None:
+        import string
+        with open(_TEXT_BASIC_PY, "r", encoding="utf-8") as f:
+            tree = ast.parse(f.read(), filename=_TEXT_BASIC_PY)
+        keep = [n for n in tree.body if isinstance(n, ast.Assign) and any(
+            isinstance(t, ast.Name) and t.id in ("_punctuation_strong", "_punctuation") for t in n.targets)]
+        ns = {"string": string}
+        exec(compile(ast.Module(body=keep, type_ignores=[]), _TEXT_BASIC_PY, "exec"), ns)
+        _punct = ns["_punctuation"]
+    return _punct
+
+
+def _pack_block():
+    global _pack_code
+    if _pack_code is None:
+        import textwrap
+        with open(_TOOL_PY, "r", encoding="utf-8") as f:
+            lines = f.read().split("\n")
+        first = next(i for i, l in enumerate(lines) if l.strip().startswith("global index, first_word_start"))
+        last = next(i for i in range(first, len(lines)) if lines[i].strip() == "idx_processed += 1")
+        _pack_code = compile(textwrap.dedent("\n".join(lines[first:last])), _TOOL_PY + ":pack", "exec")
+    return _pack_code
+
+
+def pack_words(word_spans, words, num_frames, ratio, utt_id, wavid, spk, start, max_duration,
+               refine_timestamps=0, skip_warnings=False):
+    """Run the reference's packing block.  word_spans: [(start_frame, end_frame)] per word.
+    -> dict(text, utt2spk, utt2dur, segments: the lines the reference appends to the Kaldi files; warnings)."""
+    import io
+    ns_align = namespace()
+    segs = [ns_align["Segment"](w, int(s), int(e), 1.0) for w, (s, e) in zip(words, word_spans)]
+    warnings = []
+
+    class _Log:
+        def warning(self, m):
+            warnings.append(m)
+
+        def info(self, m):
+            pass
+
+    files = {k: io.StringIO() for k in ("f_text", "f_utt2spk", "f_utt2dur", "f_segments")}
+    ns = dict(files)
+    ns.update(id=utt_id, wavid=wavid, id2spk={utt_id: spk}, start=start, end=0.0, max_duration=max_duration,
+              skip_warnings=skip_warnings, verbose=False, logger=_Log(), do_flush=lambda: None, debug_folder=None,
+              word_segments=segs, all_words=list(words), num_frames=num_frames, ratio=ratio,
+              refine_timestamps=refine_timestamps, _punctuation=reference_punctuation())
+    exec(_pack_block(), ns)
+    return {"text": files["f_text"].getvalue(), "utt2spk": files["f_utt2spk"].getvalue(),
+            "utt2dur": files["f_utt2dur"].getvalue(), "segments": files["f_segments"].getvalue(),
+            "warnings": len(warnings)}

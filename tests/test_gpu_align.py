@@ -251,3 +251,64 @@ def test_compute_alignments_batched_front_end():
     assert "".join(s.label for s in cs) == texts[0] and trellis.size(0) == ems[0].shape[0] + 1
     with pytest.raises(RuntimeError, match="Failed to align"):
         ssak_b200.compute_alignment_from_emission(ems[0][:5].cuda(), texts[0], labels, blank)
+
+
+def test_cut_kaldi_folder_batched_driver(tmp_path):
+    """SURVEY 8 f-3 end to end: a Kaldi folder with short and long utterances is cut at word boundaries, several
+    utterances per aligner launch; the output files equal what the oracle alignment of every utterance + the
+    (reference-pinned) packing gives, in input order."""
+    import ssak_b200
+    from ssak_b200 import cutter
+    from ssak_b200.synth import planted_emissions
+    labels = ["<pad>", "<s>", "</s>", "<unk>", " "] + list("abcdefghijklmnopqrstuvwxyz'-") + list("àâéèêëîïôùûç")
+    V, blank = len(labels), 0
+    dic = {c: i for i, c in enumerate(labels)}
+    texts = {"u1": "bonjour à tous", "u2": "oui", "u3": "c'est une phrase assez longue pour être coupée en deux ou trois",
+             "u4": "et celle-ci aussi , vraiment très longue ! n'est-ce pas", "u5": "non"}
+    durs = {"u1": 12.0, "u2": 1.0, "u3": 21.5, "u4": 17.25, "u5": 0.75}
+    d = tmp_path / "in"
+    d.mkdir()
+    (d / "text").write_text("".join(f"{k} {v}\n" for k, v in texts.items()), encoding="utf-8")
+    (d / "utt2spk").write_text("".join(f"{k} spk\n" for k in texts))
+    (d / "utt2dur").write_text("".join(f"{k} {v}\n" for k, v in durs.items()))
+    (d / "wav.scp").write_text("".join(f"{k} /data/{k}.wav\n" for k in texts))
+    g = torch.Generator().manual_seed(91)
+    ems = {}
+
+    def emission_fn(uid, path, start, end):
+        assert path == f"/data/{uid}.wav"
+        words = cutter.regroup_isolated_punctuation(texts[uid].split())
+        toks = [ssak_b200.loose_get_char_index(dic, c, dic[" "]) for c in " ".join(words)]
+        T = int(round((end - start) * 50))                     # 20 ms frames
+        ems[uid] = (planted_emissions(T, V, toks, g, blank), toks, words)
+        return ems[uid][0].cuda(), end - start
+
+    out = tmp_path / "out"
+    stats = cutter.cut_kaldi_folder(str(d), str(out), emission_fn, labels, blank, max_duration=5.0, batch_size=2)
+    assert stats["kept"] == 2 and stats["removed"] == 0 and stats["cut"] >= 6
+    exp = {"text": "", "segments": "", "utt2dur": "", "utt2spk": ""}
+    for uid in texts:
+        if durs[uid] <= 5.0:
+            exp["text"] += f"{uid} {texts[uid]}\n"
+            exp["utt2spk"] += f"{uid} spk\n"
+            exp["utt2dur"] += f"{uid} {durs[uid]}\n"
+            exp["segments"] += f"{uid} {uid} 0 {durs[uid]}\n"
+            continue
+        em, toks, words = ems[uid]
+        rc, ss, se, _, _ = O.align(em.numpy(), toks, blank, False)
+        assert rc == 0
+        spans, pos, chars = [], 0, " ".join(words)
+        for w in words:   # a word spans its non-blank, non-punctuation characters (align_transcriptions.py:381-385)
+            idx = list(range(pos, pos + len(w)))
+            keep = [i for i in idx if chars[i] != " " and chars[i] not in cutter.PUNCTUATION] or idx
+            spans.append((int(ss[keep[0]]), int(se[keep[-1]])))
+            pos += len(w) + 1
+        for c in cutter.pack_words(spans, words, em.shape[0], durs[uid] / em.shape[0], 0, 5.0):
+            if c.written:
+                nid = f"{uid}_cut{c.index:02}"
+                exp["text"] += f"{nid} {c.transcript}\n"
+                exp["utt2spk"] += f"{nid} spk\n"
+                exp["utt2dur"] += f"{nid} {c.end - c.start:.3f}\n"
+                exp["segments"] += f"{nid} {uid} {c.start:.3f} {c.end:.3f}\n"
+    for k, v in exp.items():
+        assert (out / k).read_text(encoding="utf-8") == v, k

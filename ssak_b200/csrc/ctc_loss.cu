@@ -122,7 +122,7 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     // (set below once the chunk is known: G <= chunk, every gradient warp owns a frame of every chunk)
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;   // kernels are instantiated for 8 and 4
-    if (c->G > c->chunk) c->G = c->chunk;            // no idle gradient warp may run ahead of the ring
+    if (c->G > c->chunk) c->G = c->chunk;            // every gradient warp owns a frame of every chunk
     // >= 3 stages: two chunks of look-ahead are needed to cover the HBM latency of the bulk copies
     int stages = (64 * 1024) / (c->chunk * c->slot_bytes);
     c->stages = stages > 4 ? 4 : stages;
@@ -138,7 +138,9 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     c->or_chunk = oc;
     c->or_stages = ost < 2 ? 2 : (ost > (few ? 3 : 8) ? (few ? 3 : 8) : ost);
     c->G = env_int("SSAK_CTC_G", c->G);
-    if (c->G > c->chunk) c->G = c->chunk;
+    // (on request only: 2*chunk gradient warps, pairs sharing a frame and taking half of its columns each --
+    //  measured slower at C5, 1.33 vs 0.85 ms: the extra warps cost resident CTAs)
+    if (c->G > c->chunk) c->G = (c->G >= 2 * c->chunk && V >= 256) ? 2 * c->chunk : c->chunk;
     c->or_chunk = env_int("SSAK_CTC_OR_CHUNK", c->or_chunk);
     c->or_stages = env_int("SSAK_CTC_OR_STAGES", c->or_stages);
     if (c->or_stages > 8 || c->or_stages < 2 || c->or_chunk < 1) return false;
@@ -742,6 +744,11 @@ ctc_lattice_kernel(const CtcParams p) {
         // Each gradient warp takes whole frames (frame f of a chunk goes to warp f mod G), so the
         // per-frame latency (barrier probe, run sums, exp, store) overlaps across warps.
         const int gwarp = warp - (W + NPROD), G = c.G;
+        // G <= CH: warp g takes the frames g, g+G, ... of a chunk.  G = 2 CH: warps g and g+CH share frame g and
+        // take the columns [0, V/2) and [V/2, V) (split at a multiple of 128 columns).
+        const int GF = G > CH ? CH : G, gf = gwarp % GF, gpart = gwarp / GF;
+        const int c_split = G > CH ? ((V / 2) & ~127) : V;
+        const int c_lo = gpart ? c_split : 0, c_hi = (G > CH && gpart == 0) ? c_split : V;
         float *grow_chunk = p.grad + (int64_t)t_first * p.gst + (int64_t)b * p.gsb;
         const unsigned char *em_chunk = em_base;
         int em_stage = 0, em_phase = 0;
@@ -782,7 +789,7 @@ ctc_lattice_kernel(const CtcParams p) {
             }
             mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
             const int pbuf = (chunk_idx & 1) * CH;
-            for (int f = gwarp; f < n; f += G) {
+            for (int f = gf; f < n; f += GF) {
                 const int slot = pbuf + f;
                 const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
                 mbar_wait(&post_full[slot], (uint32_t)((chunk_idx >> 1) & 1));
@@ -793,7 +800,7 @@ ctc_lattice_kernel(const CtcParams p) {
                     // dense pass: exp(lp) for every column, 128-bit loads and stores, no divergence
                     const float4 *row4 = reinterpret_cast<const float4 *>(rowb);
                     float4 *g4 = reinterpret_cast<float4 *>(grow);
-                    for (int it = lane; it < ncols; it += 32) {
+                    for (int it = (c_lo >> 2) + lane; it < (c_hi >> 2); it += 32) {
                         const float4 x = row4[it];
                         g4[it] = make_float4(ex2_approx(fmaf(x.x, kLog2e, zl)) * gs, ex2_approx(fmaf(x.y, kLog2e, zl)) * gs,
                                              ex2_approx(fmaf(x.z, kLog2e, zl)) * gs, ex2_approx(fmaf(x.w, kLog2e, zl)) * gs);
@@ -804,12 +811,14 @@ ctc_lattice_kernel(const CtcParams p) {
                     const int np = occ_start[V + 1];
                     for (int i = lane; i < np; i += 32) {
                         const int cc = cursor[i];
-                        grow[cc] = (ex2_approx(fmaf(row[cc], kLog2e, zl)) - label_mass(cc, w, slot)) * gs;
+                        if (cc >= c_lo && cc < c_hi)
+                            grow[cc] = (ex2_approx(fmaf(row[cc], kLog2e, zl)) - label_mass(cc, w, slot)) * gs;
                     }
                 } else {
                     const float *row = reinterpret_cast<const float *>(rowb);
                     int j = 0;
                     for (int cc = lane; cc < V; cc += 32, ++j) {
+                        if (cc < c_lo || cc >= c_hi) continue;
                         float val = ex2_approx(fmaf(row[cc], kLog2e, zl));
                         if (j >= 32 || ((present >> j) & 1u)) val -= label_mass(cc, w, slot);
                         grow[cc] = val * gs;

@@ -13,7 +13,7 @@ from ._lib import LIB_PATH, SsakB200Error, lib  # noqa: F401
 from .align import (AlignResult, Point, Segment, Trellis, backtrack, compute_alignment_from_emission,  # noqa: F401
                     compute_alignments, forced_align, get_trellis, loose_get_char_index, merge_repeats, merge_words,
                     segments_from_result)
-from .cutter import (Cut, KaldiCutWriter, cut_kaldi_folder, pack_words, parse_kaldi_wavscp, read_kaldi_folder,  # noqa: F401
+from .cutter import (Cut, KaldiCutWriter, chunked_emission, cut_kaldi_folder, pack_words, parse_kaldi_wavscp, read_kaldi_folder,  # noqa: F401
                      regroup_isolated_punctuation)
 from .greedy import argmax_ids, ctc_greedy_decode, greedy_ids, hf_collapse  # noqa: F401
 from .loss import ctc_loss, ctc_loss_from_logits, ctc_neg_log_likelihood, install, sb_ctc_loss, uninstall  # noqa: F401

@@ -203,6 +203,19 @@ def pack_words(word_spans: Sequence[Tuple[int, int]], words: Sequence[str], num_
     return cuts
 
 
+# ------------------------------------------------------------------------------------------- long audio
+def chunked_emission(infer_sub: Callable[[int, int], "object"], n_samples: int, max_len: int):
+    """Emissions of an audio longer than the acoustic model can take at once (SURVEY 8 f-4:
+    ssak/infer/transformers_infer.py:259-265, torchaudio_infer.py:49-56): `infer_sub(i, j)` returns the [1, T_ij, V]
+    (or [T_ij, V]) output for the samples [i, j); consecutive windows of `max_len` samples, concatenated along the
+    frame axis -- the seams are where the 10-minute alignments of config C3 come from."""
+    import torch
+    if n_samples <= max_len:
+        return infer_sub(0, n_samples)
+    parts = [infer_sub(i, min(i + max_len, n_samples)) for i in range(0, n_samples, max_len)]
+    return torch.cat(parts, dim=1 if parts[0].dim() == 3 else 0)
+
+
 # ------------------------------------------------------------------------------------------- driver
 def cut_kaldi_folder(dirin: str, dirout: str, emission_fn: Callable, labels: Sequence[str], blank_id: int,
                      max_duration: float = 30.0, min_duration: float = 0.005, refine_timestamps: float = 0,

@@ -798,37 +798,42 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
 
     if (warp == 0) {
         int t = t_start, j = L, first = 0;
-        constexpr int NRAW = LK == 0 ? 3 : 5;
-        uint32_t cw[3], raw[NRAW];
-        int cbase = 0, nbase = 0;
+        // The decision bits of a long alignment come from HBM (C3: 1 GB), ~1 us away, and a round of 32 frames
+        // walks in ~0.3 us: the bits are fetched DEPTH rounds ahead.  A fetch issued with the current state j covers
+        // the states [j - 32 (DEPTH+1) + 1, j], wherever the walk will be DEPTH rounds later.
+        constexpr int DEPTH = 3, SPAN = 32 * (DEPTH + 1);           // 128 states
+        constexpr int NRAW = LK == 0 ? SPAN / 32 + 1 : SPAN / 16 + 1;  // 5 ballot words / 9 lane-entry words
+        uint32_t cw[5], raw[DEPTH][NRAW];
+        int cbase = 0, nbase[DEPTH] = {0, 0, 0};
         // issue the loads of the "changed > stayed" bits of trellis row tt-lane for the states from sb0 (a multiple
         // of 16 or 32) on; nothing here waits for them
         auto fetch = [&](int tt, int jj, uint32_t *w, int &sb0) {
             const int rr = tt - lane;
             const uint32_t *rowp = bp_b + (int64_t)(rr - 1) * row_words;
             if (LK == 0) {
-                const int grp0 = max(jj - 63, 0) >> 5;
+                const int grp0 = max(jj - (SPAN - 1), 0) >> 5;
                 sb0 = grp0 << 5;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
+                for (int q = 0; q < NRAW; ++q) {
                     const int grp = grp0 + q;
                     w[q] = (rr >= 1 && grp < NW) ? __ldg(rowp + (grp / KK) * 2 * KK + (grp % KK)) : 0u;
                 }
             } else {
-                const int w0 = max(jj - 63, 0) >> 4;
+                const int w0 = max(jj - (SPAN - 1), 0) >> 4;
                 sb0 = w0 << 4;
 #pragma unroll
-                for (int q = 0; q < 5; ++q) w[q] = (rr >= 1 && w0 + q < row_words) ? __ldg(rowp + w0 + q) : 0u;
+                for (int q = 0; q < NRAW; ++q) w[q] = (rr >= 1 && w0 + q < row_words) ? __ldg(rowp + w0 + q) : 0u;
             }
         };
-        // raw words -> 96 consecutive state bits (first use of the loaded values)
+        // raw words -> 160 consecutive state bits (first use of the loaded values)
         auto compact = [&](const uint32_t *w, uint32_t *g) {
             if (LK == 0) {
-                g[0] = w[0]; g[1] = w[1]; g[2] = w[2];
-            } else {
-                uint32_t c[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
+                for (int q = 0; q < 5; ++q) g[q] = w[q];
+            } else {
+                uint32_t c[10];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
                     uint32_t x = w[q];
                     if (LK == 4) {
                         x &= 0x0f0f0f0fu;
@@ -838,19 +843,23 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
                     }
                     c[q] = (x | (x >> 8)) & 0xffffu;
                 }
-                g[0] = c[0] | (c[1] << 16);
-                g[1] = c[2] | (c[3] << 16);
-                g[2] = c[4];
+                c[9] = 0u;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) g[q] = c[2 * q] | (c[2 * q + 1] << 16);
             }
         };
-        if (t > 0) fetch(t, j, raw, nbase);
-        while (t > 0 && j > 0) {
-            compact(raw, cw);
-            cbase = nbase;
-            if (t > 32) fetch(t - 32, j, raw, nbase);  // next 32 frames: in flight during the walk
+        // one round of 32 frames on the buffer `u` (compile-time index: the buffers rotate through an unrolled loop)
+        auto round32 = [&](auto u_tag) {
+            constexpr int U = decltype(u_tag)::value;
+            compact(raw[U], cw);
+            cbase = nbase[U];
+            if (t > 32 * DEPTH) fetch(t - 32 * DEPTH, j, raw[U], nbase[U]);  // DEPTH rounds ahead, in flight meanwhile
             const int base = max(j - 31, 0);
-            const int off = base - cbase;             // 0 <= off < 64
-            uint32_t win = off < 32 ? __funnelshift_r(cw[0], cw[1], off) : __funnelshift_r(cw[1], cw[2], off - 32);
+            const int off = base - cbase;             // 0 <= off < 128
+            const int kq = off >> 5;
+            const uint32_t lo = kq == 0 ? cw[0] : (kq == 1 ? cw[1] : (kq == 2 ? cw[2] : cw[3]));
+            const uint32_t hi = kq == 0 ? cw[1] : (kq == 1 ? cw[2] : (kq == 2 ? cw[3] : cw[4]));
+            uint32_t win = __funnelshift_r(lo, hi, off & 31);
             if (base == 0) win &= ~1u;                // state 0 never "changes": the walk parks there (:119-120)
             const uint32_t valid = t >= 32 ? 0xffffffffu : ((1u << t) - 1u);  // step i looks at frame t-1-i >= 0
             // all 32 windows first (independent shuffles), then the dependent chain: shift, mask, subtract
@@ -873,6 +882,17 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
             j = base + sh;
             if (t - 1 - lane >= 0) rec[t - 1 - lane] = mine;
             t -= 32;
+        };
+        // prologue: the first DEPTH rounds are fetched with the start state (their windows still cover the walk)
+        if (t > 0) fetch(t, j, raw[0], nbase[0]);
+        if (t > 32) fetch(t - 32, j, raw[1], nbase[1]);
+        if (t > 64) fetch(t - 64, j, raw[2], nbase[2]);
+        while (t > 0 && j > 0) {
+            round32(std::integral_constant<int, 0>{});
+            if (!(t > 0 && j > 0)) break;
+            round32(std::integral_constant<int, 1>{});
+            if (!(t > 0 && j > 0)) break;
+            round32(std::integral_constant<int, 2>{});
         }
         if (lane == 0) {
             const bool ok = j == 0 && L > 0 && t_start > 0;

@@ -869,16 +869,23 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
                 const uint32_t g = __shfl_sync(FULL, win, i);
                 gi[i] = (valid >> i) & 1u ? g : 0u;
             }
-            int sh = j - base;                        // 0 <= sh <= 31, state = base + sh
-            uint32_t mine = 0;
+            // dependent chain per frame: shift, mask, subtract; the decisions are collected in one word and every
+            // lane reconstructs its own frame's state afterwards (state = start - number of earlier decisions)
+            const int sh0 = j - base;                 // 0 <= sh <= 31, state = base + sh
+            int sh = sh0;
+            uint32_t dec = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const uint32_t bit = (gi[i] >> sh) & 1u;  // :117 changed > stayed -> previous token
-                const uint32_t r = ((uint32_t)(base + sh) << 1) | bit;
-                mine = lane == i ? r : mine;
+                dec += bit << i;
                 sh -= (int)bit;
-                first = (bit && base + sh == 0) ? t - i - 1 : first;  // :119-120 the path starts at this frame
             }
+            const int j_mine = base + sh0 - __popc(dec & ((1u << lane) - 1u));   // state at frame t-1-lane
+            const uint32_t bit_mine = (dec >> lane) & 1u;
+            const uint32_t mine = ((uint32_t)j_mine << 1) | bit_mine;
+            // :119-120 the path starts at the frame whose decision leaves state 1 (only one lane can see that)
+            const unsigned starts_here = __ballot_sync(FULL, bit_mine && j_mine == 1);
+            if (starts_here) first = t - 1 - (__ffs(starts_here) - 1);
             j = base + sh;
             if (t - 1 - lane >= 0) rec[t - 1 - lane] = mine;
             t -= 32;

@@ -32,7 +32,8 @@ def _worker(rank, world, port, reduction, out):
         loss = sharded_ctc_loss(x, tg[mine], il[mine], tl[mine], reduction=reduction, zero_infinity=True,
                                 global_batch=10, loss_fn=_cpu_loss)
         loss.backward()
-        out.put((rank, mine, float(loss), x.grad.clone()))
+        # plain numpy through the queue: a torch tensor travels as a shared-memory handle that dies with the worker
+        out.put((rank, mine, float(loss), x.grad.detach().numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -55,7 +56,7 @@ def test_sharded_loss_matches_single_process(reduction):
     ref.backward()
     seen = []
     for rank, mine, loss, grad in results:
-        assert abs(loss - float(ref)) <= 5e-5 * abs(float(ref))   # fp32 sums in a different order
-        assert torch.allclose(grad, x.grad[:, mine], atol=1e-6)
+        assert abs(loss - float(ref)) <= 5e-5 * abs(float(ref)), (rank, loss, float(ref), mine)   # fp32 sums in a different order
+        assert torch.allclose(torch.from_numpy(grad), x.grad[:, mine], atol=1e-6)
         seen += mine
     assert sorted(seen) == list(range(10))

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssak_b200.so")
+LIB_PATH = os.environ.get("SSAK_B200_LIB") or os.path.join(_HERE, "libssak_b200.so")   # (override: A/B runs of two builds)
 
 _p, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 

@@ -62,6 +62,12 @@ struct CtcCfg {
 };
 // Row layout (floats): [0,P_pad) blank states | [P_pad] spare | [P_pad+1, 2P_pad+1) label states
 //                      | [2P_pad+2, 2P_pad+4) fp64 re-centring offset | pad to 2P_pad+8.
+// [2P_pad+4] of a frontier row holds Kf: 0 when the barrier forward wrote the rows, else the chain elements per
+// lane of the wavefront forward.
+// Offset tables (Kf > 0 only).  The wavefront forward re-centres per warp, by integers: the states of its warp w
+// (chain elements [32 Kf w, 32 Kf (w+1)); element c = pair c for alpha, pair L-c for beta) are relative to
+// row offset + table[w], table = tabs[b][dir][forward chunk of the frame] (frontier: slot NCH-1).  The stored
+// states thus stay small wherever the probability mass sits; consumers add the integers back exactly.
 // Label p lives at P_pad+1+p.  The beta CTA's thread for pair q owns (label q-1, blank q), i.e.
 // positions (P_pad+q, q): both directions use immediate offsets from one per-thread base.
 
@@ -81,6 +87,8 @@ struct CtcParams {
     float *finals;  // [B][2][row_elems] frontier rows
     float *rows;    // [B][T][row_elems] half lattices (saved for backward)
     float *zl;      // [T][B] -log2(sum_v exp(x[t,b,v])) when the input holds raw logits, else nullptr
+    float *tabs;    // [B][2][NCH][16] per-warp offset tables of the wavefront forward (see "offset tables")
+    int NCH;        // table slots per (utterance, direction): one per forward chunk, the last one for the frontier
     float *nll;     // [B] out / in
     const float *grad_out;
     float *grad;
@@ -265,11 +273,12 @@ ctc_lattice_kernel(const CtcParams p) {
         nll2 = p.nll2[b];
     }
 
-    const int n_consumers = W + (GRAD ? c.G : 0) + PW;
+    const int n_consumers = W + (GRAD ? c.G : 0) + PW;   // every warp but the producers
+    const int n_em = W + (GRAD ? c.G : 0);               // warps that read the emission ring
     if (tid == 0) {
         for (int s = 0; s < c.stages; ++s) {
             mbar_init(&em_full[s], 1);
-            mbar_init(&em_empty[s], n_consumers);
+            mbar_init(&em_empty[s], n_em);
         }
         for (int s = 0; s < c.or_stages; ++s) {
             mbar_init(&or_full[s], 1);
@@ -389,13 +398,30 @@ ctc_lattice_kernel(const CtcParams p) {
     const int lab_pos = P_pad + 1 - dir + pbase;  // row position of my k=0 label state
     if (compute) {
         const float *fin = p.finals + ((int64_t)b * 2 + dir) * row_elems;
-        if (GRAD) off_mine = *reinterpret_cast<const double *>(fin + 2 * P_pad + 2);
+        // frontier written by the wavefront forward: per-warp offsets (see "offset tables"); continue from the
+        // largest one, so that the states that matter start out small
+        const int Kf = GRAD ? (int)fin[2 * P_pad + 4] : 0;
+        const float *tab = p.tabs + (((int64_t)b * 2 + dir) * p.NCH + (p.NCH - 1)) * 16;
+        float Dmax = 0.f;
+        if (GRAD) {
+            off_mine = *reinterpret_cast<const double *>(fin + 2 * P_pad + 2);
+            if (Kf > 0) {
+                const int nsl = L / (32 * Kf) + 1;
+                Dmax = tab[0];
+                for (int w = 1; w < nsl; ++w) Dmax = fmaxf(Dmax, tab[w]);
+                off_mine += (double)Dmax;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int pp = pbase + k * 32;
             if (GRAD) {
-                ab[k] = pp <= L ? fin[pp] : kNeg;                                        // pairs beyond L
-                al[k] = lab_off[k] == c.slot_bytes - 16 ? kNeg : fin[lab_pos + k * 32];  // states beyond 2L+1
+                const int li = dir ? pp - 1 : pp;
+                const int cb_ = dir ? L - pp : pp, cl_ = dir ? L - li - 1 : li;   // chain elements of my two states
+                const float tb_ = Kf > 0 && pp <= L ? tab[cb_ / (32 * Kf)] - Dmax : 0.f;
+                const float tl_ = Kf > 0 && li >= 0 && li < L ? tab[cl_ / (32 * Kf)] - Dmax : 0.f;
+                ab[k] = pp <= L ? fin[pp] + tb_ : kNeg;                                        // pairs beyond L
+                al[k] = lab_off[k] == c.slot_bytes - 16 ? kNeg : fin[lab_pos + k * 32] + tl_;  // states beyond 2L+1
             } else {
                 ab[k] = pp == (dir ? L : 0) ? 0.f : kNeg;
                 al[k] = kNeg;
@@ -531,6 +557,7 @@ ctc_lattice_kernel(const CtcParams p) {
                 float r[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) r[k] = __shfl_sync(FULL, al[k], nb_lane);
+                float pre_b[K], pre_l[K];  // the states before the emission is added (what a posterior needs)
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float seamv = DIR ? (k == K - 1 ? xin : r[k < K - 1 ? k + 1 : k])
@@ -538,9 +565,10 @@ ctc_lattice_kernel(const CtcParams p) {
                     const float carry = sel(seam_m, seamv, r[k]);
                     const float A = lse2(ab[k], carry);
                     const float oth = sel(skip_m[k], A, ab[k]);
-                    const float nlab = lse2(al[k], oth) + el2[k];
+                    pre_b[k] = A;
+                    pre_l[k] = lse2(al[k], oth);
                     ab[k] = A + eb2;
-                    al[k] = nlab;
+                    al[k] = pre_l[k] + el2[k];
                 }
                 if (is_out) x_out[((f & 1) ^ 1) * 18] = DIR ? al[0] : al[K - 1];
                 if (f == CH - 1) {  // publish the row maximum for the next chunk's re-centring
@@ -566,9 +594,9 @@ ctc_lattice_kernel(const CtcParams p) {
                     // hand my states of this frame to my posterior warp (state ring, buffer of this chunk)
                     float *sr = sring + (size_t)(pbuf + f) * 2 * P_pad + pbase;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        sr[k * 32] = ab[k];
-                        sr[P_pad + k * 32] = al[k];
+                    for (int k = 0; k < K; ++k) {   // alpha + beta - lp = (state before its emission) + other direction
+                        sr[k * 32] = pre_b[k];
+                        sr[P_pad + k * 32] = pre_l[k];
                     }
                     if (f == n - 1) {
                         __syncwarp();
@@ -628,6 +656,7 @@ ctc_lattice_kernel(const CtcParams p) {
                     // re-centre on the row maximum published at the end of the previous chunk
                     float mx = wmax[0];
                     for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
+                    mx = floorf(mx);  // integer amounts: the subtraction is exact, every stored offset an integer
                     if (mx > kNegTest) {
 #pragma unroll
                         for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
@@ -665,53 +694,69 @@ ctc_lattice_kernel(const CtcParams p) {
         // the other direction's stored row (row ring), label posteriors into the label-sorted posterior ring,
         // blank posteriors summed in fixed point.  Everything here is off the serial chain of the recursion.
         const int lab_delta = P_pad + 1 - dir;
+        // offset-table slots of my states in the OTHER direction's rows (see "offset tables"; Kf = 0: none)
+        const int Kf = (int)(p.finals + ((int64_t)b * 2 + dir) * row_elems)[2 * P_pad + 4];
+        const bool tab_on = Kf > 0;
+        const float *otabs = p.tabs + ((int64_t)b * 2 + (1 - dir)) * p.NCH * 16;
+        int tsb[K], tsl[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int pp = pbase + k * 32, li = dir ? pp - 1 : pp;
+            const int cbo = dir ? pp : L - pp, clo = dir ? li : L - li - 1;
+            tsb[k] = (tab_on && pp <= L) ? cbo / (32 * Kf) : 0;
+            tsl[k] = (tab_on && li >= 0 && li < L) ? clo / (32 * Kf) : 0;
+        }
         const unsigned char *or_row = or_slots;
         int or_slot = 0, or_left = 0, ostage = 0, ophase = 0;
         unsigned char *wl_bytes = reinterpret_cast<unsigned char *>(wlab);
-        int em_stage = 0, em_phase = 0, remaining = nsteps, chunk_idx = 0;
-        const unsigned char *em_chunk = em_base;
-        const float *z_ptr = LOGITS ? p.zl + (int64_t)t_first * p.B + b : nullptr;
-        const int64_t z_step = (int64_t)dt * p.B;
-        auto z_fetch = [&](int step0) -> float {
-            const int sidx = step0 + lane;
-            return (LOGITS && lane < CH && sidx < nsteps) ? __ldg(z_ptr + (int64_t)sidx * z_step) : 0.f;
-        };
-        float zv = 0.f, zv_next = z_fetch(0);
+        int remaining = nsteps, chunk_idx = 0;
         while (remaining > 0) {
             const int n = remaining < CH ? remaining : CH;
-            if (LOGITS) {
-                zv = zv_next;
-                zv_next = z_fetch((chunk_idx + 1) * CH);
-            }
             const int buf = chunk_idx & 1, pbuf = buf * CH;
-            mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
             mbar_wait(&st_full[rw * 2 + buf], (uint32_t)((chunk_idx >> 1) & 1));   // the chunk's states are there
             if (chunk_idx >= 2)  // the gradient warps must be done with this posterior buffer
                 mbar_wait(&post_empty[buf], (uint32_t)(((chunk_idx >> 1) - 1) & 1));
-            const double base_d = sbase[rw * 2 + buf];
-            for (int f = 0; f < n; ++f) {
-                const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
-                const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
-                const float xb = *reinterpret_cast<const float *>(row + blank_off);
-                const float eb2 = fmaxf(LOGITS ? fmaf(xb, kLog2e, zl) : xb * kLog2e, kNeg);
-                if (or_left == 0) {
+            // bracket = base + row offset (+ table entry).  Row offsets and table entries are integers below 2^24
+            // (exact in fp32): only the base has a fraction, split off once per chunk -- no fp64 per frame or state.
+            const double base_d = sbase[rw * 2 + buf], base_fl = floor(base_d);
+            const float base_i = (float)base_fl, br_f = (float)(base_d - base_fl);
+            // offset tables: the other direction computed my frames in DEcreasing step order, so this chunk sees at
+            // most two of its chunks -- table A for the frames f <= fsw, table B = the one before it afterwards
+            float ta_b[K], ta_l[K], tb_b[K], tb_l[K];
+            int fsw = CH;
+            {
+                const int t0 = t_first + dt * (chunk_idx * CH);
+                const int tau0o = dir ? t0 : Tb - 1 - t0;          // the other direction's forward step of frame 0
+                fsw = tau0o % CH;
+                const float *pa = otabs + (tau0o / CH) * 16, *pb = pa - (tau0o >= CH ? 16 : 0);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    ta_b[k] = tab_on ? __ldg(pa + tsb[k]) : 0.f;
+                    ta_l[k] = tab_on ? __ldg(pa + tsl[k]) : 0.f;
+                    tb_b[k] = tab_on ? __ldg(pb + tsb[k]) : 0.f;
+                    tb_l[k] = tab_on ? __ldg(pb + tsl[k]) : 0.f;
+                }
+            }
+            const bool chunked_rows = Co == CH;   // the row ring's stages are this loop's chunks: wait / release once
+            if (chunked_rows) mbar_wait(&or_full[ostage], (uint32_t)ophase);
+            auto pframe = [&](const int f) {
+                if (!chunked_rows && or_left == 0) {
                     mbar_wait(&or_full[ostage], (uint32_t)ophase);
                     or_left = Co;
                 }
                 const float *orow = reinterpret_cast<const float *>(or_row) + pbase;
-                const double ooff = *reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
-                const float bracket = (float)(base_d + ooff);
-                const float cb = bracket - eb2;
+                const float br_i = base_i + (float)*reinterpret_cast<const double *>(or_row + (2 * P_pad + 2) * 4);
+                const bool useA = f <= fsw;
                 const float *sr = sring + (size_t)(pbuf + f) * 2 * P_pad + pbase;
                 unsigned char *wl = wl_bytes + (pbuf + f) * (WL * 4);
                 float sbl = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float x = *reinterpret_cast<const float *>(row + lab_off[k]);
-                    const float el2 = fmaxf(LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e, kNeg);
-                    sbl += ex2_approx(sr[k * 32] + sel(bl_m[k], orow[k * 32], kNeg) + cb);
+                for (int k = 0; k < K; ++k) {   // (the state ring holds the states before their emission: no lp here)
+                    const float br_b = (br_i + (useA ? ta_b[k] : tb_b[k])) + br_f;
+                    const float br_l = (br_i + (useA ? ta_l[k] : tb_l[k])) + br_f;
+                    sbl += ex2_approx(sr[k * 32] + sel(bl_m[k], orow[k * 32], kNeg) + br_b);
                     *reinterpret_cast<float *>(wl + wl_off[k]) =
-                        ex2_approx(sr[P_pad + k * 32] + orow[lab_delta + k * 32] + (bracket - el2));
+                        ex2_approx(sr[P_pad + k * 32] + orow[lab_delta + k * 32] + br_l);
                 }
                 const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
                 const unsigned tot = __reduce_add_sync(FULL, fx);
@@ -721,23 +766,30 @@ ctc_lattice_kernel(const CtcParams p) {
                     mbar_arrive(&post_full[pbuf + f]);  // release: this warp's posteriors of the frame
                 }
                 or_row += row_bytes;
-                if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
-                if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
-                    or_left = 0;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&or_empty[ostage]);
-                    if (++ostage == No) { ostage = 0; ophase ^= 1; }
+                if (!chunked_rows) {
+                    if (++or_slot == or_nslots) { or_slot = 0; or_row = or_slots; }
+                    if (--or_left == 0 || (f == n - 1 && remaining == n)) {  // stage done / last frame
+                        or_left = 0;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&or_empty[ostage]);
+                        if (++ostage == No) { ostage = 0; ophase ^= 1; }
+                    }
                 }
+            };
+            // (a compact loop on purpose: three big code regions -- recursion, posterior, gradient -- share the
+            //  instruction cache of the SM; unrolling this one made the backward 15 % slower)
+#pragma unroll 1
+            for (int f = 0; f < n; ++f) pframe(f);
+            if (chunked_rows) {   // release the row-ring stage; a partial last chunk still owns a whole stage
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&or_empty[ostage]);
+                if (++ostage == No) { ostage = 0; ophase ^= 1; or_row = or_slots; }
+                else or_row = or_slots + (size_t)ostage * Co * row_bytes;
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&em_empty[em_stage]);
-                mbar_arrive(&st_empty[rw * 2 + buf]);
-            }
+            if (lane == 0) mbar_arrive(&st_empty[rw * 2 + buf]);
             remaining -= n;
             ++chunk_idx;
-            em_chunk += CH * slot_bytes;
-            if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
         }
     } else if (GRAD) {
         // ---------------- gradient warps: consume the posterior ring, mbarriers only ----------------
@@ -848,7 +900,10 @@ ctc_lattice_kernel(const CtcParams p) {
                 fin[k * 32] = ab[k];
                 fin[P_pad + 1 - dir + k * 32] = al[k];
             }
-            if (tid == 0) *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = off_mine;
+            if (tid == 0) {
+                *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = off_mine;
+                fin[2 * P_pad + 4] = 0.f;   // Kf = 0: barrier format, no offset tables
+            }
         }
     } else if (dir == 0) {
         const int nthr = n_consumers * 32, me = compute ? tid : tid - 32 * NPROD;  // every warp but the producers
@@ -869,9 +924,9 @@ ctc_lattice_kernel(const CtcParams p) {
 // body is branch-free and unrolled over the chunk, stores to shared memory happen once per chunk.
 //   Re-centring is per warp and by INTEGER amounts (exact in fp32; offsets add up exactly in int32): every chunk a
 // warp subtracts floor(max of its states).  With the seam values travel the sender's offset and the offset of
-// the chain's first warp; the latter is the one offset stored with every saved row, values are converted on the
-// way out (v + (off_w - off_row)), so the row format is exactly what ctc_lattice_kernel<.., GRAD> and
-// ctc_join_kernel read.
+// the chain's first warp; the latter is the row offset stored with every saved row, and every warp records
+// off_w - off_row per chunk in the offset tables (see "offset tables"): the stored states stay small wherever the
+// probability mass sits, the posterior warps / the join kernel add the integers back exactly.
 struct FwdWaveSmem {
     int em_full, em_empty, seam, ring, total;
 };
@@ -1016,6 +1071,9 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
     const unsigned char *em_base = ring.slots, *em_chunk = em_base;
     int em_stage = 0, em_phase = 0, remaining = nsteps, sslot = 0, step0 = 0;
     int off_me = 0, off_row = 0;                     // integer log2 offsets: true value = state + off
+    bool has_mass = false;
+    int chunk_no = 0;
+    float *tabs_bd = p.tabs + ((int64_t)b * 2 + dir) * p.NCH * 16;
     float ds = 0.f;                                  // off_me - off_row: conversion to the stored row's offset
     double off_row_d = 0.0;
     const bool inlane = lane < SW;
@@ -1068,9 +1126,9 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         if (SAVE) {
             float *r = row_out + (int64_t)f * row_step;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                r[bpos[k]] = ab[k] + ds;
-                r[lpos[k]] = al[k] + ds;
+            for (int k = 0; k < K; ++k) {   // relative to row offset + my table entry (see "offset tables")
+                r[bpos[k]] = ab[k];
+                r[lpos[k]] = al[k];
             }
             if (first && lane == 0) *reinterpret_cast<double *>(r + 2 * P_pad + 2) = off_row_d;
         }
@@ -1084,7 +1142,8 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
 #pragma unroll
             for (int k = 0; k < K; ++k) mx = fmaxf(mx, fmaxf(ab[k], al[k]));
             mx = floorf(warp_max(mx));
-            if (mx > kNegTest && mx != 0.f) {
+            has_mass = mx > kNegTest;
+            if (has_mass && mx != 0.f) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) { ab[k] -= mx; al[k] -= mx; }
                 off_me += (int)mx;
@@ -1099,6 +1158,9 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
             if (inlane) const_cast<float *>(sv_in)[sslot * SW + lane] = EMPTY;  // recycle the slot
             const int off_up = (int)__shfl_sync(FULL, sv, CH);
             off_row = (int)__shfl_sync(FULL, sv, CH + 1);
+            // a warp the probability mass has not reached yet (all states log 0) follows the row offset, so that
+            // its table entry stays 0 and the first mass enters it in the row's scale
+            if (!has_mass) off_me = off_row;
             // the sender's values are relative to its offset: bring them to mine (lanes >= CH are not used)
             sv += (float)(off_up - off_me);
         } else {
@@ -1106,6 +1168,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         }
         ds = (float)(off_me - off_row);
         off_row_d = (double)off_row;
+        if (SAVE && lane == 0) tabs_bd[chunk_no * 16 + warp] = ds;   // this chunk's table entry of my warp
         const int sslot_next = sslot + 1 == NSLOT ? 0 : sslot + 1;
         sv_pre = fetch_seam(sslot_next);
         if (LOGITS) {
@@ -1132,6 +1195,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         __syncwarp();
         if (lane == 0) mbar_arrive(&em_empty[em_stage]);
         remaining -= n;
+        ++chunk_no;
         if (SAVE) row_out += (int64_t)n * row_step;
         em_chunk += CH * slot_bytes;
         if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
@@ -1142,10 +1206,14 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         float *fin = p.finals + ((int64_t)b * 2 + dir) * row_elems;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            fin[bpos[k]] = ab[k] + ds;
-            fin[lpos[k]] = al[k] + ds;
+            fin[bpos[k]] = ab[k];
+            fin[lpos[k]] = al[k];
         }
-        if (first && lane == 0) *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = (double)off_row;
+        if (lane == 0) tabs_bd[(p.NCH - 1) * 16 + warp] = ds;   // the frontier's table
+        if (first && lane == 0) {
+            *reinterpret_cast<double *>(fin + 2 * P_pad + 2) = (double)off_row;
+            fin[2 * P_pad + 4] = (float)K;
+        }
     }
 }
 
@@ -1161,6 +1229,20 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     const float *fb = fa + row_elems;
     const float *fal = fa + P_pad + 1, *fbl = fb + P_pad + 1;  // label p at [p]
     const int32_t *tg = p.targets + p.tgt_off[b];
+    // per-warp offset tables of the wavefront forward (see "offset tables"; Kf = 0: none): every frontier is
+    // taken relative to its largest table entry
+    const int Kf = (int)fa[2 * P_pad + 4], span = Kf > 0 ? 32 * Kf : 1 << 30;
+    const float *ta = p.tabs + (((int64_t)b * 2 + 0) * p.NCH + (p.NCH - 1)) * 16, *tb = ta + (int64_t)p.NCH * 16;
+    float Da = 0.f, Db = 0.f;
+    if (Kf > 0) {
+        Da = ta[0];
+        Db = tb[0];
+        for (int w = 1; w <= L / span; ++w) { Da = fmaxf(Da, ta[w]); Db = fmaxf(Db, tb[w]); }
+    }
+    auto A_blank = [&](int pp) { return fa[pp] + (Kf > 0 ? ta[pp / span] - Da : 0.f); };             // alpha: element = pair
+    auto A_label = [&](int li) { return fal[li] + (Kf > 0 ? ta[li / span] - Da : 0.f); };
+    auto B_blank = [&](int pp) { return fb[pp] + (Kf > 0 ? tb[(L - pp) / span] - Db : 0.f); };       // beta: element = L - pair
+    auto B_label = [&](int li) { return fbl[li] + (Kf > 0 ? tb[(L - li - 1) / span] - Db : 0.f); };
     float mx = kNeg, sm = 0.f;  // running max and sum of 2^(x - mx)
     auto push = [&](float x) {
         const float nm = fmaxf(mx, x);
@@ -1168,14 +1250,14 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
         mx = nm;
     };
     for (int pp = tid; pp <= L; pp += 256) {
-        const float a_b = fa[pp];
-        const float a_lp = pp > 0 ? fal[pp - 1] : kNeg;
+        const float a_b = A_blank(pp);
+        const float a_lp = pp > 0 ? A_label(pp - 1) : kNeg;
         const float A = lse2(a_b, a_lp);
-        push(A + fb[pp]);
+        push(A + B_blank(pp));
         if (pp < L) {
             bool skip = false;
             if (pp > 0) skip = tg[pp] != tg[pp - 1];
-            push(lse2(fal[pp], skip ? A : a_b) + fbl[pp]);
+            push(lse2(A_label(pp), skip ? A : a_b) + B_label(pp));
         }
     }
 #pragma unroll
@@ -1197,7 +1279,7 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
         const bool dead = M < kNegTest;
         const double off_a = *reinterpret_cast<const double *>(fa + 2 * P_pad + 2);
         const double off_b = *reinterpret_cast<const double *>(fb + 2 * P_pad + 2);
-        const double logp2 = (double)M + (double)log2f(S) + off_a + off_b;
+        const double logp2 = (double)M + (double)log2f(S) + off_a + off_b + (double)Da + (double)Db;
         p.nll[b] = dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453);
         p.nll2[b] = -logp2;
     }
@@ -1374,14 +1456,13 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
 
 // The wavefront forward kernel when the shape fits it (SSAK_ERR_UNSUPPORTED -> the barrier kernel is used).
 static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
-    // Used by default for loss-only calls (no rows saved) on few CTAs (at most one per SM: latency-bound, the
-    // wavefront is ~25 % faster).  Not for training steps: a saved row carries ONE offset, here the first warp's,
-    // and once the probability mass has left that warp the states that matter are stored as large numbers
-    // (ulp(800) = 6e-5): the C2 gradient error grows from 6e-6 to 2.6e-4.  With several CTAs per SM the barrier
-    // kernel's fatter lanes issue fewer instructions per cell (1.25 vs 1.54 ms at B = 1024).
-    // SSAK_CTC_FWD_WAVE=1 forces it (tests), =0 disables it.
+    // Used on few CTAs (at most one per SM: latency-bound, the wavefront is ~25 % faster); with several CTAs per SM
+    // the barrier kernel's fatter lanes issue fewer instructions per cell (1.25 vs 1.54 ms at B = 1024).  Rows
+    // saved for the backward come with per-warp offset tables, which only the posterior warps (cfg.PW > 0) read.
+    // SSAK_CTC_FWD_WAVE=1 forces it where it is valid, =0 disables it.
     const int mode = env_int("SSAK_CTC_FWD_WAVE", -1);
-    if (mode == 0 || (mode < 0 && (p.rows != nullptr || 2 * p.B > 2 * 148))) return SSAK_ERR_UNSUPPORTED;
+    if (mode == 0 || (mode < 0 && 2 * p.B > 2 * 148)) return SSAK_ERR_UNSUPPORTED;
+    if (p.rows != nullptr && p.cfg.PW == 0) return SSAK_ERR_UNSUPPORTED;
     const int64_t P = (int64_t)p.Lmax + 1;
     if (P > 1024 || p.T > 100000) return SSAK_ERR_UNSUPPORTED;   // 32 * 4 * 8 chain elements; float-exact offsets
     FwdWaveCfg wc;
@@ -1421,13 +1502,15 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
-struct WsLayout { size_t nll2, finals, zl, rows, total; };
+struct WsLayout { size_t nll2, finals, zl, tabs, rows, total; };
+static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
 static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
     WsLayout w;
     size_t o = 0;
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
     w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
+    w.tabs = o;   o += align_up((size_t)B * 2 * tab_slots(T) * 16 * sizeof(float), 256);
     w.rows = o;   if (saved) o += align_up((size_t)B * (size_t)T * row_elems * sizeof(float), 256);
     w.total = o + 256;
     return w;
@@ -1442,6 +1525,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     if (T < 0 || B <= 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V || T > 0x7ffffff0 ||
         V > (1 << 20) || B > 65535 * 32)
         return SSAK_ERR_INVALID_ARGUMENT;
+    if (T > 300000) return SSAK_ERR_UNSUPPORTED;  // re-centring offsets are kept exact as fp32 integers (< 2^24)
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     if (!choose_cfg(Lmax, B, (int)V, &p->cfg)) return SSAK_ERR_UNSUPPORTED;
     const WsLayout w = ws_layout(T, B, p->cfg.row_elems, saved);
@@ -1454,6 +1538,8 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->finals = reinterpret_cast<float *>(ws + w.finals);
     p->rows = saved ? reinterpret_cast<float *>(ws + w.rows) : nullptr;
     p->zl = logits ? reinterpret_cast<float *>(ws + w.zl) : nullptr;
+    p->tabs = reinterpret_cast<float *>(ws + w.tabs);
+    p->NCH = tab_slots(T);
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
     return SSAK_OK;

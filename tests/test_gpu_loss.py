@@ -297,14 +297,8 @@ def test_loss_forward_kernels_agree(fwd, monkeypatch):
             il[3], tl[3] = 4, 3
         loss, grad = _ours(lp, tg, il, tl, 0, "none", True)
         rl, rg = _torch_cpu(lp, tg, il, tl, 0, "none", True)
-        if fwd.startswith("wave") and T > 1000:
-            # long utterances: the wavefront forward stores rows against the first warp's offset, the gradient is
-            # only good to ~5e-4 there (why it is not the default for training steps); the loss itself is exact
-            _assert_close(loss, rg.float(), rl, rg, f"{fwd}/{seed}")
-            assert (grad.double() - rg).abs().max().item() <= 1e-3
-        else:
-            _assert_close(loss, grad, rl, rg, f"{fwd}/{seed}")
-        # loss-only call (no gradient requested): the default route of the wavefront kernel
+        _assert_close(loss, grad, rl, rg, f"{fwd}/{seed}")
+        # loss-only call (no gradient requested, no rows saved)
         import ssak_b200
         with torch.no_grad():
             l2 = ssak_b200.ctc_loss(lp.cuda(), tg, il, tl, 0, "none", True).cpu()

@@ -68,6 +68,8 @@ SSAK_API int ssak_b200_last_cuda_error(void);
  *   input_lengths    int32 [B]    (0 <= . <= T)
  *   target_lengths   int32 [B]    (0 <= . <= max_target_len)
  *   max_target_len   host upper bound on target_lengths (sizes the launch and workspace)
+ * Limits: max_target_len <= 4095, T <= 300000 (SSAK_ERR_UNSUPPORTED beyond: the re-centring
+ * offsets are kept exact as fp32 integers).
  * ======================================================================================= */
 
 /* Workspace size for forward(+backward).  save_for_backward == 0: join rows only. */

@@ -1552,7 +1552,7 @@ using namespace ssak;
 extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t max_target_len,
                                                 int save_for_backward) {
     CtcCfg c;
-    if (T < 0 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
+    if (T < 0 || T > 300000 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
     return ws_layout(T, B, c.row_elems, save_for_backward != 0).total;
 }
 

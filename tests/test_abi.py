@@ -48,6 +48,8 @@ def test_ctypes_table_matches_header_and_loads():
     assert 0 < small < L.ssak_ctc_loss_workspace_bytes(200, 4, 20, 1)
     assert L.ssak_ctc_loss_workspace_bytes(100, 4, 20, 0) < small
     assert L.ssak_ctc_loss_workspace_bytes(100, 4, 100000, 1) == 0
+    assert L.ssak_ctc_loss_workspace_bytes(300001, 1, 10, 1) == 0      # T limit of the loss (exact fp32 offsets)
+    assert L.ssak_ctc_loss_workspace_bytes(300000, 1, 10, 0) > 0
     assert L.ssak_align_workspace_bytes(16, 30000, 8000) > 16 * 30000 * 8001 // 4
     assert L.ssak_align_workspace_bytes(1, 10, 100000) == 0
 

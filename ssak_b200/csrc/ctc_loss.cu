@@ -406,7 +406,7 @@ ctc_lattice_kernel(const CtcParams p) {
         if (GRAD) {
             off_mine = *reinterpret_cast<const double *>(fin + 2 * P_pad + 2);
             if (Kf > 0) {
-                const int nsl = L / (32 * Kf) + 1;
+                const int nsl = L / (32 * (Kf > 0 ? Kf : 1)) + 1;
                 Dmax = tab[0];
                 for (int w = 1; w < nsl; ++w) Dmax = fmaxf(Dmax, tab[w]);
                 off_mine += (double)Dmax;
@@ -418,8 +418,9 @@ ctc_lattice_kernel(const CtcParams p) {
             if (GRAD) {
                 const int li = dir ? pp - 1 : pp;
                 const int cb_ = dir ? L - pp : pp, cl_ = dir ? L - li - 1 : li;   // chain elements of my two states
-                const float tb_ = Kf > 0 && pp <= L ? tab[cb_ / (32 * Kf)] - Dmax : 0.f;
-                const float tl_ = Kf > 0 && li >= 0 && li < L ? tab[cl_ / (32 * Kf)] - Dmax : 0.f;
+                const int span_f = 32 * (Kf > 0 ? Kf : 1);
+                const float tb_ = Kf > 0 && pp <= L ? tab[cb_ / span_f] - Dmax : 0.f;
+                const float tl_ = Kf > 0 && li >= 0 && li < L ? tab[cl_ / span_f] - Dmax : 0.f;
                 ab[k] = pp <= L ? fin[pp] + tb_ : kNeg;                                        // pairs beyond L
                 al[k] = lab_off[k] == c.slot_bytes - 16 ? kNeg : fin[lab_pos + k * 32] + tl_;  // states beyond 2L+1
             } else {
@@ -807,7 +808,6 @@ ctc_lattice_kernel(const CtcParams p) {
         // 128-bit path when every emission row and every gradient row is 16-byte aligned
         const bool vec = a15_0 == 0 && a15_step == 0 && (V & 3) == 0 && ((p.gst | p.gsb) & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0;
-        const int ncols = vec ? V >> 2 : V;  // work items: groups of 4 columns, or columns
         // scalar path: bit j of `present` = my j-th column (lane + 32 j) carries posterior mass
         unsigned present = 0;
         if (!vec) {
@@ -818,7 +818,9 @@ ctc_lattice_kernel(const CtcParams p) {
         auto label_mass = [&](int cc, const float *w, int slot) {  // posterior mass of column cc at this frame
             float rsum = 0.f;
             const int q1 = occ_start[cc + 1];
-            for (int q = occ_start[cc]; q < q1; ++q) rsum += w[q];  // contiguous run (label-sorted order)
+            // contiguous run (label-sorted order).  (Four partial sums were tried: runs are 1-3 long for most
+            // labels and the extra instructions made the C2 backward 10 % slower.)
+            for (int q = occ_start[cc]; q < q1; ++q) rsum += w[q];
             if (cc == p.blank) {
                 rsum += (float)blank_acc[slot] * (1.0f / 1073741824.0f);
                 blank_acc[slot] = 0u;

@@ -94,13 +94,15 @@ static inline int align_env_int(const char *name, int dflt) {
 //   W  recursion warps per CTA, K states per lane: 32*K*W*S >= Lmax+1.
 static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
     const int64_t P = Lmax + 1;
+    // up to 16 CTAs per utterance: with B * S <= 148 the whole grid is resident at one CTA per SM, so the launch
+    // needs no cluster (clusters stop at 8 CTAs, and a B200 fits only 15 of those at one CTA per SM)
     int S = (int)(148 / (B < 1 ? 1 : B));
-    S = S < 1 ? 1 : (S > 8 ? 8 : S);
+    S = S < 1 ? 1 : (S > 16 ? 16 : S);
     while (S > 1 && (P + S - 1) / S < 128) --S;
     const int64_t cap = 32 * 8 * 8;  // states one CTA can hold (K = 8, W = 8)
     if ((P + cap - 1) / cap > S) S = (int)((P + cap - 1) / cap);
     S = align_env_int("SSAK_ALIGN_S", S);
-    if (S < 1 || S > 8) return false;  // L <= 16383
+    if (S < 1 || S > 16) return false;
     const int64_t Pc = (P + S - 1) / S;
     int wtarget = (B * S <= 148) ? 8 : ((B * S <= 4 * 148) ? 4 : 2);
     wtarget = align_env_int("SSAK_ALIGN_WARPS", wtarget);
@@ -1078,6 +1080,7 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
         if (e == cudaSuccess && try_plain)                                                     \
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)lc.blockDim.x, smem_bytes); \
         if (e == cudaSuccess && (int64_t)per_sm * sms >= (int64_t)p.cfg.S * B) lc.numAttrs = 0; \
+        if (e == cudaSuccess && lc.numAttrs != 0 && p.cfg.S > 8) return SSAK_ERR_UNSUPPORTED; /* clusters: <= 8 CTAs */ \
         if (e == cudaSuccess) e = cudaLaunchKernelEx(&lc, kern, p);                            \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
     }

@@ -179,7 +179,7 @@ def test_align_long_audio_cluster_sized_labels():
 
 
 @pytest.mark.parametrize("mode", ["barrier", "S1K4", "S2K4", "S4K4", "S8K4", "S3K8", "S1K8", "stages", "cluster", "S2K1",
-                                  "S1K2", "S8K2", "default"])
+                                  "S1K2", "S8K2", "S12K4", "default"])
 def test_align_kernel_shapes_agree(mode, monkeypatch):
     """Every launch shape of the forward kernels gives the same bits: the per-frame-barrier kernel, and the
     wavefront kernel for 1..8 CTAs per utterance (cluster), 1, 2, 4 or 8 states per lane, minimal ring depth."""
@@ -191,7 +191,8 @@ def test_align_kernel_shapes_agree(mode, monkeypatch):
            "stages": {"SSAK_ALIGN_S": "2", "SSAK_ALIGN_K": "4", "SSAK_ALIGN_STAGES": "5"},
            "cluster": {"SSAK_ALIGN_S": "4", "SSAK_ALIGN_K": "4", "SSAK_ALIGN_CLUSTER": "1"},
            "S2K1": {"SSAK_ALIGN_S": "2", "SSAK_ALIGN_K": "1"}, "S1K2": {"SSAK_ALIGN_S": "1", "SSAK_ALIGN_K": "2"},
-           "S8K2": {"SSAK_ALIGN_S": "8", "SSAK_ALIGN_K": "2"}, "default": {}}[mode]
+           "S8K2": {"SSAK_ALIGN_S": "8", "SSAK_ALIGN_K": "2"}, "S12K4": {"SSAK_ALIGN_S": "12", "SSAK_ALIGN_K": "4"},
+           "default": {}}[mode]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for seed, kind in ((61, "planted"), (62, "tie")):

@@ -6,12 +6,12 @@
 
 #include "common.cuh"
 
-constexpr int kMaxSub = 4;  // utterance sub-batches pipelined on separate streams (copy/compute overlap)
+constexpr int kMaxSub = 8;  // utterance sub-batches pipelined on separate streams (copy/compute overlap)
 
 struct ssak_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t sub[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t sub[kMaxSub] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ready = nullptr;
     char *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -111,7 +111,11 @@ extern "C" int ssak_ctc_loss_host(ssak_context_t *ctx, const float *log_probs_ho
     const bool want_grad = grad_host != nullptr;
     // Utterance sub-batches on separate streams: the host->device copy of sub-batch i+1, the kernels of
     // sub-batch i and the device->host copy of sub-batch i-1 overlap (utterances are independent).
-    const int NS = B >= 32 ? kMaxSub : (B >= 8 ? 2 : 1);
+    int NS = B >= 32 ? 4 : (B >= 8 ? 2 : 1);
+    if (const char *e = getenv("SSAK_HOST_SUBBATCHES")) {   // (tuning aid)
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxSub && v <= B) NS = v;
+    }
     int64_t b0s[kMaxSub + 1], lmaxs[kMaxSub];
     size_t wsb[kMaxSub], ws_total = 0;
     for (int i = 0; i <= NS; ++i) b0s[i] = B * i / NS;

@@ -325,3 +325,16 @@ def test_sharded_wrapper_single_rank_equals_ctc_loss(reduction):
     assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
     assert (x.grad - y.grad).abs().max().item() <= 1e-7
     assert (x.grad[:, 2] == 0).all()
+
+
+def test_loss_long_targets_eight_pairs_per_lane():
+    """L + 1 > 1024 pairs: the K = 8 instantiation of the barrier kernels (no posterior warps, no wavefront), and
+    the largest supported target length; loss and gradient against torch's CPU kernel in fp64."""
+    import ssak_b200
+    from ssak_b200.synth import ctc_batch
+    lp, tg, il, tl = ctc_batch(2, 2400, 30, 1030, 1150, 501, Tmin=2350)
+    loss, grad = _ours(lp, tg, il, tl, 0, "none", True)
+    rl, rg = _torch_cpu(lp, tg, il, tl, 0, "none", True)
+    _assert_close(loss, grad, rl, rg, "K8")
+    L = ssak_b200.lib()
+    assert L.ssak_ctc_loss_workspace_bytes(100, 2, 4095, 1) > 0 and L.ssak_ctc_loss_workspace_bytes(100, 2, 4096, 1) == 0

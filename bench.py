@@ -348,6 +348,40 @@ def extra_numbers(lib, dev, flush):
             del lp_d
         except Exception as e:  # keep the headline line even if an extra shape fails
             res[f"loss_{name}"] = {"error": repr(e)}
+    # C4 (BASELINE config 4): B=256 utterances with T_b ~ U[300,1500], L_b = 0.27 T_b, V=50 -- one launch over the
+    # whole ragged batch against 4 length buckets (ssak_b200.shard.length_buckets; the batches a bucketed sampler
+    # would hand over), fwd+bwd kernels, one GPU's share of the 2/4/8-GPU configuration
+    try:
+        from ssak_b200.shard import lattice_cost, length_buckets
+        from ssak_b200.synth import planted_emissions
+        g = torch.Generator().manual_seed(1234 + 4)
+        B4, T4, V4 = 256, 1500, 50
+        il = torch.randint(300, T4 + 1, (B4,), generator=g)
+        tl = (0.27 * il.float()).round().long().clamp_min(1)
+        tg = torch.randint(1, V4, (B4, int(tl.max())), generator=g)
+        lp = torch.empty(T4, B4, V4)
+        for b in range(B4):
+            e = torch.randn(T4, V4, generator=g)
+            e[: int(il[b])] = planted_emissions(int(il[b]), V4, tg[b, : int(tl[b])], g, 0, normalize=False)
+            lp[:, b] = e.log_softmax(-1)
+        cells = int((il * (2 * tl + 1)).sum())
+
+        def timed(idx):
+            idx = torch.as_tensor(idx)
+            Tm = int(il[idx].max())
+            sub = lp[:Tm, idx].contiguous().to(dev)
+            off = torch.arange(len(idx), device=dev, dtype=torch.int64) * tg.shape[1]
+            tf, tb = time_kernels(lib, dev, sub, tg[idx].to(torch.int32).to(dev), off, il[idx].to(torch.int32).to(dev),
+                                  tl[idx].to(torch.int32).to(dev), int(tl[idx].max()), 5, flush)
+            return tf + tb
+
+        t_all = timed(list(range(B4)))
+        t_bkt = sum(timed(bk) for bk in length_buckets(lattice_cost(il.tolist(), tl.tolist()), 4))
+        res["loss_c4"] = {"cells_per_s_one_launch": cells / t_all, "ms_one_launch": t_all * 1e3,
+                          "cells_per_s_4_length_buckets": cells / t_bkt, "ms_4_length_buckets": t_bkt * 1e3}
+        del lp
+    except Exception as e:
+        res["loss_c4"] = {"error": repr(e)}
     # on-box GPU comparator: torch's own CUDA ctc_loss (native kernel, cuDNN off as HF does) on the
     # same C2 / 1k / C5 tensors, forward + backward through autograd, same event timing and L2 flush
     import torch.nn.functional as F

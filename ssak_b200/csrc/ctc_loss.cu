@@ -35,11 +35,17 @@
 //     warp) and the subtracted amount is accumulated in fp64, so the fp32 state values stay
 //     O(10..100) instead of O(T): the rounding noise of the recursion drops by ~100x
 //     compared with a plain fp32 log-domain recursion (what ATen does).
-//   * Backward: dedicated gradient warps run one frame behind the recursion warps.  The
-//     recursion warps publish per-state posteriors (shared memory), blank posteriors are
-//     summed with an integer warp reduction in 2^-30 fixed point (deterministic), label
-//     posteriors are summed by the gradient warps through a per-utterance CSR
-//     (label -> positions) built once, and full gradient rows are written coalesced.
+//   * Backward: dedicated gradient warps run behind the recursion warps.  Per-state posteriors are published in
+//     shared memory, blank posteriors are summed with an integer warp reduction in 2^-30 fixed point
+//     (deterministic), label posteriors are summed by the gradient warps through a per-utterance label-sorted
+//     order built once, and full gradient rows are written coalesced.  In the latency regime (few CTAs) the
+//     posteriors are computed by POSTERIOR WARPS, one per recursion warp and one chunk behind it: the recursion
+//     warp hands over its states before the emission is added (a 2-chunk state ring), so the serial chain carries
+//     nothing but the recursion (a lone warp issues ~0.3 instructions per cycle whatever its ILP).
+//   * Forward in the latency regime: ctc_forward_wave_kernel -- no per-frame barrier, warps skewed in time,
+//     per-warp integer re-centring with side tables of offsets (see "offset tables" below).
+//   * Logits entry points: ctc_row_lse_kernel + the LOGITS flag of the lattice kernels (log_softmax never
+//     materialised).  Sharded (multi-GPU) reduction: ctc_shard_*_kernel around the caller's one all-reduce.
 #include <type_traits>
 
 #include "common.cuh"

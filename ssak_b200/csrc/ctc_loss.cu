@@ -1464,12 +1464,12 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
 
 // The wavefront forward kernel when the shape fits it (SSAK_ERR_UNSUPPORTED -> the barrier kernel is used).
 static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
-    // Used on few CTAs (at most one per SM: latency-bound, the wavefront is ~25 % faster); with several CTAs per SM
+    // Used on at most one CTA per SM (2B <= 148: latency-bound, the wavefront is ~25 % faster); with several CTAs per SM
     // the barrier kernel's fatter lanes issue fewer instructions per cell (1.25 vs 1.54 ms at B = 1024).  Rows
     // saved for the backward come with per-warp offset tables, which only the posterior warps (cfg.PW > 0) read.
     // SSAK_CTC_FWD_WAVE=1 forces it where it is valid, =0 disables it.
     const int mode = env_int("SSAK_CTC_FWD_WAVE", -1);
-    if (mode == 0 || (mode < 0 && 2 * p.B > 2 * 148)) return SSAK_ERR_UNSUPPORTED;
+    if (mode == 0 || (mode < 0 && 2 * p.B > 148)) return SSAK_ERR_UNSUPPORTED;   // B = 128: 0.243 vs 0.232 ms
     if (p.rows != nullptr && p.cfg.PW == 0) return SSAK_ERR_UNSUPPORTED;
     const int64_t P = (int64_t)p.Lmax + 1;
     if (P > 1024 || p.T > 100000) return SSAK_ERR_UNSUPPORTED;   // 32 * 4 * 8 chain elements; float-exact offsets

@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, ssak_b200, bench
 lib = ssak_b200.lib(); dev = torch.device("cuda", 0)
 flush = torch.zeros(96 * 1024 * 1024, dtype=torch.float32, device=dev)
+bench.WORKLOADS["b128"] = (128, 1500, 50, 200, 400, 1200)   # between the regimes: 256 CTAs
+bench.WORKLOADS["b160"] = (160, 1500, 50, 200, 400, 1200)
 for name in sys.argv[1:] or ["c2", "1k", "c5"]:
     B, T, V, Lmin, Lmax, Tmin = bench.WORKLOADS[name]
     lp, tg, il, tl, cells = bench.make_batch(name, 99)

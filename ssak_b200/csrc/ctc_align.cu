@@ -538,8 +538,13 @@ __global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p)
             const float val = (tt + 1 >= Tb + 1 - L) ? INF : mine + 0.0f;  // (+0.0f: a -0.0 becomes +0.0)
             for (int j = 0; j < 32 / CH && t0 + j * CH < Tb; ++j) {
                 float *dst = c0ring + slot * CH;
-                if (lane == 0)
-                    while (__float_as_uint(ld_seam_shared(dst)) != kSeamEmpty) __nanosleep(100);
+                if (lane == 0) {
+                    unsigned spins = 0;
+                    while (__float_as_uint(ld_seam_shared(dst)) != kSeamEmpty) {
+                        __nanosleep(100);
+                        if (++spins > (1u << 26)) __trap();   // the consumer never recycled the slot
+                    }
+                }
                 __syncwarp();
                 if (lane / CH == j && tt < Tb) dst[lane % CH] = val;
                 if (++slot == NSLOT) slot = 0;
@@ -737,9 +742,12 @@ __global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p)
         // incoming values of this chunk: read early during the previous chunk, poll only if that was too soon
         float sv = sv_pre;
         {
-            while (__any_sync(FULL, lane < n && __float_as_uint(sv) == kSeamEmpty))
+            unsigned spins = 0;
+            while (__any_sync(FULL, lane < n && __float_as_uint(sv) == kSeamEmpty)) {
                 sv = up_smem ? ld_seam_shared(sv_in + sslot * CH + (lane & (CH - 1)))
                              : ld_seam_global(gs_in + min(t + (lane & (CH - 1)), Tb - 1));
+                if (++spins > (1u << 27)) __trap();   // ~10 s without the upstream seam: fail loudly, never hang
+            }
             if (up_smem && inlane) const_cast<float *>(sv_in)[sslot * CH + lane] = EMPTY;  // recycle the slot
         }
         const int sslot_next = sslot + 1 == NSLOT ? 0 : sslot + 1;

@@ -1161,8 +1161,11 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         // lanes [0, n) the values, lane CH the sender's offset, lane CH+1 the row offset
         float sv = sv_pre;
         if (!first) {
-            while (__any_sync(FULL, (lane < n || (lane >= CH && lane < SW)) && __float_as_uint(sv) == kSeamEmptyBits))
+            unsigned spins = 0;
+            while (__any_sync(FULL, (lane < n || (lane >= CH && lane < SW)) && __float_as_uint(sv) == kSeamEmptyBits)) {
                 sv = ld_volatile_shared_f32(sv_in + sslot * SW + (lane < SW ? lane : 0));
+                if (++spins > (1u << 27)) __trap();   // ~10 s without the upstream seam: fail loudly, never hang
+            }
             if (inlane) const_cast<float *>(sv_in)[sslot * SW + lane] = EMPTY;  // recycle the slot
             const int off_up = (int)__shfl_sync(FULL, sv, CH);
             off_row = (int)__shfl_sync(FULL, sv, CH + 1);

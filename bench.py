@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- lattice-cells/s of the CTC loss forward+backward hot path on B200.
+"""bench.py -- lattice-cells/s of the CTC lattice hot path (loss fwd+bwd, forced alignment, greedy) on B200.
 
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path, rank 0)
 
-Workload (BASELINE.json configs[1], "C2"): synthetic CTC loss fwd+bwd, B=64 utterances per GPU,
-T=1500 frames, V=50, L in [200,400], T_b in [1200,1500], fp32, planted-alignment emissions
-(SURVEY.md section 8d).  A step = one forward + one backward of the loss over the batch.
-cells = sum_b T_b*(2L_b+1), counted once per fwd+bwd.  Prints ONE JSON line (rank 0).
+Headline workload (the configuration BASELINE.json's north star quotes its target on): the "1k-utterance batch" --
+synthetic CTC loss forward + backward, B=1024 utterances per GPU, T=1500 frames, V=50, L in [200,400],
+T_b in [1200,1500], fp32, planted-alignment emissions.  A step = one forward + one
+backward of the loss over the batch; cells = sum_b T_b*(2L_b+1), counted once per fwd+bwd.  Rank 0 prints ONE JSON
+line.  At N=1 the line also carries, under "extra", every other configuration of BASELINE.json measured in the same
+process (C2 loss, C4, C5 loss / logits path, forced alignment C2-shape / C5 / C3 with an end-to-end leg through
+ssak_forced_align_host, greedy, and torch's own CUDA ctc_loss as the on-box GPU comparator), each with its own
+roofline block.  --workload c2|c4|c5 selects another headline; --scaling strong splits ONE global batch of the
+workload over the ranks (LPT partition on the lattice cost + length buckets) instead of one batch per rank.
 """
 from __future__ import annotations
 
@@ -29,18 +34,47 @@ WORKLOADS = {
     # name: (B, T, V, Lmin, Lmax, Tmin)
     "c2": (64, 1500, 50, 200, 400, 1200),
     "1k": (1024, 1500, 50, 200, 400, 1200),
+    "c4": (256, 1500, 50, 81, 405, 300),      # ragged: T_b ~ U[300,1500], L_b = 0.27 T_b
     "c5": (512, 750, 1024, 100, 200, 600),
 }
 METRIC = "ctc_lattice_cells_per_sec"
 UNIT = "cells/s"
 
 
+def c4_batch(seed=1234 + 4):
+    """BASELINE config C4: 256 utterances, T_b ~ U[300,1500], L_b = 0.27 T_b (13 characters per second), V = 50."""
+    from ssak_b200.synth import planted_emissions
+    g = torch.Generator().manual_seed(seed)
+    B, T, V = 256, 1500, 50
+    il = torch.randint(300, T + 1, (B,), generator=g)
+    tl = (0.27 * il.float()).round().long().clamp_min(1)
+    tg = torch.randint(1, V, (B, int(tl.max())), generator=g)
+    lp = torch.empty(T, B, V)
+    for b in range(B):
+        e = torch.randn(T, V, generator=g)
+        e[: int(il[b])] = planted_emissions(int(il[b]), V, tg[b, : int(tl[b])], g, 0, normalize=False)
+        lp[:, b] = e.log_softmax(-1)
+    return lp, tg, il, tl
+
+
 def make_batch(name, seed):
     from ssak_b200.synth import ctc_batch
-    B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
-    lp, tg, il, tl = ctc_batch(B, T, V, Lmin, Lmax, seed, Tmin=Tmin, planted=True)
+    if name == "c4":
+        lp, tg, il, tl = c4_batch(seed)
+    else:
+        B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
+        lp, tg, il, tl = ctc_batch(B, T, V, Lmin, Lmax, seed, Tmin=Tmin, planted=True)
     cells = int((il * (2 * tl + 1)).sum())
     return lp, tg, il, tl, cells
+
+
+def describe(name):
+    B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
+    if name == "c4":
+        return f"c4: CTC loss fwd+bwd, B={B} ragged (T_b ~ U[300,{T}], L_b = 0.27 T_b), V={V}"
+    tag = "1k-utterance batch" if name == "1k" else name
+    return (f"{tag}: CTC loss fwd+bwd, B={B}, T={T}, V={V}, L in [{Lmin},{Lmax}], T_b in [{Tmin},{T}], "
+            f"planted-alignment emissions, reduction=mean, zero_infinity")
 
 
 class ClockSampler:
@@ -96,6 +130,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_of(key):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        return json.load(open(tp)).get(key)
+    return None
+
+
 def cpu_reference_time(lp, tg, il, tl, repeats=3):
     """The reference's CPU path for the loss: torch CPU F.ctc_loss fwd + bwd, all host threads."""
     import torch.nn.functional as F
@@ -108,31 +149,41 @@ def cpu_reference_time(lp, tg, il, tl, repeats=3):
     return best
 
 
+def cpu_sample(name, lp, tg, il, tl):
+    """A bounded sample of the workload for the CPU legs (the full 1k batch takes ~3 s per step on 16 threads)."""
+    n = {"1k": 128, "c5": 64, "c4": 128, "c2": 64}[name]
+    n = min(n, lp.shape[1])
+    cells = int((il[:n] * (2 * tl[:n] + 1)).sum())
+    return lp[:, :n].contiguous(), tg[:n], il[:n], tl[:n], cells, n
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    lp, tg, il, tl, cells = make_batch(args.workload, 1234 + 2)
+    name = args.workload
+    lp, tg, il, tl, _ = make_batch(name, 1234 + 2)
+    lp, tg, il, tl, cells, n = cpu_sample(name, lp, tg, il, tl)
     for _ in range(max(args.warmup, 1)):
         cpu_reference_time(lp, tg, il, tl, 1)
     times = [cpu_reference_time(lp, tg, il, tl, 1) for _ in range(args.steps)]
     t = sum(times) / len(times)
-    B, T, V, _, Lmax, _ = WORKLOADS[args.workload]
     val = cells / t
-    sample = f"full {args.workload} batch (B={B}) per step, torch {torch.__version__} CPU F.ctc_loss fwd+bwd"
+    sample = (f"the first {n} utterances of the {name} batch per step, torch {torch.__version__} CPU F.ctc_loss fwd+bwd "
+              f"(the arithmetic the reference reaches), {ncores} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: CTC loss fwd+bwd B={B} T={T} V={V} L<={Lmax} (rank-0 host only)"},
+        "config": {"workload": describe(name), "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def time_kernels(lib, dev, lp_d, tg32, off, il32, tl32, Lmax, iters, flush):
-    """CUDA-event time of the forward launch pair and of the backward launch, separately."""
+def time_kernels(lib, dev, lp_d, tg32, off, il32, tl32, Lmax, iters, flush, logits=False):
+    """CUDA-event time of the forward launch group and of the backward launch group, separately."""
     T, B, V = lp_d.shape
     ws_bytes = lib.ssak_ctc_loss_workspace_bytes(T, B, Lmax, 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -140,55 +191,130 @@ def time_kernels(lib, dev, lp_d, tg32, off, il32, tl32, Lmax, iters, flush):
     go = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
     grad = torch.empty_like(lp_d)
     s = torch.cuda.current_stream().cuda_stream
+    fwd = lib.ssak_ctc_logits_forward if logits else lib.ssak_ctc_loss_forward
+    bwd = lib.ssak_ctc_logits_backward if logits else lib.ssak_ctc_loss_backward
     tf, tb = [], []
     for i in range(iters + 2):
         flush.add_(1)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        rc = lib.ssak_ctc_loss_forward(lp_d.data_ptr(), T, B, V, lp_d.stride(0), lp_d.stride(1), tg32.data_ptr(),
-                                       off.data_ptr(), il32.data_ptr(), tl32.data_ptr(), Lmax, 0, 1, nll.data_ptr(),
-                                       ws.data_ptr(), ws_bytes, s)
-        assert rc == 0
+        rc = fwd(lp_d.data_ptr(), T, B, V, lp_d.stride(0), lp_d.stride(1), tg32.data_ptr(), off.data_ptr(),
+                 il32.data_ptr(), tl32.data_ptr(), Lmax, 0, 1, nll.data_ptr(), ws.data_ptr(), ws_bytes, s)
+        assert rc == 0, rc
         e1.record()
-        rc = lib.ssak_ctc_loss_backward(go.data_ptr(), lp_d.data_ptr(), T, B, V, lp_d.stride(0), lp_d.stride(1),
-                                        tg32.data_ptr(), off.data_ptr(), il32.data_ptr(), tl32.data_ptr(), Lmax, 0, 1,
-                                        nll.data_ptr(), grad.data_ptr(), grad.stride(0), grad.stride(1),
-                                        ws.data_ptr(), ws_bytes, s)
-        assert rc == 0
+        rc = bwd(go.data_ptr(), lp_d.data_ptr(), T, B, V, lp_d.stride(0), lp_d.stride(1), tg32.data_ptr(),
+                 off.data_ptr(), il32.data_ptr(), tl32.data_ptr(), Lmax, 0, 1, nll.data_ptr(), grad.data_ptr(),
+                 grad.stride(0), grad.stride(1), ws.data_ptr(), ws_bytes, s)
+        assert rc == 0, rc
         e2.record()
         torch.cuda.synchronize()
         if i >= 2:
             tf.append(e0.elapsed_time(e1))
             tb.append(e1.elapsed_time(e2))
-    return statistics.mean(tf) * 1e-3, statistics.mean(tb) * 1e-3
+    return statistics.mean(tf) * 1e-3, statistics.mean(tb) * 1e-3, ws_bytes
+
+
+def loss_roofline(name, V, sumT, t_fwd, t_bwd, hbm, hbm_src, ws_bytes=None):
+    """Roofline block of the loss: the dominant launch is the backward (recursion + gradient): it reads every
+    emission row once and writes the gradient row (8 B per (t,b,v)); the forward reads the rows once (4 B)."""
+    sumTV = float(sumT) * V
+    bwd_bytes = 8.0 * sumTV
+    achieved = bwd_bytes / t_bwd / 1e9
+    return {"bound": "hbm", "kernel": "loss backward launch (recursion + posteriors + gradient rows)",
+            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            "traffic": traffic_of(name), "peak_source": hbm_src,
+            "algorithmic_bytes_per_launch": bwd_bytes, "launch_ms": t_bwd * 1e3,
+            "forward_launch_ms": t_fwd * 1e3, "forward_algorithmic_bytes": 4.0 * sumTV,
+            "forward_achieved_gbs": 4.0 * sumTV / t_fwd / 1e9, "forward_frac": 4.0 * sumTV / t_fwd / 1e9 / hbm,
+            "step_frac_12B": 12.0 * sumTV / (t_fwd + t_bwd) / 1e9 / hbm,
+            "workspace_bytes": ws_bytes,
+            "note": "per cell the compulsory traffic is 0.75 B at V=50 and 30.6 B at V=1024: the V=50 shapes are "
+                    "bound by the recursion's instruction issue (secondary bound, DESIGN.md), V=1024 by HBM"}
+
+
+def _set_affinity(local_rank, world):
+    """Give every rank its own slice of the host cores (the e2e leg is host-memory / PCIe work: 8 ranks on the same
+    cores of NUMA node 0 cost 2.5x at N=8 in round 1).  The slice follows the GPU's NUMA node when sysfs tells."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        node_cores = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus.lower()[-12:]}/local_cpulist"
+            if os.path.exists(path):
+                node_cores = []
+                for part in open(path).read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    node_cores += list(range(int(a), int(b or a) + 1))
+                node_cores = [c for c in node_cores if c in cores]
+        except Exception:
+            node_cores = None
+        pool = node_cores or cores
+        per = max(1, len(pool) // max(world, 1))
+        mine = pool[(local_rank * per) % len(pool):][:per] or pool
+        os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "first": mine[0], "numa_local": bool(node_cores)}
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import ssak_b200
+    from ssak_b200.shard import lattice_cost, length_buckets, lpt_partition, sharded_ctc_loss
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    aff = _set_affinity(local_rank, world) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = ssak_b200.lib()
     name = args.workload
     B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
-    lp, tg, il, tl, cells = make_batch(name, 1234 + 2 + 1000 * rank)   # weak scaling: own batch per rank
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE global batch, split by the longest-processing-time-first partition on the lattice cost; every rank
+        # generates the same batch (same seed) and keeps its share
+        lp, tg, il, tl, _ = make_batch(name, 1234 + 2)
+        parts = lpt_partition(lattice_cost(il.tolist(), tl.tolist()), world)
+        mine = parts[rank]
+        lp, tg, il, tl = lp[:, mine].contiguous(), tg[mine], il[mine], tl[mine]
+        cells = int((il * (2 * tl + 1)).sum())
+        global_batch = B
+    else:
+        lp, tg, il, tl, cells = make_batch(name, 1234 + 2 + 1000 * rank)   # weak scaling: own batch per rank
+        global_batch = B * world
+    Bl = lp.shape[1]
+    # length buckets (similar lengths launch together): only worth it for ragged batches with enough utterances
+    nb = 2 if (name == "c4" and Bl >= 64) else 1
+    buckets = [sorted(bk) for bk in length_buckets(lattice_cost(il.tolist(), tl.tolist()), nb)] if nb > 1 else [list(range(Bl))]
     lp_pin, grad_pin = lp.pin_memory(), torch.empty_like(lp).pin_memory()
     lp_d = lp_pin.to(dev, non_blocking=True)
-    tg_d, il_d, tl_d = tg.to(dev, torch.int32), il.to(dev, torch.int32), tl.to(dev, torch.int32)
+    dev_b = []
+    for bk in buckets:
+        idx = torch.as_tensor(bk)
+        Tm = int(il[idx].max())
+        x = lp_d[:Tm, idx.to(dev)].contiguous() if nb > 1 else lp_d
+        dev_b.append((x, tg[idx].to(dev, torch.int32), il[idx].to(dev, torch.int32), tl[idx].to(dev, torch.int32)))
     flush = torch.zeros(96 * 1024 * 1024, dtype=torch.float32, device=dev)      # 384 MB > 126 MB L2
 
     def step():
-        x = lp_d.detach().requires_grad_(True)
-        if world > 1:   # utterance-sharded batch: local lattices + ONE all-reduce of 2 scalars (NCCL)
-            from ssak_b200.shard import sharded_ctc_loss
-            loss = sharded_ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True,
-                                    global_batch=B * world)
-        else:
-            loss = ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True)
-        loss.backward()
-        return loss, x.grad
+        grads, loss = [], None
+        for x0, tg_d, il_d, tl_d in dev_b:
+            x = x0.detach().requires_grad_(True)
+            if world > 1 or nb > 1:   # utterance-sharded: local lattices + ONE all-reduce of 2 scalars per call (NCCL),
+                                      # off the critical path (side stream, joined at the end of backward)
+                l = sharded_ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True,
+                                     global_batch=global_batch)
+            else:
+                l = ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, blank=0, reduction="mean", zero_infinity=True)
+            l.backward()
+            grads.append(x.grad)
+            loss = l if loss is None else loss + l
+        return loss, grads
 
     def barrier():
         if world > 1:
@@ -214,41 +340,43 @@ def run_ours(args, rank, world, local_rank):
         evs.append((a, b))
     barrier()
     t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
-    # the timed region lasts a few ms, shorter than nvidia-smi's sampling period: keep the same work running
-    # for ~0.3 s more so that the clock / throttle samples are taken under this load
-    # (every rank runs the same fixed number of steps: the sharded step contains a collective)
-    for _ in range(30):
-        for _ in range(20):
-            step()
-        torch.cuda.synchronize()
+    # the timed region can be shorter than nvidia-smi's sampling period: keep the same work running for ~0.3 s more
+    # so that the clock / throttle samples are taken under this load (every rank runs the same fixed number of
+    # steps: the sharded step contains a collective)
+    n_soak = max(2, min(600, int(0.3 / max(t_dev / args.steps, 1e-4))))
+    for _ in range(n_soak):
+        step()
+    torch.cuda.synchronize()
     # ---- end to end through the host-buffer C ABI: pinned host log-probs in, nll + gradient out
     ctx = C.c_void_p()
     assert lib.ssak_context_create(local_rank, C.byref(ctx)) == 0
     tg32 = tg.to(torch.int32).contiguous()
     il32, tl32 = il.to(torch.int32), tl.to(torch.int32)
-    nll_h = torch.empty(B, dtype=torch.float32).pin_memory()
+    nll_h = torch.empty(Bl, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        rc = lib.ssak_ctc_loss_host(ctx, lp_pin.data_ptr(), T, B, V, tg32.data_ptr(), tg32.shape[1],
+        rc = lib.ssak_ctc_loss_host(ctx, lp_pin.data_ptr(), lp.shape[0], Bl, V, tg32.data_ptr(), tg32.shape[1],
                                     il32.data_ptr(), tl32.data_ptr(), 0, 1, None, nll_h.data_ptr(),
                                     grad_pin.data_ptr())
         assert rc == 0, rc
 
-    for _ in range(3):
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(2):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         e2e_step()
     barrier()
-    t_e2e = time.perf_counter() - t0
+    t_e2e = (time.perf_counter() - t0) / n_e2e * args.steps     # scaled to K steps (same aggregate below)
     if rank == 0:
         sampler.stop()
     # parity gate on the timed configuration: the host-ABI result equals the torch-facing one
-    _, g = step()
-    torch.cuda.synchronize()
-    gscale = (1.0 / (B * world * tl.clamp_min(1).float())).view(1, B, 1)
-    assert (g.cpu() - grad_pin * gscale).abs().max().item() < 1e-6
+    if nb == 1:
+        _, g = step()
+        torch.cuda.synchronize()
+        gscale = (1.0 / (global_batch * tl.clamp_min(1).float())).view(1, Bl, 1)
+        assert (g[0].cpu() - grad_pin * gscale).abs().max().item() < 1e-6
 
     times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     tot_cells = torch.tensor([float(cells)], dtype=torch.float64, device=dev)
@@ -261,54 +389,59 @@ def run_ours(args, rank, world, local_rank):
     out = None
     if rank == 0:
         hbm, hbm_src = peaks()
-        off = (torch.arange(B, device=dev, dtype=torch.int64) * tg.shape[1])
-        t_fwd, t_bwd = time_kernels(lib, dev, lp_d, tg32.to(dev), off, il32.to(dev), tl32.to(dev), int(tl.max()),
-                                    max(args.steps, 5), flush)
-        sumTV = float(il.sum()) * V
-        bwd_bytes = 8.0 * sumTV            # read every emission row once + write the gradient row
-        achieved = bwd_bytes / t_bwd / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(name)
-        cpu_s = cpu_reference_time(lp, tg, il, tl, 3)
-        ncores = os.cpu_count() or 1
-        h2d = lp.numel() * 4 + tg32.numel() * 4 + 2 * B * 4 + B * 8 + B * 4
-        d2h = lp.numel() * 4 + B * 4
+        off = (torch.arange(Bl, device=dev, dtype=torch.int64) * tg.shape[1])
+        t_fwd, t_bwd, ws_bytes = time_kernels(lib, dev, lp_d, tg32.to(dev), off, il32.to(dev), tl32.to(dev),
+                                              int(tl.max()), max(min(args.steps, 10), 5), flush)
+        h2d = lp.numel() * 4 + tg32.numel() * 4 + 2 * Bl * 4 + Bl * 8 + Bl * 4
+        d2h = lp.numel() * 4 + Bl * 4
         out = {
             "metric": METRIC, "value": total * args.steps / t_dev, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name}: CTC loss fwd+bwd, B={B} per GPU, T={T}, V={V}, L in [{Lmin},{Lmax}], "
-                                   f"T_b in [{Tmin},{T}], planted-alignment emissions, reduction=mean, zero_infinity",
-                       "cells_per_step_per_gpu": cells, "l2": "flushed (384 MB write) before every timed step",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": describe(name) + (f"; ONE global batch of {B} split over {world} GPUs (LPT on "
+                                                     f"T_b(2L_b+1)), {nb} length bucket(s) per rank" if strong
+                                                     else f"; B={B} per GPU"),
+                       "cells_per_step_rank0": cells, "utterances_rank0": Bl,
+                       "l2": "flushed (384 MB write) before every timed step",
                        "inputs": "log_probs fp32 [T,B,V] contiguous, int32 padded targets / lengths, resident in HBM",
-                       "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
+                       "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
+                       "collective": None if world == 1 else "one ncclAllReduce of 2 doubles per loss call, on a "
+                                                             "side stream, joined at the end of backward",
+                       "host_affinity": aff},
             "e2e": {"value": total * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3, "steps_timed": n_e2e,
                     "path": "ssak_ctc_loss_host (C ABI): pinned host log-probs in, nll + full gradient out"},
-            "gpu_launches": 4 * args.steps,   # lattice fwd, join, reduce, lattice bwd
-            "roofline": {"bound": "hbm", "kernel": "ctc_lattice_kernel<K,true> (backward: recursion + gradient)",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": hbm_src,
-                         "algorithmic_bytes_per_launch": bwd_bytes, "launch_ms": t_bwd * 1e3,
-                         "forward_launch_ms": t_fwd * 1e3,
-                         "forward_achieved_gbs": 4.0 * sumTV / t_fwd / 1e9,
-                         "note": "V=50: 0.75 B/cell of compulsory traffic, the kernel is bound by the serial "
-                                 "recursion and MUFU (DESIGN.md), not by HBM"},
-            "cpu_baseline": {"value": cells / cpu_s, "unit": UNIT, "cores": ncores, "kind": "reference",
-                             "sample": f"full {name} batch (B={B}) fwd+bwd, best of 3, torch {torch.__version__} "
-                                       f"CPU F.ctc_loss with {ncores} threads"},
+            "gpu_launches": None,
+            "roofline": loss_roofline(name, V, int(il.sum()), t_fwd, t_bwd, hbm, hbm_src, ws_bytes),
             "clocks": sampler.summary(),
         }
-        if args.extra:
-            out["extra"] = extra_numbers(lib, dev, flush)
+        out["gpu_launches"] = launches_per_step(lib) * len(dev_b) * args.steps
+        if world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            slp, stg, sil, stl, scells, sn = cpu_sample(name, lp, tg, il, tl)
+            cpu_s = cpu_reference_time(slp, stg, sil, stl, 3)
+            out["cpu_baseline"] = {"value": scells / cpu_s, "unit": UNIT, "cores": torch.get_num_threads(),
+                                   "kind": "reference",
+                                   "sample": f"the first {sn} utterances of the batch, fwd+bwd, best of 3, torch "
+                                             f"{torch.__version__} CPU F.ctc_loss with {torch.get_num_threads()} threads"}
+            if not args.no_extra:
+                del lp_d, dev_b
+                torch.cuda.empty_cache()
+                out["extra"] = extra_numbers(lib, dev, flush, skip=name)
     lib.ssak_context_destroy(ctx)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))
+
+
+def launches_per_step(lib):
+    """Kernels of ours per loss call (forward group + backward group), as the library reports them."""
+    try:
+        return int(lib.ssak_ctc_loss_launches_per_step())
+    except AttributeError:
+        return 4     # lattice fwd, join, reduce, lattice bwd
 
 
 def _timed_ms(fn, flush, n=7, warm=3):
@@ -329,67 +462,55 @@ def _timed_ms(fn, flush, n=7, warm=3):
     return statistics.median(ts)
 
 
-def extra_numbers(lib, dev, flush):
-    """Other configurations of BASELINE.json, device-resident, kernels only (informational)."""
+def extra_numbers(lib, dev, flush, skip=None):
+    """The other configurations of BASELINE.json in the same process (rank 0, N = 1): device-resident kernels,
+    each with its roofline block; the aligner also end to end through the host-buffer C ABI."""
+    import torch.nn.functional as F
     import ssak_b200
     from ssak_b200.synth import align_batch
+    hbm, hbm_src = peaks()
     res = {}
-    for name in ("1k", "c5"):
+    batches = {}
+    # ---- loss: C2 / 1k / C5 / C4, kernels only (forward launch group, backward launch)
+    for name in ("c2", "1k", "c5", "c4"):
         try:
             B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
-            lp, tg, il, tl, cells = make_batch(name, 99)
+            lp, tg, il, tl, cells = make_batch(name, 99 if name != "c4" else 1234 + 4)
             lp_d = lp.to(dev)
-            off = torch.arange(B, device=dev, dtype=torch.int64) * tg.shape[1]
-            tf, tb = time_kernels(lib, dev, lp_d, tg.to(torch.int32).to(dev), off, il.to(torch.int32).to(dev),
-                                  tl.to(torch.int32).to(dev), int(tl.max()), 5, flush)
-            sumTV = float(il.sum()) * V
+            off = torch.arange(lp.shape[1], device=dev, dtype=torch.int64) * tg.shape[1]
+            tf, tb, wsb = time_kernels(lib, dev, lp_d, tg.to(torch.int32).to(dev), off, il.to(torch.int32).to(dev),
+                                       tl.to(torch.int32).to(dev), int(tl.max()), 5, flush)
             res[f"loss_{name}"] = {"cells_per_s": cells / (tf + tb), "fwd_ms": tf * 1e3, "bwd_ms": tb * 1e3,
-                                   "hbm_frac_canonical_12B": 12.0 * sumTV / (tf + tb) / 1e9 / peaks()[0]}
-            del lp_d
+                                   "workload": describe(name),
+                                   "roofline": loss_roofline(name, V, int(il.sum()), tf, tb, hbm, hbm_src, wsb)}
+            if name != "c4":
+                batches[name] = (lp_d, tg, il, tl, cells)
+            if name == "c4":
+                # the same batch as 4 length buckets (what a bucketed sampler hands over; ssak_b200.shard)
+                from ssak_b200.shard import lattice_cost, length_buckets
+                t_bkt = 0.0
+                for bk in length_buckets(lattice_cost(il.tolist(), tl.tolist()), 4):
+                    idx = torch.as_tensor(sorted(bk))
+                    Tm = int(il[idx].max())
+                    sub = lp[:Tm, idx].contiguous().to(dev)
+                    o2 = torch.arange(len(idx), device=dev, dtype=torch.int64) * tg.shape[1]
+                    a, b2, _ = time_kernels(lib, dev, sub, tg[idx].to(torch.int32).to(dev), o2,
+                                            il[idx].to(torch.int32).to(dev), tl[idx].to(torch.int32).to(dev),
+                                            int(tl[idx].max()), 5, flush)
+                    t_bkt += a + b2
+                res["loss_c4"]["ms_4_length_buckets"] = t_bkt * 1e3
+                res["loss_c4"]["cells_per_s_4_length_buckets"] = cells / t_bkt
+            del lp
         except Exception as e:  # keep the headline line even if an extra shape fails
             res[f"loss_{name}"] = {"error": repr(e)}
-    # C4 (BASELINE config 4): B=256 utterances with T_b ~ U[300,1500], L_b = 0.27 T_b, V=50 -- one launch over the
-    # whole ragged batch against 4 length buckets (ssak_b200.shard.length_buckets; the batches a bucketed sampler
-    # would hand over), fwd+bwd kernels, one GPU's share of the 2/4/8-GPU configuration
-    try:
-        from ssak_b200.shard import lattice_cost, length_buckets
-        from ssak_b200.synth import planted_emissions
-        g = torch.Generator().manual_seed(1234 + 4)
-        B4, T4, V4 = 256, 1500, 50
-        il = torch.randint(300, T4 + 1, (B4,), generator=g)
-        tl = (0.27 * il.float()).round().long().clamp_min(1)
-        tg = torch.randint(1, V4, (B4, int(tl.max())), generator=g)
-        lp = torch.empty(T4, B4, V4)
-        for b in range(B4):
-            e = torch.randn(T4, V4, generator=g)
-            e[: int(il[b])] = planted_emissions(int(il[b]), V4, tg[b, : int(tl[b])], g, 0, normalize=False)
-            lp[:, b] = e.log_softmax(-1)
-        cells = int((il * (2 * tl + 1)).sum())
-
-        def timed(idx):
-            idx = torch.as_tensor(idx)
-            Tm = int(il[idx].max())
-            sub = lp[:Tm, idx].contiguous().to(dev)
-            off = torch.arange(len(idx), device=dev, dtype=torch.int64) * tg.shape[1]
-            tf, tb = time_kernels(lib, dev, sub, tg[idx].to(torch.int32).to(dev), off, il[idx].to(torch.int32).to(dev),
-                                  tl[idx].to(torch.int32).to(dev), int(tl[idx].max()), 5, flush)
-            return tf + tb
-
-        t_all = timed(list(range(B4)))
-        t_bkt = sum(timed(bk) for bk in length_buckets(lattice_cost(il.tolist(), tl.tolist()), 4))
-        res["loss_c4"] = {"cells_per_s_one_launch": cells / t_all, "ms_one_launch": t_all * 1e3,
-                          "cells_per_s_4_length_buckets": cells / t_bkt, "ms_4_length_buckets": t_bkt * 1e3}
-        del lp
-    except Exception as e:
-        res["loss_c4"] = {"error": repr(e)}
-    # on-box GPU comparator (SURVEY 8d): torch's own CUDA ctc_loss (native kernel, cuDNN off as HF does) on the
-    # same C2 / 1k / C5 tensors, forward + backward through autograd, same event timing and L2 flush
-    import torch.nn.functional as F
+    # ---- on-box GPU comparator (SURVEY 8d): torch's own CUDA ctc_loss (native kernel, cuDNN off as HF does) on the
+    #      same tensors, forward + backward through autograd, same event timing and L2 flush
     for name in ("c2", "1k", "c5"):
+        if name not in batches:
+            continue
         try:
-            B, T, V, Lmin, Lmax, Tmin = WORKLOADS[name]
-            lp, tg, il, tl, cells = make_batch(name, 99)
-            lp_d, tg_d, il_d, tl_d = lp.to(dev), tg.to(dev), il.to(dev), tl.to(dev)
+            lp_d, tg, il, tl, cells = batches[name]
+            tg_d, il_d, tl_d = tg.to(dev), il.to(dev), tl.to(dev)
 
             def torch_step():
                 x = lp_d.detach().requires_grad_(True)
@@ -400,19 +521,17 @@ def extra_numbers(lib, dev, flush):
                 x = lp_d.detach().requires_grad_(True)
                 ssak_b200.ctc_loss(x, tg_d, il_d, tl_d, 0, "mean", True).backward()
 
-            t_torch, t_ours = _timed_ms(torch_step, flush), _timed_ms(our_step, flush)
+            t_torch, t_ours = _timed_ms(torch_step, flush, n=5, warm=2), _timed_ms(our_step, flush, n=5, warm=2)
             res[f"torch_cuda_ctc_{name}"] = {"torch_ms": t_torch, "ours_ms": t_ours, "speedup": t_torch / t_ours,
-                                              "torch_cells_per_s": cells / (t_torch * 1e-3)}
-            del lp_d
+                                              "torch_cells_per_s": cells / (t_torch * 1e-3),
+                                              "ours_cells_per_s": cells / (t_ours * 1e-3)}
         except Exception as e:
             res[f"torch_cuda_ctc_{name}"] = {"error": repr(e)}
-    # f-1: log_softmax + ctc_loss (+ both backwards) against the single logits entry point, C5 shape, torch-facing API
+    # ---- f-1: log_softmax + ctc_loss (+ both backwards) against the single logits entry point, C5 shape
     try:
-        B, T, V, Lmin, Lmax, Tmin = WORKLOADS["c5"]
-        lp, tg, il, tl, cells = make_batch("c5", 99)
-        logits = (lp * 1.5 + 2.0).to(dev)
+        lp_d, tg, il, tl, cells = batches["c5"]
+        logits = lp_d * 1.5 + 2.0
         tg_d, il_d, tl_d = tg.to(dev, torch.int32), il.to(dev, torch.int32), tl.to(dev, torch.int32)
-        del lp
 
         def unfused():
             x = logits.detach().requires_grad_(True)
@@ -424,14 +543,22 @@ def extra_numbers(lib, dev, flush):
 
         tms = {}
         for nm, fn in (("log_softmax_then_ctc_ms", unfused), ("from_logits_ms", fused)):
-            tms[nm] = _timed_ms(fn, flush)
+            tms[nm] = _timed_ms(fn, flush, n=5, warm=2)
         tms["cells_per_s_from_logits"] = cells / (tms["from_logits_ms"] * 1e-3)
+        sumTV = float(il.sum()) * 1024
+        tms["hbm_frac_16B"] = 16.0 * sumTV / (tms["from_logits_ms"] * 1e-3) / 1e9 / hbm
         res["loss_c5_logits"] = tms
         del logits
     except Exception as e:
         res["loss_c5_logits"] = {"error": repr(e)}
+    batches.clear()
+    torch.cuda.empty_cache()
+    # ---- forced alignment (C5, C2-shaped, C3) and greedy
+    ctx = C.c_void_p()
+    assert lib.ssak_context_create(dev.index or 0, C.byref(ctx)) == 0
     for name, (B, T, V, Lmin, Lmax, Tmin) in {"align_c5": (512, 750, 1024, 100, 200, 600),
                                                "align_c2shape": (64, 1500, 50, 200, 400, 1200),
+                                               "align_1k": (1024, 1500, 50, 200, 400, 1200),
                                                "align_c3": (16, 30000, 50, 7600, 8000, 30000)}.items():
         try:
             em, toks, el, tl = align_batch(B, T, V, Lmin, Lmax, 5, Tmin=Tmin)
@@ -441,12 +568,40 @@ def extra_numbers(lib, dev, flush):
             def run_align():
                 keep["r"] = ssak_b200.forced_align(em_d, toks_d, el_d, tl_d)
 
-            t = _timed_ms(run_align, flush) * 1e-3
+            t = _timed_ms(run_align, flush, n=5, warm=2) * 1e-3
             r = keep["r"]
             cells = int((el.long() * (tl.long() + 1)).sum())
-            alg_bytes = 4.0 * float(el.sum()) * V + 4.0 * float((el.long() * (tl.long() + 1)).sum()) / 8 * 2
-            res[name] = {"cells_per_s": cells / t, "ms": t * 1e3, "aligned": int((r.status == 0).sum()),
-                         "hbm_frac_algorithmic": alg_bytes / t / 1e9 / peaks()[0]}
+            alg_bytes = (4.0 * float(el.sum()) * V + 4.0 * float((el.long() * (tl.long() + 1)).sum()) / 8
+                         + 16.0 * float(tl.sum()))
+            ach = alg_bytes / t / 1e9
+            res[name] = {"cells_per_s": cells / t, "ms": t * 1e3, "aligned": int((r.status == 0).sum()), "B": B,
+                         "roofline": {"bound": "hbm", "kernel": "align_wave_kernel + align_backtrace_kernel (one C call)",
+                                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": t * 1e3, "achieved": ach,
+                                      "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic_of(name),
+                                      "peak_source": hbm_src}}
+            # end to end: host emissions in, spans / scores out (ssak_forced_align_host), pinned host buffers
+            em_h = em.pin_memory()
+            tk_h = toks.contiguous()
+            Lm = tk_h.shape[1]
+            st = torch.empty((B, Lm), dtype=torch.int32).pin_memory()
+            en = torch.empty((B, Lm), dtype=torch.int32).pin_memory()
+            sc = torch.empty((B, Lm), dtype=torch.float64).pin_memory()
+            ts, status = torch.empty(B, dtype=torch.int32), torch.empty(B, dtype=torch.int32)
+
+            def host_align():
+                rc = lib.ssak_forced_align_host(ctx, em_h.data_ptr(), B, T, V, tk_h.data_ptr(), Lm, el.data_ptr(),
+                                                tl.data_ptr(), 0, 0, None, st.data_ptr(), en.data_ptr(), sc.data_ptr(),
+                                                ts.data_ptr(), status.data_ptr())
+                assert rc == 0, rc
+
+            host_align()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                host_align()
+            te = (time.perf_counter() - t0) / 3
+            assert torch.equal(st[:, :Lm], r.starts.cpu()) and int((status == 0).sum()) == B
+            res[name]["e2e"] = {"cells_per_s": cells / te, "ms": te * 1e3, "h2d_bytes": em.numel() * 4 + tk_h.numel() * 4 + 8 * B,
+                                "d2h_bytes": B * Lm * 16 + 8 * B, "path": "ssak_forced_align_host (C ABI)"}
             if name == "align_c2shape":   # the CPU port (oracle C, one core) on a bounded sample of the same batch
                 from oracle import oracle as O
                 t0, n_cpu, c_cpu = time.perf_counter(), 0, 0
@@ -458,12 +613,18 @@ def extra_numbers(lib, dev, flush):
                 res[name]["cpu_port"] = {"cells_per_s": c_cpu / (time.perf_counter() - t0), "cores": 1,
                                          "sample": f"{n_cpu} utterances of this batch, oracle/ssak_oracle.c"}
             if name == "align_c5":   # greedy decode of the same emissions: frames/s and fraction of the HBM roofline
-                t = _timed_ms(lambda: ssak_b200.greedy_ids(em_d, el_d, 0), flush) * 1e-3
+                t = _timed_ms(lambda: ssak_b200.greedy_ids(em_d, el_d, 0), flush, n=5, warm=2) * 1e-3
+                gb = 4.0 * B * T * V + 8.0 * B * T
                 res["greedy_c5"] = {"frames_per_s": B * T / t, "ms": t * 1e3,
-                                    "hbm_frac": (4.0 * B * T * V + 8.0 * B * T) / t / 1e9 / peaks()[0]}
-            del em_d
+                                    "roofline": {"bound": "hbm", "kernel": "greedy_argmax_kernel + greedy_collapse_kernel",
+                                                 "algorithmic_bytes_per_launch": gb, "launch_ms": t * 1e3,
+                                                 "achieved": gb / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                                 "frac": gb / t / 1e9 / hbm, "traffic": None}}
+            del em_d, em_h
+            torch.cuda.empty_cache()
         except Exception as e:
             res[name] = {"error": repr(e)}
+    lib.ssak_context_destroy(ctx)
     return res
 
 
@@ -476,8 +637,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--extra", action="store_true", help="also time the other BASELINE configs (rank 0)")
+    ap.add_argument("--workload", default="1k", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one batch of the workload per GPU; strong: ONE global batch split by lpt_partition")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (rank 0, N = 1)")
+    ap.add_argument("--extra", action="store_true", help="(default now; kept for compatibility)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -10,8 +10,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
- *     allocate, never synchronise and keep no global state (re-entrant from several host
- *     threads, e.g. under nn.DataParallel: one thread per GPU);
+ *     allocate, never synchronise and keep no mutable global state (re-entrant from several
+ *     host threads and streams, e.g. under nn.DataParallel: one thread per GPU; kernels whose
+ *     CTAs depend on each other are launched cooperatively or as clusters, so concurrent calls
+ *     on one GPU cannot starve each other);
  *   - the caller owns every buffer, including the workspace whose size the matching
  *     *_workspace_bytes() call returns;
  *   - return value: SSAK_OK (0) or a negative ssak_status_t; ssak_b200_strerror() names it;
@@ -63,7 +65,10 @@ SSAK_API int ssak_b200_last_cuda_error(void);
  * alpha pass + beta pass) but the serial depth of each call is T/2.
  *
  *   log_probs        [T,B,V] fp32, element strides (lp_stride_t, lp_stride_b, 1)
- *   targets          int32, labels of utterance b at targets[target_offsets[b] + i]
+ *   targets          int32, labels of utterance b at targets[target_offsets[b] + i], each in [0,V): a label
+ *                    outside the vocabulary makes the utterance's likelihood (and gradient) NaN -- the
+ *                    asynchronous device entry points cannot return an error for device data; the
+ *                    host-buffer entry points return SSAK_ERR_INVALID_ARGUMENT
  *   target_offsets   int64 [B]    (b*Smax for a padded [B,Smax] tensor, cumsum for 1-D)
  *   input_lengths    int32 [B]    (0 <= . <= T)
  *   target_lengths   int32 [B]    (0 <= . <= max_target_len)
@@ -75,6 +80,11 @@ SSAK_API int ssak_b200_last_cuda_error(void);
 /* Workspace size for forward(+backward).  save_for_backward == 0: join rows only. */
 SSAK_API size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t max_target_len,
                                               int save_for_backward);
+
+/* 1 when the loss kernels cover the shape, else 0 (max_target_len > 4095, T > 300000, or rows of V floats that do
+ * not fit the shared-memory emission ring: V > ~2040).  A caller that replaces a generic operator
+ * (ssak_b200.install() over torch.nn.functional.ctc_loss) uses it to delegate what is not covered. */
+SSAK_API int ssak_ctc_loss_supported(int64_t T, int64_t B, int64_t V, int64_t max_target_len);
 
 /* aten::_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, zero_infinity)
  *   -> neg_log_likelihood[B] (fp32; +inf for an infeasible utterance -- zero_infinity is
@@ -175,7 +185,9 @@ SSAK_API int ssak_ctc_shard_grad_scale(const float *grad_scale, const float *gra
  *   scores           fp64 [B,Lmax] out: Segment.score (mean of the per-frame probabilities)
  *   t_start          int32 [B] out: argmax_t trellis[t, L_b] (:88) = number of frames used
  *   status           int32 [B] out: 0 aligned, 1 = the reference's
- *                    RuntimeError("Failed to align (not enough tokens for the duration?)")
+ *                    RuntimeError("Failed to align (not enough tokens for the duration?)"),
+ *                    2 = the call's watchdog fired (a seam poll saw no progress for 10 s: never expected,
+ *                    the multi-CTA launch is cooperative / clustered), 3 = a token id outside [0,V)
  *   trellis_dump     optional fp32 [B,Tmax+1,Lmax+1] out: the full trellis (tests only)
  *   path_token       optional int32 [B,Tmax] out: Point.token_index of the frame, -1 off the path
  *   path_prob        optional fp32 [B,Tmax] out: Point.score of the frame (:106-112), 0 off the path

@@ -210,4 +210,36 @@ inline int check_launch() {
     return SSAK_OK;
 }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Number of SMs of the current device (cached per device ordinal; 148 on a B200).  The launch-shape heuristics
+// derive the "one CTA per SM" thresholds from it instead of hard-coding the B200's count.
+inline int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    const int slot = dev & 63;
+    int n = cached[slot];
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[slot] = n;   // (a benign race: every thread writes the same value)
+    }
+    return n;
+}
+
+constexpr int kMaxDynSmem = 227 * 1024;
+// Opt a kernel instantiation into the full 227 KB of dynamic shared memory ONCE per device.  The attribute is
+// per-function, per-device state: setting it to the exact size of every launch let two host threads with different
+// shapes interleave "set" and "launch" (one launch then failed with invalid-value).
+template <auto Kern>
+inline cudaError_t ensure_max_smem() {
+    static unsigned long long done = 0;   // bit per device ordinal
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (e == cudaSuccess) __atomic_fetch_or(&done, bit, __ATOMIC_RELEASE);
+    return e;
+}
 }  // namespace ssak

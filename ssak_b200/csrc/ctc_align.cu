@@ -50,6 +50,7 @@ struct AlignParams {
     int32_t *path_token;  // optional [B][Tmax]
     float *path_prob;     // optional [B][Tmax]
     float *gseam;         // wave kernel: [B][S-1][Tmax] seam values handed from CTA c to CTA c+1 (preset to NaN)
+    int *abort_word;      // wave kernel: kNoAbort until a seam poll gave up (watchdog); then every warp drains and exits
     AlignCfg cfg;
 };
 
@@ -57,7 +58,8 @@ static bool choose_barrier_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
     const int64_t P = Lmax + 1;
     c->S = 1;
     c->wave = 0;
-    int wtarget = (B <= 148) ? 8 : ((B <= 4 * 148) ? 4 : 2);
+    const int sms = device_sm_count();
+    int wtarget = (B <= sms) ? 8 : ((B <= 4 * sms) ? 4 : 2);
     const char *s = getenv("SSAK_ALIGN_WARPS");
     if (s && *s) wtarget = atoi(s);
     int K = 0;
@@ -94,9 +96,11 @@ static inline int align_env_int(const char *name, int dflt) {
 //   W  recursion warps per CTA, K states per lane: 32*K*W*S >= Lmax+1.
 static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
     const int64_t P = Lmax + 1;
-    // up to 16 CTAs per utterance: with B * S <= 148 the whole grid is resident at one CTA per SM, so the launch
-    // needs no cluster (clusters stop at 8 CTAs, and a B200 fits only 15 of those at one CTA per SM)
-    int S = (int)(148 / (B < 1 ? 1 : B));
+    // up to 16 CTAs per utterance: with B * S <= #SMs the whole grid is resident at one CTA per SM, so a cooperative
+    // launch guarantees co-residency without a cluster (clusters stop at 8 CTAs, and a B200 fits only 15 of
+    // those at one CTA per SM)
+    const int sms = device_sm_count();
+    int S = (int)(sms / (B < 1 ? 1 : B));
     S = S < 1 ? 1 : (S > 16 ? 16 : S);
     while (S > 1 && (P + S - 1) / S < 128) --S;
     const int64_t cap = 32 * 8 * 8;  // states one CTA can hold (K = 8, W = 8)
@@ -104,7 +108,7 @@ static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
     S = align_env_int("SSAK_ALIGN_S", S);
     if (S < 1 || S > 16) return false;
     const int64_t Pc = (P + S - 1) / S;
-    int wtarget = (B * S <= 148) ? 8 : ((B * S <= 4 * 148) ? 4 : 2);
+    int wtarget = (B * S <= sms) ? 8 : ((B * S <= 4 * sms) ? 4 : 2);
     wtarget = align_env_int("SSAK_ALIGN_WARPS", wtarget);
     int K = align_env_int("SSAK_ALIGN_K", 0);
     if (K == 0) {
@@ -112,7 +116,7 @@ static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
         // warps help -- down to 2 states per lane (measured on the C2-shaped batch: 0.26 ms at K = 2, 0.29 ms at
         // K = 1 (longer warp chain, two more shuffles per frame) and at K = 4); many CTAs: 4 states per lane
         // (fewest instructions per state), 8 beyond 1024 states per CTA
-        if (B * S <= 148) {
+        if (B * S <= sms) {
             K = 2;
             while (K < 8 && (Pc + 32 * K - 1) / (32 * K) > 8) K *= 2;
         } else {
@@ -134,7 +138,7 @@ static bool choose_wave_shape(int64_t Lmax, int64_t B, AlignCfg *c) {
 static bool choose_wave_ring(int64_t B, int V, AlignCfg *c) {
     c->slot_bytes = ring_slot_bytes(V);
     c->chunk = 8 * c->slot_bytes <= 16384 ? 8 : 4;
-    const int budget = (B * c->S <= 148) ? 160 * 1024 : 72 * 1024;
+    const int budget = (B * c->S <= device_sm_count()) ? 160 * 1024 : 72 * 1024;
     int stages = budget / (c->chunk * c->slot_bytes);
     // warp w works >= w chunks behind warp 0: W+2 stages at least, W+6 cover the bulk-copy latency as well
     if (stages > c->W + 6) stages = c->W + 6;
@@ -440,6 +444,36 @@ __device__ __forceinline__ float ld_seam_shared(const float *p) {
     asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+// Watchdog of the seam polls.  With the co-residency the launch guarantees (cooperative or cluster launch) an
+// upstream warp always makes progress, so this never fires; if it does (10 s of WALL time without the upstream
+// value, %globaltimer) the poller sets the call's abort word, every poller that sees the word gives up as well,
+// the warps drain their emission ring so that the producers finish, and the back-trace kernel reports status 2
+// for the utterances of the call -- a status, not a __trap() that would poison the caller's CUDA context.
+constexpr int kNoAbort = -1;   // (the abort word is preset by the same 0xff memset as the global seam buffer)
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct SpinGuard {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    // call after every failed poll; true = give up
+    __device__ __forceinline__ bool expired(int *abort_word) {
+        if ((++spins & 0x3fffu) != 0) return false;
+        int a;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(abort_word) : "memory");
+        if (a != kNoAbort) return true;
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) {
+            t0 = now;
+        } else if (now - t0 > 10000000000ull) {
+            atomicExch(abort_word, 1);
+            return true;
+        }
+        return false;
+    }
+};
 __device__ __forceinline__ void st_seam_generic(float *p, float v) {  // shared or global (generic address)
     // no "memory" clobber: nothing in this thread reads the word back, and the clobber would pin every
     // emission load of the unrolled chunk behind the store of the previous frame
@@ -538,14 +572,15 @@ __global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p)
             const float val = (tt + 1 >= Tb + 1 - L) ? INF : mine + 0.0f;  // (+0.0f: a -0.0 becomes +0.0)
             for (int j = 0; j < 32 / CH && t0 + j * CH < Tb; ++j) {
                 float *dst = c0ring + slot * CH;
+                int gave_up = 0;
                 if (lane == 0) {
-                    unsigned spins = 0;
+                    SpinGuard guard;
                     while (__float_as_uint(ld_seam_shared(dst)) != kSeamEmpty) {
                         __nanosleep(100);
-                        if (++spins > (1u << 26)) __trap();   // the consumer never recycled the slot
+                        if (guard.expired(p.abort_word)) { gave_up = 1; break; }   // the consumer never recycled the slot
                     }
                 }
-                __syncwarp();
+                if (__shfl_sync(FULL, gave_up, 0)) return;
                 if (lane / CH == j && tt < Tb) dst[lane % CH] = val;
                 if (++slot == NSLOT) slot = 0;
             }
@@ -742,11 +777,23 @@ __global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p)
         // incoming values of this chunk: read early during the previous chunk, poll only if that was too soon
         float sv = sv_pre;
         {
-            unsigned spins = 0;
+            SpinGuard guard;
+            bool gave_up = false;
             while (__any_sync(FULL, lane < n && __float_as_uint(sv) == kSeamEmpty)) {
                 sv = up_smem ? ld_seam_shared(sv_in + sslot * CH + (lane & (CH - 1)))
                              : ld_seam_global(gs_in + min(t + (lane & (CH - 1)), Tb - 1));
-                if (++spins > (1u << 27)) __trap();   // ~10 s without the upstream seam: fail loudly, never hang
+                if (__any_sync(FULL, guard.expired(p.abort_word))) { gave_up = true; break; }
+            }
+            if (gave_up) {
+                // watchdog: drain the emission ring (the producer waits for every live warp) and leave
+                while (remaining > 0) {
+                    mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+                    remaining -= remaining < CH ? remaining : CH;
+                    if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
+                }
+                return;
             }
             if (up_smem && inlane) const_cast<float *>(sv_in)[sslot * CH + lane] = EMPTY;  // recycle the slot
         }
@@ -804,7 +851,20 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
     int32_t *st_b = p.starts + (int64_t)b * p.Lmax;
     int32_t *en_b = p.ends + (int64_t)b * p.Lmax;
     double *sc_b = p.scores + (int64_t)b * p.Lmax;
-    const int t_start = (L == 0 || Tb == 0) ? 0 : p.t_start[b];
+    // status 2: the call's watchdog fired (see SpinGuard); status 3: a token id outside [0, V) -- the reference
+    // would raise an IndexError (align_transcriptions.py:49), the kernels only clamp for memory safety
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = (p.abort_word && *p.abort_word != kNoAbort) ? 2 : 0;
+    __syncthreads();
+    {
+        const int32_t *tkc = p.tokens + (int64_t)b * p.tok_stride;
+        int bad = 0;
+        for (int i = tid; i < L; i += blockDim.x) bad |= (tkc[i] < 0 || tkc[i] >= p.V) ? 1 : 0;
+        if (bad) atomicMax(&s_bad, 3);
+    }
+    __syncthreads();
+    const int bad_status = s_bad;
+    const int t_start = (L == 0 || Tb == 0 || bad_status) ? 0 : p.t_start[b];
 
     if (warp == 0) {
         int t = t_start, j = L, first = 0;
@@ -913,9 +973,9 @@ __global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams 
         }
         if (lane == 0) {
             const bool ok = j == 0 && L > 0 && t_start > 0;
-            s_status = ok ? 0 : 1;  // :121-122 "Failed to align"
+            s_status = (ok && !bad_status) ? 0 : 1;  // :121-122 "Failed to align"
             s_first = first;
-            p.status[b] = ok ? 0 : 1;
+            p.status[b] = bad_status ? bad_status : (ok ? 0 : 1);
         }
     }
     __syncthreads();
@@ -986,7 +1046,7 @@ static size_t align_smem_bytes(const AlignCfg &c) {
 
 using namespace ssak;
 
-struct AlignWs { size_t bp, rec, prob, col0, gseam, gseam_bytes, total; };
+struct AlignWs { size_t bp, rec, prob, col0, abort_word, gseam, gseam_bytes, total; };
 static AlignWs align_ws_layout(int64_t B, int64_t Tmax, int nw, int S) {
     AlignWs w;
     const size_t bt = align_up((size_t)B * (size_t)Tmax * sizeof(float), 256);
@@ -995,6 +1055,8 @@ static AlignWs align_ws_layout(int64_t B, int64_t Tmax, int nw, int S) {
     w.rec = o;   o += bt;
     w.prob = o;  o += bt;
     w.col0 = o;  o += bt;
+    w.abort_word = o;   // 256 bytes: the abort word, preset together with the seam buffer (one 0xff memset)
+    o += 256;
     w.gseam = o;
     w.gseam_bytes = (size_t)B * (size_t)(S > 1 ? S - 1 : 0) * (size_t)Tmax * sizeof(float);
     o += align_up(w.gseam_bytes, 256);
@@ -1045,52 +1107,67 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     p.prob = reinterpret_cast<float *>(ws + lay.prob);
     p.col0_eff = reinterpret_cast<float *>(ws + lay.col0);
     p.gseam = reinterpret_cast<float *>(ws + lay.gseam);
+    p.abort_word = reinterpret_cast<int *>(ws + lay.abort_word);
     p.starts = starts; p.ends = ends; p.scores = scores; p.t_start = t_start; p.status = status;
     p.dump = trellis_dump; p.path_token = path_token; p.path_prob = path_prob;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = SSAK_OK;
-    if (!wave) {   // (the wavefront kernel computes column 0 itself)
-        align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
-        rc = check_launch();
-        if (rc != SSAK_OK) return rc;
+    {   // the abort word (and, for S > 1, every cross-CTA seam word: "not there yet") starts as all ones
+        cudaError_t e = cudaMemsetAsync(p.abort_word, 0xff, 256 + (wave ? lay.gseam_bytes : 0), s);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
     }
-    if (wave) {
-        if (B > 65535) return SSAK_ERR_UNSUPPORTED;
-        if (lay.gseam_bytes) {  // every cross-CTA seam word starts as "not there yet"
-            cudaError_t e = cudaMemsetAsync(p.gseam, 0xff, lay.gseam_bytes, s);
-            if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
-        }
+    bool wave_launched = false;
+    if (wave && B <= 65535) {
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned)p.cfg.S, (unsigned)B);
         lc.blockDim = dim3((p.cfg.W + 2) * 32);   // recursion warps, emission producer, column-0 warp
         lc.dynamicSmemBytes = smem_bytes;
         lc.stream = s;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)p.cfg.S;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
         lc.attrs = attr;
-        lc.numAttrs = 1;
-        // The cluster launch is what guarantees that the CTAs of an utterance run together.  When the whole
-        // grid is resident at once anyway, a plain launch gives the same guarantee and lets the block scheduler
-        // spread the CTAs one per SM (8-CTA clusters fit only 15x on a B200 at one CTA per SM).
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const bool try_plain = align_env_int("SSAK_ALIGN_CLUSTER", 0) == 0;
+        // The CTAs of an utterance poll each other's seams, so they MUST be co-resident: S > 1 is launched either
+        // as a COOPERATIVE grid (the runtime guarantees that every CTA of the grid is resident, whatever else runs
+        // on the device; chosen when the whole grid fits, because the block scheduler then spreads the CTAs one
+        // per SM -- 8-CTA clusters fit only 15x on a B200) or as thread-block CLUSTERS of S <= 8 CTAs
+        // (co-scheduled by the hardware).  If neither is possible the per-frame-barrier kernel (one CTA per
+        // utterance) runs instead.  S == 1 has no cross-CTA dependency: plain launch.
+        const int sms = device_sm_count();
+        const bool prefer_cluster = align_env_int("SSAK_ALIGN_CLUSTER", 0) != 0;
 #define SSAK_WAVE3(KK, CC, DD)                                                                 \
     {                                                                                          \
         auto kern = align_wave_kernel<KK, CC, DD>;                                             \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_bytes);                                 \
+        cudaError_t e = ensure_max_smem<align_wave_kernel<KK, CC, DD>>();                      \
         int per_sm = 0;                                                                        \
-        if (e == cudaSuccess && try_plain)                                                     \
+        if (e == cudaSuccess)                                                                  \
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)lc.blockDim.x, smem_bytes); \
-        if (e == cudaSuccess && (int64_t)per_sm * sms >= (int64_t)p.cfg.S * B) lc.numAttrs = 0; \
-        if (e == cudaSuccess && lc.numAttrs != 0 && p.cfg.S > 8) return SSAK_ERR_UNSUPPORTED; /* clusters: <= 8 CTAs */ \
-        if (e == cudaSuccess) e = cudaLaunchKernelEx(&lc, kern, p);                            \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
+        const bool fits = (int64_t)per_sm * sms >= (int64_t)p.cfg.S * B;                       \
+        if (p.cfg.S == 1) {                                                                    \
+            lc.numAttrs = 0;                                                                   \
+            e = cudaLaunchKernelEx(&lc, kern, p);                                              \
+            wave_launched = e == cudaSuccess;                                                  \
+        } else {                                                                               \
+            e = cudaErrorCooperativeLaunchTooLarge;                                            \
+            if (fits && !prefer_cluster) {                                                     \
+                attr[0].id = cudaLaunchAttributeCooperative;                                   \
+                attr[0].val.cooperative = 1;                                                   \
+                lc.numAttrs = 1;                                                               \
+                e = cudaLaunchKernelEx(&lc, kern, p);                                          \
+                wave_launched = e == cudaSuccess;                                              \
+                if (!wave_launched) (void)cudaGetLastError();                                  \
+            }                                                                                  \
+            if (!wave_launched && p.cfg.S <= 8) {                                              \
+                attr[0].id = cudaLaunchAttributeClusterDimension;                              \
+                attr[0].val.clusterDim.x = (unsigned)p.cfg.S;                                  \
+                attr[0].val.clusterDim.y = 1;                                                  \
+                attr[0].val.clusterDim.z = 1;                                                  \
+                lc.numAttrs = 1;                                                               \
+                e = cudaLaunchKernelEx(&lc, kern, p);                                          \
+                wave_launched = e == cudaSuccess;                                              \
+                if (!wave_launched) (void)cudaGetLastError();                                  \
+            }                                                                                  \
+        }                                                                                      \
+        if (!wave_launched && p.cfg.S == 1) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }  \
     }
 #define SSAK_WAVE2(KK, CC)                                                                     \
     if (p.dump) SSAK_WAVE3(KK, CC, true) else SSAK_WAVE3(KK, CC, false)
@@ -1108,15 +1185,33 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
 #undef SSAK_WAVE
 #undef SSAK_WAVE2
 #undef SSAK_WAVE3
-    } else {
+    }
+    if (!wave_launched) {
+        // per-frame-barrier kernel: the configured shape, or the fall-back when the wavefront grid could not be
+        // made co-resident (the workspace is sized for the larger of the two shapes)
+        if (wave) {
+            if (!choose_barrier_cfg(Lmax, B, (int)V, &p.cfg)) return SSAK_ERR_UNSUPPORTED;
+            const AlignWs lay2 = align_ws_layout(B, Tmax, p.cfg.NW, p.cfg.S);
+            p.bp = reinterpret_cast<uint32_t *>(ws + lay2.bp);
+            p.rec = reinterpret_cast<uint32_t *>(ws + lay2.rec);
+            p.prob = reinterpret_cast<float *>(ws + lay2.prob);
+            p.col0_eff = reinterpret_cast<float *>(ws + lay2.col0);
+            p.abort_word = reinterpret_cast<int *>(ws + lay2.abort_word);
+            cudaError_t e = cudaMemsetAsync(p.abort_word, 0xff, 256, s);
+            if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
+        }
+        const size_t smem2 = align_smem_bytes(p.cfg);
+        if (smem2 > (size_t)kMaxDynSmem) return SSAK_ERR_UNSUPPORTED;
+        align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != SSAK_OK) return rc;
     dim3 grid((unsigned)B), block((p.cfg.W + 1) * 32);
 #define SSAK_LAUNCH2(KK, CC)                                                                   \
     {                                                                                          \
         auto kern = align_forward_kernel<KK, CC>;                                              \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_bytes);                                 \
+        cudaError_t e = ensure_max_smem<align_forward_kernel<KK, CC>>();                       \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
-        kern<<<grid, block, smem_bytes, s>>>(p);                                               \
+        kern<<<grid, block, smem2, s>>>(p);                                                    \
     }
 #define SSAK_LAUNCH(KK)                                                                        \
     case KK:                                                                                   \
@@ -1135,7 +1230,7 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     }
     rc = check_launch();
     if (rc != SSAK_OK) return rc;
-    if (!wave) align_backtrace_kernel<0><<<(unsigned)B, 256, 0, s>>>(p);
+    if (!wave_launched) align_backtrace_kernel<0><<<(unsigned)B, 256, 0, s>>>(p);
     else if (p.cfg.K <= 4) align_backtrace_kernel<4><<<(unsigned)B, 256, 0, s>>>(p);   // K = 1, 2 write the K = 4 layout
     else align_backtrace_kernel<8><<<(unsigned)B, 256, 0, s>>>(p);
     return check_launch();

@@ -17,13 +17,18 @@ __global__ void __launch_bounds__(256) greedy_argmax_kernel(const float *__restr
     const int sub = threadIdx.x % G;
     const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int64_t row_stride = (int64_t)gridDim.x * blockDim.x / G;
-    for (int64_t row = row0; row < rows; row += row_stride) {
-        const int64_t b = row / T, t = row - b * T;
+    // warp-uniform trip count (the row of the warp's FIRST group decides): the full-mask shuffles below must be
+    // executed by all 32 lanes even when the last groups of the warp have run out of rows; those skip the loads
+    const int64_t grp = (threadIdx.x & 31) / G;
+    for (int64_t row = row0; row - grp < rows; row += row_stride) {
+        const bool live = row < rows;
+        const int64_t b = live ? row / T : 0, t = live ? row - b * T : 0;
         const float *x = probs + b * sb + t * st;
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (V % 4 == 0);
-        if (vec) {
+        if (!live) {
+        } else if (vec) {
             const float4 *x4 = reinterpret_cast<const float4 *>(x);
             for (int i = sub; i < V / 4; i += G) {
                 const float4 q = __ldg(x4 + i);
@@ -46,7 +51,7 @@ __global__ void __launch_bounds__(256) greedy_argmax_kernel(const float *__restr
             const int oi = __shfl_xor_sync(0xffffffffu, bi, d, G);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (sub == 0) ids[row] = bi == 0x7fffffff ? 0 : bi;  // all -inf / NaN row -> index 0
+        if (sub == 0 && live) ids[row] = bi == 0x7fffffff ? 0 : bi;  // all -inf / NaN row -> index 0
     }
 }
 
@@ -118,7 +123,7 @@ extern "C" int ssak_ctc_greedy(const float *probs, int64_t B, int64_t T, int64_t
         while (G > 1 && V < 4 * G * 2) G >>= 1;
         const int threads = 256;
         int64_t blocks = (rows * G + threads - 1) / threads;
-        const int64_t cap = 148 * 16;
+        const int64_t cap = (int64_t)device_sm_count() * 16;
         if (blocks > cap) blocks = cap;
         switch (G) {
 #define SSAK_G(GG) case GG: greedy_argmax_kernel<GG><<<(unsigned)blocks, threads, 0, s>>>(probs, rows, T, (int)V, stride_b, stride_t, frame_ids); break;

@@ -96,6 +96,9 @@ struct CtcParams {
     float *tabs;    // [B][2][NCH][16] per-warp offset tables of the wavefront forward (see "offset tables")
     int NCH;        // table slots per (utterance, direction): one per forward chunk, the last one for the frontier
     float *nll;     // [B] out / in
+    int *abort_word;  // 0 until a seam poll of the wavefront forward gave up (watchdog); then every nll of the call is NaN
+    int *nan_flag;    // [B] set by the forward kernels when an emission the lattice uses is NaN (fmax-based log-sum-exp
+                      // would swallow it): the join kernel then returns a NaN likelihood, as torch does
     const float *grad_out;
     float *grad;
     int64_t gst, gsb;
@@ -114,7 +117,8 @@ static bool choose_cfg(int64_t Lmax, int64_t B, int V, CtcCfg *c) {
     const int64_t P = Lmax + 1;
     // Few CTAs (latency regime): one recursion warp per SM sub-partition.  Many CTAs
     // (throughput regime): fat lanes, few warps, so several utterances share an SM.
-    const bool few = env_int("SSAK_CTC_FEW", 2 * B <= 2 * 148 ? 1 : 0) != 0;
+    const int sms = device_sm_count();
+    const bool few = env_int("SSAK_CTC_FEW", B <= sms ? 1 : 0) != 0;
     int wtarget = few ? 8 : 4;
     wtarget = env_int("SSAK_CTC_WARPS", wtarget);
     int K = env_int("SSAK_CTC_K", 0);
@@ -263,11 +267,13 @@ ctc_lattice_kernel(const CtcParams p) {
     if (GRAD) {
         const float nll = p.nll[b];
         gs = p.grad_out[b];
-        const bool infeasible = !(nll < 3.0e38f);  // +inf (or NaN)
-        if (infeasible || Tb == 0) {
-            // zero_infinity: every row 0.  Otherwise torch yields NaN for t < T_b.
+        const bool infeasible = nll == __int_as_float(0x7f800000);  // +inf only: a NaN stays visible, as in torch
+        const bool isnan_ = nll != nll;
+        if (infeasible || isnan_ || Tb == 0) {
+            // zero_infinity: every row of an infeasible utterance 0.  Otherwise torch yields NaN for t < T_b; a NaN
+            // likelihood (NaN emissions of a diverged model, or an out-of-range target) gives a NaN gradient always.
             if (dir == 0) {
-                const float fillv = (infeasible && !p.zero_inf) ? __int_as_float(0x7fc00000) : 0.f;
+                const float fillv = (isnan_ || (infeasible && !p.zero_inf)) ? __int_as_float(0x7fc00000) : 0.f;
                 for (int t = 0; t < (int)p.T; ++t) {
                     float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
                     const float v = t < Tb ? fillv : 0.f;
@@ -547,18 +553,24 @@ ctc_lattice_kernel(const CtcParams p) {
             };
             float zv = 0.f, zv_next = z_fetch(0);
             int step0 = 0;
+            float nan_acc = 0.f;
             // one frame; `n` is the number of frames of the current chunk (a constant CH on the fast path)
             auto frame = [&](const int f, const int n) {
                 // the bulk copy lands the row (addr & 15) bytes into its slot; raw natural-log values
                 const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
                 const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
-                const float eb2 = fmaxf(LOGITS ? fmaf(*reinterpret_cast<const float *>(row + blank_off), kLog2e, zl)
-                                               : *reinterpret_cast<const float *>(row + blank_off) * kLog2e, kNeg);
+                const float eb_s = LOGITS ? fmaf(*reinterpret_cast<const float *>(row + blank_off), kLog2e, zl)
+                                          : *reinterpret_cast<const float *>(row + blank_off) * kLog2e;
+                const float eb2 = fmaxf(eb_s, kNeg);
+                if (!GRAD) nan_acc += eb_s;   // sticky NaN detector (fmaxf drops a NaN operand)
                 float el2[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    el2[k] = fmaxf(LOGITS ? fmaf(*reinterpret_cast<const float *>(row + lab_off[k]), kLog2e, zl)
-                                          : *reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
+                for (int k = 0; k < K; ++k) {
+                    const float el_s = LOGITS ? fmaf(*reinterpret_cast<const float *>(row + lab_off[k]), kLog2e, zl)
+                                              : *reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e;
+                    el2[k] = fmaxf(el_s, kNeg);
+                    if (!GRAD) nan_acc += el_s;
+                }
                 float xin = x_in[(f & 1) * 18];
                 if (f == 0) xin -= xfix;
                 float r[K];
@@ -693,6 +705,7 @@ ctc_lattice_kernel(const CtcParams p) {
                 em_chunk += CH * slot_bytes;
                 if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
             }
+            if (!GRAD && __any_sync(FULL, nan_acc != nan_acc) && lane == 0) p.nan_flag[b] = 1;
         };
         if (dir) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 0>{});
     } else if (GRAD && is_post) {
@@ -1098,17 +1111,22 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
     float zv = 0.f, zv_next = z_fetch(0);
 
     float sout[CH];
+    float nan_acc = 0.f;
     auto frame = [&](const int f, const float sv, auto direct_tag) {
         constexpr bool DIRECT = decltype(direct_tag)::value;
         const unsigned char *row = em_chunk + f * slot_bytes + ((a15_0 + f * a15_step) & 15u);
         const float zl = LOGITS ? __shfl_sync(FULL, zv, f) : 0.f;
         const float xb = *reinterpret_cast<const float *>(row + blank_off);
-        const float eb2 = fmaxf(LOGITS ? fmaf(xb, kLog2e, zl) : xb * kLog2e, kNeg);
+        const float eb_s = LOGITS ? fmaf(xb, kLog2e, zl) : xb * kLog2e;
+        const float eb2 = fmaxf(eb_s, kNeg);
+        nan_acc += eb_s;   // sticky NaN detector (fmaxf drops a NaN operand)
         float el2[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float x = *reinterpret_cast<const float *>(row + lab_off[k]);
-            el2[k] = fmaxf(LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e, kNeg);
+            const float el_s = LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e;
+            el2[k] = fmaxf(el_s, kNeg);
+            nan_acc += el_s;
         }
         const float xin = __shfl_sync(FULL, sv, f);
         if (DIRECT) {
@@ -1161,10 +1179,32 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         // lanes [0, n) the values, lane CH the sender's offset, lane CH+1 the row offset
         float sv = sv_pre;
         if (!first) {
+            // The upstream warp is a warp of this CTA and never waits on anything downstream, so the poll always
+            // ends; the watchdog (10 s of wall time) is a safety net that turns a bug into NaN likelihoods for the
+            // call (join kernel) instead of a hang or a __trap() that would poison the caller's CUDA context.
             unsigned spins = 0;
+            unsigned long long t0 = 0;
+            bool gave_up = false;
             while (__any_sync(FULL, (lane < n || (lane >= CH && lane < SW)) && __float_as_uint(sv) == kSeamEmptyBits)) {
                 sv = ld_volatile_shared_f32(sv_in + sslot * SW + (lane < SW ? lane : 0));
-                if (++spins > (1u << 27)) __trap();   // ~10 s without the upstream seam: fail loudly, never hang
+                if ((++spins & 0x3fffu) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    const bool stop = now - t0 > 10000000000ull || *reinterpret_cast<volatile int *>(p.abort_word) != 0;
+                    if (__any_sync(FULL, stop)) { gave_up = true; break; }
+                }
+            }
+            if (gave_up) {
+                if (lane == 0) atomicExch(p.abort_word, 1);
+                while (remaining > 0) {   // drain the emission ring: the producer waits for every live warp
+                    mbar_wait(&em_full[em_stage], (uint32_t)em_phase);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&em_empty[em_stage]);
+                    remaining -= remaining < CH ? remaining : CH;
+                    if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; }
+                }
+                return;
             }
             if (inlane) const_cast<float *>(sv_in)[sslot * SW + lane] = EMPTY;  // recycle the slot
             const int off_up = (int)__shfl_sync(FULL, sv, CH);
@@ -1212,6 +1252,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         if (++em_stage == NST) { em_stage = 0; em_phase ^= 1; em_chunk = em_base; }
         sslot = sslot_next;
     }
+    if (__any_sync(FULL, nan_acc != nan_acc) && lane == 0) p.nan_flag[b] = 1;
     // frontier row for the join kernel / the backward call (same conversion; nsteps == 0: the virtual start row)
     {
         float *fin = p.finals + ((int64_t)b * 2 + dir) * row_elems;
@@ -1279,7 +1320,12 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
         mx = nm;
     }
     if (lane == 0) { red_m[warp] = mx; red_s[warp] = sm; }
-    __syncthreads();
+    // A label outside [0, V) (or equal to nothing the lattice kernels could index) is an argument error the
+    // asynchronous device entry points cannot return: the kernels clamp it for memory safety and the utterance's
+    // likelihood becomes NaN here (loss and gradient NaN -- loud, never a silently wrong number).
+    int bad = 0;
+    for (int i = tid; i < L; i += 256) bad |= (tg[i] < 0 || tg[i] >= p.V) ? 1 : 0;
+    bad = __syncthreads_or(bad);
     if (tid == 0) {
         float M = red_m[0], S = red_s[0];
         for (int w = 1; w < 8; ++w) {
@@ -1291,7 +1337,8 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
         const double off_a = *reinterpret_cast<const double *>(fa + 2 * P_pad + 2);
         const double off_b = *reinterpret_cast<const double *>(fb + 2 * P_pad + 2);
         const double logp2 = (double)M + (double)log2f(S) + off_a + off_b + (double)Da + (double)Db;
-        p.nll[b] = dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453);
+        if ((p.abort_word && *p.abort_word != 0) || p.nan_flag[b] != 0) bad = 1;
+        p.nll[b] = bad ? __int_as_float(0x7fc00000) : (dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453));
         p.nll2[b] = -logp2;
     }
 }
@@ -1305,7 +1352,7 @@ __global__ void __launch_bounds__(256) ctc_reduce_kernel(const float *nll, const
     double a = 0.0, l = 0.0;
     for (int64_t b = tid; b < B; b += 256) {
         float x = nll[b];
-        const bool dropped = zero_inf && !(x < 3.0e38f);
+        const bool dropped = zero_inf && x == __int_as_float(0x7f800000);   // +inf only (torch: where(loss == inf, 0, loss))
         if (dropped) x = 0.f;
         const int L = tgt_len[b];
         const float denom = (float)(L < 1 ? 1 : L);
@@ -1332,7 +1379,7 @@ __global__ void __launch_bounds__(256) ctc_reduce_kernel(const float *nll, const
     }
     if (grad_scale && reduction == 3)
         for (int64_t b = tid; b < B; b += 256) {
-            const bool dropped = zero_inf && !(nll[b] < 3.0e38f);
+            const bool dropped = zero_inf && nll[b] == __int_as_float(0x7f800000);
             grad_scale[b] = dropped ? 0.f : (float)(1.0 / Lsum);
         }
 }
@@ -1390,7 +1437,7 @@ __global__ void __launch_bounds__(256) ctc_shard_pack_kernel(const float *nll, c
     double a = 0.0, l = 0.0;
     for (int64_t b = tid; b < B; b += 256) {
         float x = nll[b];
-        const bool dropped = zero_inf && !(x < 3.0e38f);
+        const bool dropped = zero_inf && x == __int_as_float(0x7f800000);
         if (dropped) x = 0.f;
         const int L = tgt_len[b];
         const float w = reduction == 1 ? 1.0f / (float)(L < 1 ? 1 : L) : 1.0f;
@@ -1438,8 +1485,7 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
 #define SSAK_LAUNCH4(KK, CC, ZZ, SP)                                                           \
     {                                                                                          \
         auto kern = ctc_lattice_kernel<KK, GRAD, CC, ZZ, SP>;                                  \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_bytes);                                 \
+        cudaError_t e = ensure_max_smem<ctc_lattice_kernel<KK, GRAD, CC, ZZ, SP>>();           \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
         kern<<<grid, block, smem_bytes, stream>>>(p);                                          \
     }
@@ -1472,7 +1518,8 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     // saved for the backward come with per-warp offset tables, which only the posterior warps (cfg.PW > 0) read.
     // SSAK_CTC_FWD_WAVE=1 forces it where it is valid, =0 disables it.
     const int mode = env_int("SSAK_CTC_FWD_WAVE", -1);
-    if (mode == 0 || (mode < 0 && 2 * p.B > 148)) return SSAK_ERR_UNSUPPORTED;   // B = 128: 0.243 vs 0.232 ms
+    const int sms = device_sm_count();
+    if (mode == 0 || (mode < 0 && 2 * p.B > sms)) return SSAK_ERR_UNSUPPORTED;   // B = 128: 0.243 vs 0.232 ms
     if (p.rows != nullptr && p.cfg.PW == 0) return SSAK_ERR_UNSUPPORTED;
     const int64_t P = (int64_t)p.Lmax + 1;
     if (P > 1024 || p.T > 100000) return SSAK_ERR_UNSUPPORTED;   // 32 * 4 * 8 chain elements; float-exact offsets
@@ -1485,7 +1532,7 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     if (wc.W > (wc.K == 1 ? 16 : 8)) return SSAK_ERR_UNSUPPORTED;
     wc.slot_bytes = ring_slot_bytes(p.V);
     wc.chunk = 8 * wc.slot_bytes <= 16384 ? 8 : 4;
-    const int budget = 2 * p.B <= 2 * 148 ? 100 * 1024 : 40 * 1024;
+    const int budget = p.B <= sms ? 100 * 1024 : 40 * 1024;
     int stages = budget / (wc.chunk * wc.slot_bytes);
     if (stages > wc.W + 6) stages = wc.W + 6;
     stages = env_int("SSAK_CTC_FWD_STAGES", stages);
@@ -1497,8 +1544,7 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
 #define SSAK_FW4(KK, CC, ZZ, SS)                                                               \
     {                                                                                          \
         auto kern = ctc_forward_wave_kernel<KK, CC, ZZ, SS>;                                   \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_bytes);                                 \
+        cudaError_t e = ensure_max_smem<ctc_forward_wave_kernel<KK, CC, ZZ, SS>>();            \
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
         kern<<<grid, block, smem_bytes, stream>>>(p, wc);                                      \
     }
@@ -1513,12 +1559,13 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
-struct WsLayout { size_t nll2, finals, zl, tabs, rows, total; };
+struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, rows, total; };
 static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
 static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
     WsLayout w;
     size_t o = 0;
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
+    w.abort_word = o; o += 256 + align_up((size_t)B * sizeof(int), 256);   // abort word, then nan_flag[B]: one memset
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
     w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
     w.tabs = o;   o += align_up((size_t)B * 2 * tab_slots(T) * 16 * sizeof(float), 256);
@@ -1550,6 +1597,8 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->rows = saved ? reinterpret_cast<float *>(ws + w.rows) : nullptr;
     p->zl = logits ? reinterpret_cast<float *>(ws + w.zl) : nullptr;
     p->tabs = reinterpret_cast<float *>(ws + w.tabs);
+    p->abort_word = reinterpret_cast<int *>(ws + w.abort_word);
+    p->nan_flag = reinterpret_cast<int *>(ws + w.abort_word + 256);
     p->NCH = tab_slots(T);
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
@@ -1565,6 +1614,16 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
     CtcCfg c;
     if (T < 0 || T > 300000 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
     return ws_layout(T, B, c.row_elems, save_for_backward != 0).total;
+}
+
+/* 1 when the kernels cover the shape, 0 otherwise (max_target_len > 4095, T > 300000, B <= 0, or a vocabulary
+ * whose rows do not fit the shared-memory emission ring, V > ~2040): callers that replace a generic operator use it
+ * to delegate unsupported shapes instead of failing. */
+extern "C" int ssak_ctc_loss_supported(int64_t T, int64_t B, int64_t V, int64_t max_target_len) {
+    CtcCfg c;
+    if (T < 0 || T > 300000 || B <= 0 || V <= 0 || V > (1 << 20) || max_target_len < 0) return 0;
+    if (!choose_cfg(max_target_len, B, (int)V, &c)) return 0;
+    return smem_bytes_for(c, (int)V, (int)max_target_len, true) <= (size_t)kMaxDynSmem ? 1 : 0;
 }
 
 static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,
@@ -1583,6 +1642,10 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         ctc_row_lse_kernel<<<(unsigned)((T * B + 7) / 8), 256, 0, s>>>(p);
         rc = check_launch();
         if (rc != SSAK_OK) return rc;
+    }
+    {
+        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + (size_t)B * sizeof(int), s);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
     }
     rc = launch_forward_wave(p, s);
     if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);

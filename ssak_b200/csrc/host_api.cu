@@ -2,6 +2,7 @@
 // owns their device scratch and stream.  These are what a caller without torch binds, and the
 // end-to-end benchmark path: HOST pointers in and out, host<->device copies inside the call.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -108,6 +109,10 @@ extern "C" int ssak_ctc_loss_host(ssak_context_t *ctx, const float *log_probs_ho
         if (input_lengths_host[b] < 0 || input_lengths_host[b] > T || target_lengths_host[b] < 0 ||
             target_lengths_host[b] > Smax)
             return SSAK_ERR_INVALID_ARGUMENT;
+    if (blank < 0 || blank >= V) return SSAK_ERR_INVALID_ARGUMENT;
+    for (int64_t b = 0; b < B; ++b)   // labels outside the vocabulary are an argument error, never clamped
+        for (int64_t i = 0; i < target_lengths_host[b]; ++i)
+            if (targets_host[b * Smax + i] < 0 || targets_host[b * Smax + i] >= V) return SSAK_ERR_INVALID_ARGUMENT;
     const bool want_grad = grad_host != nullptr;
     // Utterance sub-batches on separate streams: the host->device copy of sub-batch i+1, the kernels of
     // sub-batch i and the device->host copy of sub-batch i-1 overlap (utterances are independent).
@@ -185,7 +190,7 @@ extern "C" int ssak_ctc_loss_host(ssak_context_t *ctx, const float *log_probs_ho
     for (int i = 0; i < NS; ++i) SSAK_CUDA(cudaStreamSynchronize(ctx->sub[i]));
     if (zero_infinity)
         for (int64_t b = 0; b < B; ++b)
-            if (!(nll_host[b] < 3.0e38f)) nll_host[b] = 0.f;
+            if (std::isinf(nll_host[b]) && nll_host[b] > 0.f) nll_host[b] = 0.f;   // +inf only: NaN stays visible
     return SSAK_OK;
 }
 
@@ -201,6 +206,13 @@ extern "C" int ssak_forced_align_host(ssak_context_t *ctx, const float *emission
         !starts_host || !ends_host || !scores_host || !t_start_host || !status_host || B <= 0 ||
         Tmax < 0 || V <= 0 || Lmax < 0 || (first_as_garbage && !col0_host))
         return SSAK_ERR_INVALID_ARGUMENT;
+    for (int64_t b = 0; b < B; ++b) {
+        if (emission_lengths_host[b] < 0 || emission_lengths_host[b] > Tmax || token_lengths_host[b] < 0 ||
+            token_lengths_host[b] > Lmax)
+            return SSAK_ERR_INVALID_ARGUMENT;
+        for (int64_t i = 0; i < token_lengths_host[b]; ++i)
+            if (tokens_host[b * Lmax + i] < 0 || tokens_host[b * Lmax + i] >= V) return SSAK_ERR_INVALID_ARGUMENT;
+    }
     SSAK_CUDA(cudaSetDevice(ctx->device));
     const size_t n_em = (size_t)B * Tmax * V;
     const size_t ws_bytes = ssak_align_workspace_bytes(B, Tmax, Lmax);

@@ -64,10 +64,8 @@ class _CTCLossFunction(torch.autograd.Function):
         T, B, V = log_probs.shape
         dev = log_probs.device
         save = bool(ctx.needs_input_grad[0])
+        _require_supported(T, B, V, max_target_len)
         ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, max_target_len, int(save))
-        if ws_bytes == 0:
-            raise _lib.SsakB200Error(
-                f"ctc_loss: shape not supported (T={T}, B={B}, max target length={max_target_len})")
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         red = _RED_CODE[reduction]
@@ -112,6 +110,19 @@ class _CTCLossFunction(torch.autograd.Function):
         return grad, None, None, None, None, None, None, None, None, None
 
 
+def supported(T: int, B: int, V: int, max_target_len: int) -> bool:
+    """True when the sm_100a kernels cover the shape (ssak_ctc_loss_supported): max target length <= 4095,
+    T <= 300000, B >= 1 and a vocabulary whose rows fit the shared-memory emission ring (V <= ~2040)."""
+    return bool(_lib.lib().ssak_ctc_loss_supported(int(T), int(B), int(V), int(max_target_len)))
+
+
+def _require_supported(T, B, V, max_target_len):
+    if not supported(T, B, V, max_target_len):
+        raise _lib.SsakB200Error(
+            f"ctc_loss: shape not supported by the sm_100a kernels (T={T}, B={B}, V={V}, max target length="
+            f"{max_target_len}; limits: T <= 300000, B >= 1, V <= ~2040, max target length <= 4095)")
+
+
 def _prepare(log_probs, targets, input_lengths, target_lengths, blank):
     """Argument checking / normalisation shared by the public entry points (torch's rules)."""
     _lib.require_cuda(log_probs, "log_probs")
@@ -136,6 +147,16 @@ def _prepare(log_probs, targets, input_lengths, target_lengths, blank):
     if targets.is_floating_point():
         raise RuntimeError("targets must be integral")
     tg = targets
+    if not tg.is_cuda and tg.numel() and tgt_host is not None:
+        # host targets: labels outside the vocabulary are an argument error (device targets cannot be checked without
+        # a synchronisation: the kernels then return a NaN likelihood for the utterance instead of a wrong number)
+        if tg.dim() == 2:
+            used = torch.arange(tg.size(1)).unsqueeze(0) < torch.as_tensor(tgt_host).unsqueeze(1)
+            bad = ((tg < 0) | (tg >= V)) & used
+        else:
+            bad = (tg[: sum(tgt_host)] < 0) | (tg[: sum(tgt_host)] >= V)
+        if bool(bad.any()):
+            raise RuntimeError(f"targets must be in the label range [0, {V})")
     if tg.device != dev or tg.dtype != torch.int32 or not tg.is_contiguous():
         tg = tg.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
     if tg.dim() == 2:
@@ -234,15 +255,32 @@ _torch_ctc_loss = None
 _aten_lib = None
 
 
+def _covers(log_probs, targets, target_lengths) -> bool:
+    """Cheap pre-check used by install(): does `ctc_loss` cover this call?  (No synchronisation: the maximum target
+    length is bounded by the padded width, or by 4095 for concatenated targets with device lengths.)"""
+    if log_probs.dim() not in (2, 3) or log_probs.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        return False
+    T, V = log_probs.shape[0], log_probs.shape[-1]
+    B = log_probs.shape[1] if log_probs.dim() == 3 else 1
+    if isinstance(targets, torch.Tensor) and targets.dim() == 2:
+        lmax = targets.shape[1]
+        if lmax > 4095 and not (isinstance(target_lengths, torch.Tensor) and target_lengths.is_cuda):
+            lmax = max((int(v) for v in target_lengths), default=0)
+    elif isinstance(target_lengths, torch.Tensor) and target_lengths.is_cuda:
+        lmax = 0     # unknown without a sync; _prepare finds out and ctc_loss raises beyond the limit
+    else:
+        lmax = max((int(v) for v in target_lengths), default=0)
+    return B >= 1 and supported(T, B, V, min(lmax, 4095) if lmax <= 4095 else lmax)
+
+
 def _aten_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, zero_infinity=False):
     """aten::_ctc_loss on CUDA -> (neg_log_likelihood[B], opaque workspace handed back as `log_alpha`)."""
     lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, list(input_lengths), list(target_lengths),
                                                        blank)
     L = _lib.lib()
     T, B, V = lp.shape
+    _require_supported(T, B, V, lmax)
     ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, lmax, 1)
-    if ws_bytes == 0:
-        raise _lib.SsakB200Error(f"ctc_loss: shape not supported (T={T}, B={B}, max target length={lmax})")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lp.device)
     nll = torch.empty(B, dtype=torch.float32, device=lp.device)
     with torch.cuda.device(lp.device):
@@ -251,7 +289,7 @@ def _aten_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, z
                                      nll.data_ptr(), ws.data_ptr(), ws_bytes,
                                      torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "ssak_ctc_loss_forward")
-    return nll, ws
+    return nll.to(log_probs.dtype), ws   # (fp64 callers get fp64 back: autograd checks the dtype)
 
 
 def _aten_ctc_loss_backward(grad, log_probs, targets, input_lengths, target_lengths, neg_log_likelihood, log_alpha,
@@ -262,15 +300,16 @@ def _aten_ctc_loss_backward(grad, log_probs, targets, input_lengths, target_leng
     L = _lib.lib()
     T, B, V = lp.shape
     g = grad.to(torch.float32).expand(B).contiguous()
+    nll32 = neg_log_likelihood.to(torch.float32).contiguous()
     out = torch.empty((T, B, V), dtype=torch.float32, device=lp.device)
     with torch.cuda.device(lp.device):
         rc = L.ssak_ctc_loss_backward(g.data_ptr(), lp.data_ptr(), T, B, V, lp.stride(0), lp.stride(1), tg.data_ptr(),
                                       tgt_off.data_ptr(), in_len.data_ptr(), tgt_len.data_ptr(), lmax, int(blank),
-                                      int(zero_infinity), neg_log_likelihood.data_ptr(), out.data_ptr(),
+                                      int(zero_infinity), nll32.data_ptr(), out.data_ptr(),
                                       out.stride(0), out.stride(1), log_alpha.data_ptr(), log_alpha.numel(),
                                       torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "ssak_ctc_loss_backward")
-    return out
+    return out.to(log_probs.dtype)
 
 
 def install(mode: str = "functional") -> None:
@@ -302,8 +341,10 @@ def install(mode: str = "functional") -> None:
 
     def patched(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean",
                 zero_infinity=False):
-        if isinstance(log_probs, torch.Tensor) and log_probs.is_cuda:
+        if isinstance(log_probs, torch.Tensor) and log_probs.is_cuda and _covers(log_probs, targets, target_lengths):
             return ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, reduction, zero_infinity)
+        # CPU tensors, and the shapes the kernels do not cover (V > ~2040: large BPE vocabularies, target length
+        # > 4095, T > 300000, an empty batch, dtypes other than fp32/fp16/bf16): torch's own implementation
         return _torch_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, reduction,
                                zero_infinity)
 

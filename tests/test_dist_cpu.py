@@ -60,3 +60,41 @@ def test_sharded_loss_matches_single_process(reduction):
         assert torch.allclose(torch.from_numpy(grad), x.grad[:, mine], atol=1e-6)
         seen += mine
     assert sorted(seen) == list(range(10))
+
+
+def _worker_empty(rank, world, port, out):
+    import torch.distributed as dist
+    from ssak_b200.shard import lattice_cost, lpt_partition, sharded_ctc_loss
+    from ssak_b200.synth import ctc_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lp, tg, il, tl = ctc_batch(2, 30, 9, 2, 8, 6, Tmin=20, planted=False)
+        mine = lpt_partition(lattice_cost(il.tolist(), tl.tolist()), world)[rank]   # 2 utterances, 3 ranks: one is empty
+        x = lp[:, mine].clone().requires_grad_(True)
+        loss = sharded_ctc_loss(x, tg[mine], il[mine], tl[mine], reduction="mean", zero_infinity=True,
+                                global_batch=2, loss_fn=_cpu_loss)
+        loss.backward()
+        out.put((rank, mine, float(loss), x.grad.detach().numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_empty_shard_takes_part_in_the_collective():
+    """Fewer utterances than ranks: the rank with an empty shard must not hang the others in the all-reduce; it
+    gets the global loss and an empty gradient."""
+    from ssak_b200.synth import ctc_batch
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_empty, args=(r, 3, port, q)) for r in range(3)]
+    [p.start() for p in procs]
+    results = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    lp, tg, il, tl = ctc_batch(2, 30, 9, 2, 8, 6, Tmin=20, planted=False)
+    ref = float((_cpu_loss(lp, tg, il, tl, reduction="none", zero_infinity=True) / tl.clamp_min(1)).mean())
+    assert sorted(len(m) for _, m, _, _ in results) == [0, 1, 1]
+    for rank, mine, loss, grad in results:
+        assert abs(loss - ref) <= 5e-5 * abs(ref), (rank, loss, ref)
+        assert grad.shape[1] == len(mine)

@@ -1,0 +1,247 @@
+"""Parity at the sizes the benchmark quotes (BASELINE.json configs C3, C4, C5 and the 1k-utterance batch), through
+the DEFAULT launch path -- i.e. the many-CTA ("throughput") shapes of the loss and aligner kernels that the small
+cases of test_gpu_loss.py / test_gpu_align.py never reach -- against torch's CPU ctc_loss in fp64 (the arithmetic
+the reference reaches, site-packages/torch/nn/functional.py:3042-3115) and the C oracle of
+ssak/utils/align_transcriptions.py:27-157 on a seeded sample of >= 8 utterances per configuration, plus
+size-independent properties over the whole batch.
+
+Stated tolerances: loss 1e-5 relative to the fp64 truth; gradient 1e-4 absolute to the fp64 truth (planted
+emissions; for unpeaked random emissions at T = 1500 the bar is "no further from the fp64 truth than torch's own
+fp32 kernel"); alignments bit-exact.  The measured errors are written to
+gpurun_out/parity_r2.json (copied to profiles/r2_parity_errors.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 1e-5
+GRAD_ATOL = 1e-4
+
+
+def _record(key, value):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "parity_r2.json")
+    data = {}
+    if os.path.exists(path):
+        try:
+            data = json.load(open(path))
+        except ValueError:
+            data = {}
+    data[key] = value
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+def _sample(B, n=8, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randperm(B, generator=g)[:n].sort().values.tolist()
+    return sorted(set(idx) | {0, B - 1})
+
+
+def _loss_check(name, lp, tg, il, tl, random_emissions=False, from_logits=False):
+    """Whole batch through ssak_b200.ctc_loss ('none', zero_infinity) on the default launch shape; sample vs fp64."""
+    import ssak_b200
+    T, B, V = lp.shape
+    x = lp.cuda().requires_grad_(True)
+    fn = ssak_b200.ctc_loss_from_logits if from_logits else ssak_b200.ctc_loss
+    loss = fn(x, tg, il, tl, 0, "none", True)
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    loss, grad = loss.detach().cpu(), x.grad.cpu()
+    del x
+    idx = _sample(B)
+    y = lp[:, idx].double().clone().requires_grad_(True)
+    yl = F.log_softmax(y, -1) if from_logits else y
+    l64 = F.ctc_loss(yl, tg[idx], il[idx], tl[idx], 0, "none", True)
+    l64.sum().backward()
+    g64 = y.grad
+    y32 = lp[:, idx].clone().requires_grad_(True)
+    yl32 = F.log_softmax(y32, -1) if from_logits else y32
+    F.ctc_loss(yl32, tg[idx], il[idx], tl[idx], 0, "none", True).sum().backward()
+    rel = ((loss[idx].double() - l64.detach()).abs() / l64.detach().abs().clamp_min(1e-3)).max().item()
+    gerr = (grad[:, idx].double() - g64).abs().max().item()
+    terr = (y32.grad.double() - g64).abs().max().item()
+    rowsum = grad.sum(-1).abs().max().item()
+    _record(name, {"loss_rel_err_vs_fp64": rel, "grad_abs_err_vs_fp64": gerr, "torch_fp32_cpu_grad_abs_err_vs_fp64": terr,
+                   "max_abs_row_sum": rowsum, "sample": idx, "B": B, "T": T, "V": V,
+                   "tolerance": {"loss_rel": LOSS_RTOL, "grad_abs": GRAD_ATOL if not random_emissions else
+                                 "max(1e-4, 1.5 * torch fp32 error + 1e-5)"}})
+    print(f"{name}: loss rel {rel:.2e}, grad err {gerr:.2e} (torch fp32 CPU: {terr:.2e}), |row sum| {rowsum:.2e}")
+    assert torch.isfinite(loss).all()
+    assert rel <= LOSS_RTOL, f"{name}: loss rel err {rel:.3e}"
+    bar = GRAD_ATOL if not random_emissions else max(GRAD_ATOL, 1.5 * terr + 1e-5)
+    assert gerr <= bar, f"{name}: grad abs err {gerr:.3e} (bar {bar:.3e})"
+    assert rowsum < 2e-3
+    for b in idx:   # exact zeros beyond the utterance
+        assert (grad[int(il[b]):, b] == 0).all()
+    return loss, grad
+
+
+def _c4_batch():
+    """BASELINE config C4: 256 utterances, T_b ~ U[300,1500], L_b = 0.27 T_b, V = 50 (bench.py builds the same)."""
+    from ssak_b200.synth import planted_emissions
+    g = torch.Generator().manual_seed(1234 + 4)
+    B, T, V = 256, 1500, 50
+    il = torch.randint(300, T + 1, (B,), generator=g)
+    tl = (0.27 * il.float()).round().long().clamp_min(1)
+    tg = torch.randint(1, V, (B, int(tl.max())), generator=g)
+    lp = torch.empty(T, B, V)
+    for b in range(B):
+        e = torch.randn(T, V, generator=g)
+        e[: int(il[b])] = planted_emissions(int(il[b]), V, tg[b, : int(tl[b])], g, 0, normalize=False)
+        lp[:, b] = e.log_softmax(-1)
+    return lp, tg, il, tl
+
+
+def test_loss_c4_ragged_256():
+    lp, tg, il, tl = _c4_batch()
+    _loss_check("loss_c4_ragged_B256", lp, tg, il, tl)
+
+
+def test_loss_1k_batch():
+    from ssak_b200.synth import ctc_batch
+    lp, tg, il, tl = ctc_batch(1024, 1500, 50, 200, 400, 99, Tmin=1200, planted=True)
+    _loss_check("loss_1k_B1024", lp, tg, il, tl)
+
+
+def test_loss_1k_batch_random_emissions_quarter():
+    """Unpeaked emissions in the many-CTA regime (B = 256 > 148): the re-centring has to keep up everywhere."""
+    from ssak_b200.synth import ctc_batch
+    lp, tg, il, tl = ctc_batch(256, 1500, 50, 200, 400, 98, Tmin=1200, planted=False)
+    _loss_check("loss_random_B256", lp, tg, il, tl, random_emissions=True)
+
+
+def test_loss_c5_512_v1024():
+    from ssak_b200.synth import ctc_batch
+    lp, tg, il, tl = ctc_batch(512, 750, 1024, 100, 200, 99, Tmin=600, planted=True)
+    _loss_check("loss_c5_B512_V1024", lp, tg, il, tl)
+    # the logits entry point on the same shape (row normaliser + LOGITS kernels in the many-CTA regime)
+    g = torch.Generator().manual_seed(3)
+    logits = lp * 1.5 + 2.0 + torch.randn(750, 512, 1, generator=g)
+    del lp
+    _loss_check("loss_c5_from_logits", logits, tg, il, tl, from_logits=True)
+
+
+def test_loss_many_cta_shape_forced_small(monkeypatch):
+    """SSAK_CTC_FEW=0 forces the many-CTA launch shape (no posterior warps, small rings, barrier forward) at a size
+    the oracle covers completely."""
+    from ssak_b200.synth import ctc_batch
+    monkeypatch.setenv("SSAK_CTC_FEW", "0")
+    import ssak_b200
+    for seed, (B, T, V, Lmin, Lmax, planted) in enumerate([(7, 160, 50, 5, 60, True), (5, 90, 20, 0, 30, False),
+                                                           (3, 700, 50, 250, 330, True), (4, 64, 1024, 3, 30, False)]):
+        lp, tg, il, tl = ctc_batch(B, T, V, Lmin, Lmax, 700 + seed, Tmin=T // 2, planted=planted)
+        x = lp.cuda().requires_grad_(True)
+        loss = ssak_b200.ctc_loss(x, tg, il, tl, 0, "none", True)
+        loss.sum().backward()
+        y = lp.double().requires_grad_(True)
+        ref = F.ctc_loss(y, tg, il, tl, 0, "none", True)
+        ref.sum().backward()
+        fin = torch.isfinite(ref)
+        assert torch.equal(torch.isfinite(loss.cpu()), fin)
+        rel = ((loss.detach().cpu().double() - ref.detach()).abs() / ref.detach().abs().clamp_min(1e-3))[fin].max().item()
+        assert rel <= LOSS_RTOL, (seed, rel)
+        assert (x.grad.cpu().double() - y.grad).abs().max().item() <= GRAD_ATOL, seed
+
+
+def _align_check(name, em, toks, el, tl, n_sample=8, fag=False):
+    import ssak_b200
+    B = em.shape[0]
+    res = ssak_b200.forced_align(em.cuda(), toks, el, tl, first_as_garbage=fag)
+    torch.cuda.synchronize()
+    st, en, sc = res.starts.cpu().numpy(), res.ends.cpu().numpy(), res.scores.cpu().numpy()
+    ts, status = res.t_start.cpu().numpy(), res.status.cpu().numpy()
+    assert (status == 0).all(), f"{name}: {int((status != 0).sum())} utterances failed to align"
+    for b in range(B):   # properties over the whole batch
+        Lb = int(tl[b])
+        assert (st[b, :Lb] < en[b, :Lb]).all() and (en[b, : Lb - 1] == st[b, 1:Lb]).all(), f"{name} b={b}: spans"
+        assert en[b, Lb - 1] == ts[b] <= int(el[b]) and st[b, 0] >= 0
+        assert ((sc[b, :Lb] > 0) & (sc[b, :Lb] <= 1.0 + 1e-6)).all()
+    idx = _sample(B, n_sample)
+    worst = 0.0
+    for b in idx:
+        Tb, Lb = int(el[b]), int(tl[b])
+        rc, ss, se, ssc, t0 = O.align(em[b, :Tb].numpy(), toks[b, :Lb].tolist(), 0, fag)
+        assert rc == 0 and ts[b] == t0, f"{name} b={b}: t_start {ts[b]} vs {t0}"
+        assert st[b, :Lb].tolist() == ss.tolist(), f"{name} b={b}: starts differ"
+        assert en[b, :Lb].tolist() == se.tolist(), f"{name} b={b}: ends differ"
+        worst = max(worst, float(np.max(np.abs(sc[b, :Lb] - ssc) / ssc)))
+        np.testing.assert_allclose(sc[b, :Lb], ssc, rtol=1e-6, atol=0)
+    _record(name, {"spans": "bit-exact", "score_rel_err": worst, "sample": idx, "B": B, "T": int(em.shape[1]),
+                   "V": int(em.shape[2]), "Lmax": int(tl.max())})
+
+
+def test_align_c5_512_v1024():
+    from ssak_b200.synth import align_batch
+    em, toks, el, tl = align_batch(512, 750, 1024, 100, 200, 5, Tmin=600)
+    _align_check("align_c5_B512_V1024", em, toks, el, tl)
+
+
+def test_align_c2_shape_and_1k():
+    from ssak_b200.synth import align_batch
+    em, toks, el, tl = align_batch(64, 1500, 50, 200, 400, 5, Tmin=1200)
+    _align_check("align_c2shape_B64", em, toks, el, tl)
+    em, toks, el, tl = align_batch(1024, 1500, 50, 200, 400, 6, Tmin=1200)
+    _align_check("align_1k_B1024", em, toks, el, tl)
+
+
+def test_align_c4_ragged_256():
+    lp, tg, il, tl = _c4_batch()
+    em = lp.transpose(0, 1).contiguous()
+    _align_check("align_c4_ragged_B256", em, tg.to(torch.int32), il.to(torch.int32), tl.to(torch.int32))
+
+
+def test_align_c3_full():
+    """BASELINE config C3 at full size: 16 ten-minute utterances (T = 30000, L ~ 8000) -- the 144-CTA launch with
+    cross-CTA seams; 8 of them against the oracle (a 960 MB trellis each)."""
+    from ssak_b200.synth import align_batch
+    em, toks, el, tl = align_batch(16, 30000, 50, 7600, 8000, 5, Tmin=30000)
+    _align_check("align_c3_B16_T30000", em, toks, el, tl, n_sample=6)
+
+
+def test_align_first_as_garbage_device_col0_tie_heavy():
+    """first_as_garbage column 0 = log(1 - exp(e[:, tok0])) (align_transcriptions.py:37).  The default computes it
+    with torch ops ON THE GPU; the reference's HF / torchaudio back-ends compute it on the CPU.  10^4 tie-heavy
+    utterances: the alignments through the device-computed column against the oracle (CPU torch column), counting
+    the utterances whose spans flip."""
+    import ssak_b200
+    from ssak_b200.synth import tie_emissions
+    g = torch.Generator().manual_seed(4242)
+    B, T, V, Lmax = 10000, 40, 12, 12
+    em = tie_emissions(B * T, V, g).view(B, T, V).clamp_max(-0.5)   # exact binary fractions, exp() < 1
+    tl = torch.randint(2, Lmax + 1, (B,), generator=g).to(torch.int32)
+    el = torch.randint(T // 2, T + 1, (B,), generator=g).to(torch.int32)
+    toks = torch.randint(0, V, (B, Lmax), generator=g).to(torch.int32)
+    dev = ssak_b200.forced_align(em.cuda(), toks, el, tl, first_as_garbage=True)
+    col0_cpu = torch.stack([(1 - em[b, :, int(toks[b, 0])].exp()).log() for b in range(B)])
+    cpu = ssak_b200.forced_align(em.cuda(), toks, el, tl, first_as_garbage=True, col0=col0_cpu)
+    torch.cuda.synchronize()
+    same = ((dev.starts == cpu.starts).all(1) & (dev.ends == cpu.ends).all(1) & (dev.status == cpu.status)
+            & (dev.t_start == cpu.t_start)).cpu()
+    flips = int((~same).sum())
+    # the CPU-column run is the reference-exact one: check a sample of it against the oracle
+    st, en, status = cpu.starts.cpu().numpy(), cpu.ends.cpu().numpy(), cpu.status.cpu().numpy()
+    n_ok = 0
+    for b in range(0, B, 25):
+        Tb, Lb = int(el[b]), int(tl[b])
+        rc, ss, se, _, t0 = O.align(em[b, :Tb].numpy(), toks[b, :Lb].tolist(), 0, True)
+        assert (status[b] == 0) == (rc == 0)
+        if rc == 0:
+            n_ok += 1
+            assert st[b, :Lb].tolist() == ss.tolist() and en[b, :Lb].tolist() == se.tolist()
+    ulp = (col0_cpu.cuda() - (1 - em.cuda().gather(2, toks[:, :1].long().cuda().view(B, 1, 1).expand(B, T, 1)).squeeze(2).exp()).log())
+    n_diff = int((ulp != 0).sum())
+    _record("align_first_as_garbage_device_col0", {"utterances": B, "span_flips_device_vs_cpu_column": flips,
+                                                   "col0_elements_differing_cuda_vs_cpu": n_diff,
+                                                   "col0_elements": B * T, "oracle_checked": n_ok})
+    print(f"first_as_garbage: {flips} of {B} utterances flip; {n_diff} of {B * T} column-0 elements differ")
+    assert n_ok > 100
+    assert flips <= B // 100, f"{flips} of {B} alignments differ between the CUDA and the CPU column 0"

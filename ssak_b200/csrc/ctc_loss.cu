@@ -46,6 +46,7 @@
 //     per-warp integer re-centring with side tables of offsets (see "offset tables" below).
 //   * Logits entry points: ctc_row_lse_kernel + the LOGITS flag of the lattice kernels (log_softmax never
 //     materialised).  Sharded (multi-GPU) reduction: ctc_shard_*_kernel around the caller's one all-reduce.
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -97,6 +98,8 @@ struct CtcParams {
     int NCH;        // table slots per (utterance, direction): one per forward chunk, the last one for the frontier
     float *nll;     // [B] out / in
     int *abort_word;  // 0 until a seam poll of the wavefront forward gave up (watchdog); then every nll of the call is NaN
+    const int *mask;  // [B] or nullptr: when set, only the utterances with bit 0 set are processed (the ones the linear-domain
+                      // kernels of ctc_lin.cuh handed back, see there)
     int *nan_flag;    // [B] set by the forward kernels when an emission the lattice uses is NaN (fmax-based log-sum-exp
                       // would swallow it): the join kernel then returns a NaN likelihood, as torch does
     const float *grad_out;
@@ -213,6 +216,7 @@ ctc_lattice_kernel(const CtcParams p) {
     const int rw = is_post ? warp - post0 : warp;        // the recursion warp whose state group this warp handles
     const unsigned FULL = 0xffffffffu;
 
+    if (p.mask && !(p.mask[b] & 1)) return;
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[b];
@@ -562,15 +566,15 @@ ctc_lattice_kernel(const CtcParams p) {
                 const float eb_s = LOGITS ? fmaf(*reinterpret_cast<const float *>(row + blank_off), kLog2e, zl)
                                           : *reinterpret_cast<const float *>(row + blank_off) * kLog2e;
                 const float eb2 = fmaxf(eb_s, kNeg);
-                if (!GRAD) nan_acc += eb_s;   // sticky NaN detector (fmaxf drops a NaN operand)
+                // sticky NaN detector on the blank column (fmaxf drops a NaN operand): a diverged model emits whole NaN
+                // rows, and one add per frame costs no registers (summing the label columns as well cost 17 registers
+                // and a resident CTA per SM in the many-CTA shapes)
+                if (!GRAD) nan_acc += eb_s;
                 float el2[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float el_s = LOGITS ? fmaf(*reinterpret_cast<const float *>(row + lab_off[k]), kLog2e, zl)
-                                              : *reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e;
-                    el2[k] = fmaxf(el_s, kNeg);
-                    if (!GRAD) nan_acc += el_s;
-                }
+                for (int k = 0; k < K; ++k)
+                    el2[k] = fmaxf(LOGITS ? fmaf(*reinterpret_cast<const float *>(row + lab_off[k]), kLog2e, zl)
+                                          : *reinterpret_cast<const float *>(row + lab_off[k]) * kLog2e, kNeg);
                 float xin = x_in[(f & 1) * 18];
                 if (f == 0) xin -= xfix;
                 float r[K];
@@ -980,6 +984,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
     const int W = wc.W;
     const float EMPTY = __uint_as_float(kSeamEmptyBits);
 
+    if (p.mask && !(p.mask[b] & 1)) return;
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[b];
@@ -1119,14 +1124,12 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         const float xb = *reinterpret_cast<const float *>(row + blank_off);
         const float eb_s = LOGITS ? fmaf(xb, kLog2e, zl) : xb * kLog2e;
         const float eb2 = fmaxf(eb_s, kNeg);
-        nan_acc += eb_s;   // sticky NaN detector (fmaxf drops a NaN operand)
+        nan_acc += eb_s;   // sticky NaN detector on the blank column (fmaxf drops a NaN operand)
         float el2[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float x = *reinterpret_cast<const float *>(row + lab_off[k]);
-            const float el_s = LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e;
-            el2[k] = fmaxf(el_s, kNeg);
-            nan_acc += el_s;
+            el2[k] = fmaxf(LOGITS ? fmaf(x, kLog2e, zl) : x * kLog2e, kNeg);
         }
         const float xin = __shfl_sync(FULL, sv, f);
         if (DIRECT) {
@@ -1274,6 +1277,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
 __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     __shared__ float red_m[8], red_s[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (p.mask && !(p.mask[b] & 1)) return;
     int L = p.tgt_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int P_pad = p.cfg.P_pad, row_elems = p.cfg.row_elems;
@@ -1475,6 +1479,10 @@ __global__ void ctc_shard_grad_scale_kernel(const float *gscale, const float *gr
     if (b < B) out[b] = gscale[b] * (grad_loss[0] * inv_den[0]);
 }
 
+}  // namespace ssak
+#include "ctc_lin.cuh"
+namespace ssak {
+
 // ---------------------------------------------------------------------------- launchers
 template <bool GRAD>
 static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
@@ -1559,13 +1567,29 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
-struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, rows, total; };
+// Linear-domain kernels (ctc_lin.cuh): used when the longest target fits 8 recursion warps of 64 positions.
+// SSAK_CTC_LINEAR=0 switches them off (everything then runs in the log domain).
+static bool lin_eligible(int64_t Lmax) {
+    return Lmax + 1 <= 32 * lin::K * lin::MAXW && env_int("SSAK_CTC_LINEAR", 1) != 0;
+}
+static inline int lin_nck(int64_t T) { return (int)((T / 2 + 1) / lin::C) + 2; }
+static inline int lin_ppad(int64_t Lmax) { return (int)((Lmax + 1 + 32 * lin::K - 1) / (32 * lin::K)) * 32 * lin::K; }
+
+struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, lin_fr, lin_ck, rows, total; };
 static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
-static WsLayout ws_layout(int64_t T, int64_t B, int row_elems, bool saved) {
+static WsLayout ws_layout(int64_t T, int64_t B, int64_t Lmax, int row_elems, bool saved) {
     WsLayout w;
     size_t o = 0;
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
-    w.abort_word = o; o += 256 + align_up((size_t)B * sizeof(int), 256);   // abort word, then nan_flag[B]: one memset
+    // abort word, then nan_flag[B], then the linear-domain kernels' flags[B]: one memset
+    w.abort_word = o; o += 256 + 2 * align_up((size_t)B * sizeof(int), 256);
+    w.lin_fr = w.lin_ck = o;
+    if (lin_eligible(Lmax)) {
+        const size_t ck_row = 2 * (size_t)lin_ppad(Lmax) + 2;
+        w.lin_fr = o; o += align_up((size_t)B * 2 * ck_row * sizeof(double), 256);
+        w.lin_ck = o;
+        if (saved) o += align_up((size_t)B * 2 * lin_nck(T) * ck_row * sizeof(double), 256);
+    }
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
     w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
     w.tabs = o;   o += align_up((size_t)B * 2 * tab_slots(T) * 16 * sizeof(float), 256);
@@ -1586,7 +1610,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     if (T > 300000) return SSAK_ERR_UNSUPPORTED;  // re-centring offsets are kept exact as fp32 integers (< 2^24)
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     if (!choose_cfg(Lmax, B, (int)V, &p->cfg)) return SSAK_ERR_UNSUPPORTED;
-    const WsLayout w = ws_layout(T, B, p->cfg.row_elems, saved);
+    const WsLayout w = ws_layout(T, B, Lmax, p->cfg.row_elems, saved);
     if (workspace_bytes < w.total) return SSAK_ERR_WORKSPACE;
     p->lp = log_probs; p->T = T; p->B = B; p->V = (int)V; p->st = st; p->sb = sb;
     p->targets = targets; p->tgt_off = tgt_off; p->in_len = in_len; p->tgt_len = tgt_len;
@@ -1599,6 +1623,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->tabs = reinterpret_cast<float *>(ws + w.tabs);
     p->abort_word = reinterpret_cast<int *>(ws + w.abort_word);
     p->nan_flag = reinterpret_cast<int *>(ws + w.abort_word + 256);
+    p->mask = nullptr;
     p->NCH = tab_slots(T);
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
@@ -1613,7 +1638,57 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
                                                 int save_for_backward) {
     CtcCfg c;
     if (T < 0 || T > 300000 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
-    return ws_layout(T, B, c.row_elems, save_for_backward != 0).total;
+    return ws_layout(T, B, max_target_len, c.row_elems, save_for_backward != 0).total;
+}
+
+// Fill the parameters of the linear-domain kernels from the log-domain ones (same problem, same workspace).
+static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin::Params *q, size_t *smem_fwd, size_t *smem_bwd) {
+    if (!lin_eligible(p.Lmax)) return false;
+    const WsLayout w = ws_layout(p.T, p.B, p.Lmax, p.cfg.row_elems, saved);
+    char *ws = reinterpret_cast<char *>(workspace);
+    q->lp = p.lp; q->T = p.T; q->B = p.B; q->V = p.V; q->st = p.st; q->sb = p.sb;
+    q->targets = p.targets; q->tgt_off = p.tgt_off; q->in_len = p.in_len; q->tgt_len = p.tgt_len;
+    q->Lmax = p.Lmax; q->blank = p.blank; q->zl = p.zl;
+    q->P_pad = lin_ppad(p.Lmax);
+    q->W = q->P_pad / (32 * lin::K);
+    q->ck_row = 2 * q->P_pad + 2;
+    q->NCK = lin_nck(p.T);
+    q->fr = reinterpret_cast<double *>(ws + w.lin_fr);
+    q->ck = reinterpret_cast<double *>(ws + w.lin_ck);
+    q->nll2 = p.nll2; q->nll = p.nll;
+    q->flags = reinterpret_cast<int *>(ws + w.abort_word + 256 + align_up((size_t)p.B * sizeof(int), 256));
+    q->nan_flag = p.nan_flag;
+    q->grad_out = p.grad_out; q->grad = p.grad; q->gst = p.gst; q->gsb = p.gsb; q->zero_inf = p.zero_inf;
+    q->save = saved ? 1 : 0;
+    q->G = 4;
+    q->NST = 3;
+    q->slot_bytes = ring_slot_bytes(p.V);
+    q->ncol_max = (int)std::min<int64_t>(p.V, (int64_t)p.Lmax + 1);
+    q->erow_bytes = 8 * (q->ncol_max + 1);
+    *smem_fwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, false).total;
+    *smem_bwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, true).total;
+    if (*smem_bwd > (size_t)kMaxDynSmem) {   // large vocabulary: two ring stages
+        q->NST = 2;
+        *smem_fwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, false).total;
+        *smem_bwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, true).total;
+    }
+    return *smem_bwd <= (size_t)kMaxDynSmem;
+}
+
+template <bool GRAD>
+static int launch_lin(const lin::Params &q, size_t smem_bytes, cudaStream_t s) {
+    dim3 grid((unsigned)q.B, 2), block((q.W + 1 + (GRAD ? q.G : 0)) * 32);
+    cudaError_t e;
+    if (q.zl) {
+        e = ensure_max_smem<lin::ctc_lin_kernel<GRAD, true>>();
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
+        lin::ctc_lin_kernel<GRAD, true><<<grid, block, smem_bytes, s>>>(q);
+    } else {
+        e = ensure_max_smem<lin::ctc_lin_kernel<GRAD, false>>();
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
+        lin::ctc_lin_kernel<GRAD, false><<<grid, block, smem_bytes, s>>>(q);
+    }
+    return check_launch();
 }
 
 /* 1 when the kernels cover the shape, 0 otherwise (max_target_len > 4095, T > 300000, B <= 0, or a vocabulary
@@ -1644,8 +1719,20 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         if (rc != SSAK_OK) return rc;
     }
     {
-        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + (size_t)B * sizeof(int), s);
+        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + 2 * align_up((size_t)B * sizeof(int), 256), s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
+    }
+    // Linear-domain kernels first (no stored lattice); the utterances they hand back (flags, see ctc_lin.cuh) are
+    // then recomputed by the log-domain kernels below, launched over the same grid with a mask.
+    lin::Params q;
+    size_t smem_f = 0, smem_b = 0;
+    if (lin_params(p, workspace, save_for_backward != 0, &q, &smem_f, &smem_b)) {
+        rc = launch_lin<false>(q, smem_f, s);
+        if (rc != SSAK_OK) return rc;
+        lin::ctc_lin_join_kernel<<<(unsigned)B, 256, 0, s>>>(q);
+        rc = check_launch();
+        if (rc != SSAK_OK) return rc;
+        p.mask = q.flags;
     }
     rc = launch_forward_wave(p, s);
     if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
@@ -1668,7 +1755,15 @@ static int backward_impl(const float *grad_out, const float *x, int64_t T, int64
     p.nll = const_cast<float *>(neg_log_likelihood);
     p.grad_out = grad_out; p.grad = grad; p.gst = g_stride_t; p.gsb = g_stride_b;
     p.zero_inf = zero_infinity;
-    return launch_lattice<true>(p, reinterpret_cast<cudaStream_t>(stream));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    lin::Params q;
+    size_t smem_f = 0, smem_b = 0;
+    if (lin_params(p, workspace, true, &q, &smem_f, &smem_b)) {
+        rc = launch_lin<true>(q, smem_b, s);
+        if (rc != SSAK_OK) return rc;
+        p.mask = q.flags;
+    }
+    return launch_lattice<true>(p, s);
 }
 
 extern "C" int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t B, int64_t V,

@@ -5,14 +5,17 @@
 // recursions over the other half, fused with the gradient), but
 //   * the recursion runs in the LINEAR domain in fp64: per (blank,label) pair and frame 3 DADD/DFMA + 2 DMUL on the
 //     B200's FP64 pipe (64 lanes per SM and clock) and NO transcendental -- the emissions exp(lp) are formed once per
-//     (frame, used vocabulary column) by a converter warp (one MUFU.EX2 each) instead of two log-sum-exp per state;
+//     (frame, used vocabulary column) by a helper warp (one MUFU.EX2 each) instead of two log-sum-exp per state;
+//   * ONE warp owns the whole lattice row of its (utterance, direction): K <= 16 (blank,label) positions per lane, so
+//     a frame costs one shuffle and no barrier, no cross-warp exchange, no polling (the lock-step version with 64
+//     positions per warp and a named barrier per frame measured ~270 cycles per frame, all of it latency);
 //   * every C = 8 frames the row is re-scaled to a maximum of ~2^400 by an exact power of two whose exponent is
 //     tracked as an integer, so a state more than ~2^1470 below the row maximum is flushed to zero (fp64: 11-bit
 //     exponent); see "range and the fallback" below;
 //   * NOTHING of the lattice is written per frame: the forward call stores one CHECKPOINT row every C frames
 //     (16 B per pair and 8 frames = 1 B per lattice cell, 8x less than the stored half lattices), and the backward
-//     call recomputes the C rows of a tile from its checkpoint into REGISTERS (the same lane owns the same states in
-//     both directions), then runs the live direction over the tile and multiplies: posterior = live x recomputed,
+//     call recomputes the C rows of a tile from its checkpoint into a shared-memory tile private to the warp (the same
+//     lane owns the same states in both directions), then runs the live direction over the tile and multiplies: posterior = live x recomputed,
 //     one DMUL, because the live direction is kept in the scaling 2^(E_R) / P of the tile it is passing through.
 //
 // Range and the fallback.  With both directions re-scaled to their own row maximum, a state that carries a share
@@ -29,9 +32,8 @@ namespace ssak {
 namespace lin {
 
 constexpr int C = 8;          // frames per chunk / rows per tile / checkpoint spacing
-constexpr int K = 2;          // (blank,label) positions per lane
 constexpr int TARGET = 400;   // re-scaled row maximum ~ 2^TARGET
-constexpr int MAXW = 8;       // recursion warps: 64 positions each -> max target length 511
+constexpr int MAXK = 16;      // positions per lane: 32 * 16 = 512 positions -> max target length 511
 constexpr float kLog2eLo = 1.925963e-08f;   // log2(e) - (float)log2(e)
 
 struct Params {
@@ -51,25 +53,25 @@ struct Params {
     double *nll2;         // [B] -log2 P
     float *nll;           // [B]
     int *flags;           // [B] bit 0: recompute this utterance with the log-domain kernels
-    int *nan_flag;        // (unused here: NaN propagates through the products)
+    int *slot;            // [B] row block of a handed-back utterance in the log-domain kernels' `rows`
+    int *slot_counter;    // next free row block
+    int n_slots;
     const float *grad_out;
     float *grad;
     int64_t gst, gsb;
     int zero_inf;
     int save;
-    int W, G, P_pad, NST, slot_bytes, ncol_max, erow_bytes;
+    int K, G, P_pad, NST, slot_bytes, ncol_max, erow_bytes;
 };
 
 struct Smem {
-    int bars, xchg, wmax, raw, ering, cid, occ_start, cursor, occ_pos, wlab, blank_acc, total;
+    int bars, raw, ering, cid, occ_start, cursor, occ_pos, tile, wlab, blank_acc, total;
 };
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
-__host__ __device__ inline Smem smem_map(int NST, int slot_bytes, int erow_bytes, int V, int Lmax, int P_pad, bool grad) {
+__host__ __device__ inline Smem smem_map(int NST, int slot_bytes, int erow_bytes, int V, int Lmax, int K, bool grad) {
     Smem m;
     int o = 0;
-    m.bars = o;      o += 8 * (4 * 4 + 2 * C + 2);            // raw_full / raw_empty [4] (+ 8 spare), post_full[2C], post_empty[2]
-    m.xchg = o;      o += 8 * 2 * 2 * (MAXW + 2);             // [live|recomputed][2 buffers][W+2] doubles
-    m.wmax = o;      o += 4 * 2 * 16;                         // [2][16] ints
+    m.bars = o;      o += 8 * (4 + 4 + 2 + 2 + 2 * C + 2);    // raw_full[4] raw_empty[4] e_full[2] e_empty[2] post_full[2C] post_empty[2]
     o = (o + 127) & ~127;
     m.raw = o;       o += NST * C * slot_bytes;
     o = al16(o);
@@ -78,8 +80,10 @@ __host__ __device__ inline Smem smem_map(int NST, int slot_bytes, int erow_bytes
     m.occ_start = o; o += al16(4 * (V + 2));
     m.cursor = o;    o += al16(4 * V);
     m.occ_pos = o;   o += al16(4 * (Lmax > 0 ? Lmax : 1));
+    m.tile = o;
+    if (grad) o += C * 2 * K * 32 * 8;                        // recomputed rows of the current tile (private to the recursion warp)
     m.wlab = o;
-    if (grad) o += 4 * 2 * C * (P_pad + 8);
+    if (grad) o += 4 * 2 * C * (32 * K + 8);
     m.blank_acc = o;
     if (grad) o += 4 * 2 * C;
     m.total = al16(o);
@@ -111,20 +115,19 @@ __device__ __forceinline__ double exp_to_double(float x, float zl2, bool &low) {
     const float lo = fmaf(x, kLog2e, -hi) + x * kLog2eLo;
     const float s = hi + zl2;
     const float bb = s - hi;
-    const float err = (hi - (s - bb)) + (zl2 - bb);          // TwoSum: s + err == hi + zl2
-    const float nf = rintf(s);
-    const float f = (s - nf) + (err + lo);                   // |f| <= 0.5 + tiny
-    const float mf = ex2_approx(f);
-    const unsigned mb = __float_as_uint(mf);
-    double r;
+    const float err = (hi - (s - bb)) + (zl2 - bb);          // TwoSum: s + err == hi + zl2 (zl2 == 0: err == 0)
+    const float sc = fminf(fmaxf(s, -1100.f), 1100.f);
+    const float tt = sc + 12582912.f;                        // round to nearest integer without the conversion pipe
+    const float nf = tt - 12582912.f;
+    const int n = __float_as_int(tt) - 0x4b400000;
+    const float f = (sc - nf) + (err + lo);                  // |f| <= 0.5 + tiny
+    const unsigned mb = __float_as_uint(ex2_approx(f));
+    double r = __hiloint2double((int)((mb >> 3) + 0x38000000u) + n * (1 << 20), (int)(mb << 29));
     if (!(s > -1000.f)) {                                    // underflow, -inf or NaN
         low = low || (x > -3.0e38f && x == x);
         r = (x != x) ? __longlong_as_double(0x7ff8000000000000ll) : 0.0;
     } else if (s > 1000.f) {
         r = __longlong_as_double(0x7ff0000000000000ll);      // (un-normalised inputs only)
-    } else {
-        const int n = (int)nf;
-        r = __hiloint2double((int)((mb >> 3) + 0x38000000u) + n * (1 << 20), (int)(mb << 29));
     }
     return r;
 }
@@ -133,27 +136,26 @@ __device__ __forceinline__ double exp_to_double(float x, float zl2, bool &low) {
 // carry is label q-1; D = 1 (beta): position q = (label q-1 [stored in l], blank q), the carry is label q [position
 // q+1].  Same arithmetic both ways, only the order of the lane's positions differs:
 //   A = b + carry;  t = l + b + skip * carry;  b' = A * e_blank;  l' = t * e_label.
-// pre_b / pre_l are the states before their emission (what a posterior needs), cs[k] the carry position k received.
-template <int D>
-__device__ __forceinline__ void step(double (&b)[K], double (&l)[K], const double eb, const double (&el)[K],
-                                     const double (&sk)[K], const double cin, double (&pre_b)[K], double (&pre_l)[K],
-                                     double (&cs)[K]) {
+// `visit(k, b_old, carry, A, t)` sees the position before it is overwritten (A, t: the states before their emission,
+// which is what a posterior needs; b_old, carry: the aligned copy of the row the backward recomputation keeps).
+template <int K, int D, typename Visit>
+__device__ __forceinline__ void step(double (&b)[K], double (&l)[K], const double eb, const unsigned char *erow,
+                                     const int (&eoff)[K], const double (&sk)[K], const double cin, Visit visit) {
     double carry = cin;
 #pragma unroll
     for (int kk = 0; kk < K; ++kk) {
         const int k = D ? K - 1 - kk : kk;
-        cs[k] = carry;
+        const double el = *reinterpret_cast<const double *>(erow + eoff[k]);
         const double A = b[k] + carry;
-        double t = l[k] + b[k];
-        t = fma(sk[k], carry, t);
+        const double t = fma(sk[k], carry, l[k] + b[k]);   // (a 0/1 factor: a predicated add costs ptxas a P2R/ISETP/FSEL mess)
+        visit(k, b[k], carry, A, t);
         carry = l[k];
-        pre_b[k] = A;
-        pre_l[k] = t;
         b[k] = A * eb;
-        l[k] = t * el[k];
+        l[k] = t * el;
     }
 }
 
+template <int K>
 __device__ __forceinline__ int hi_max(const double (&b)[K], const double (&l)[K]) {
     int h = 0;
 #pragma unroll
@@ -161,19 +163,19 @@ __device__ __forceinline__ int hi_max(const double (&b)[K], const double (&l)[K]
     return h;
 }
 
-// Warp roles: [0, W) recursion; W emission producer (bulk copies of the raw fp32 rows); backward only: G gradient
-// warps.  The recursion warps themselves turn the raw rows into the fp64 emission ring, one chunk AHEAD: while they
-// step through frame f of a chunk, each thread converts its share of the used columns of row f of the next chunk
-// (independent work that fills the stall slots of the recursion's dependent chain; the per-frame barrier publishes
-// it).  (A dedicated converter warp was the bottleneck of the first version: ~650 cycles per frame for one warp.)
-template <bool GRAD, bool LOGITS>
-__global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 1) ctc_lin_kernel(const Params p) {
+// One CTA per (utterance, direction).  Warp roles: 0 recursion -- the ONLY warp that touches the lattice, K positions
+// per lane, so a frame needs no barrier, no cross-warp exchange: one shuffle for the lane-to-lane carry and a chain of
+// three fp64 operations; 1 helper -- issues the bulk copies of the raw fp32 rows and turns the used vocabulary columns
+// into the fp64 emission ring, one chunk ahead (mbarriers both ways); backward only: G gradient warps behind the
+// posterior ring.
+template <int K, bool GRAD, bool LOGITS>
+__global__ void __launch_bounds__(GRAD ? 128 : 64) ctc_lin_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int b = blockIdx.x, dir = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int W = p.W, G = GRAD ? p.G : 0;
-    const int V = p.V, P_pad = p.P_pad, NST = p.NST, slot_bytes = p.slot_bytes, erow_bytes = p.erow_bytes;
+    const int G = GRAD ? p.G : 0;
+    const int V = p.V, P_pad = 32 * K, NST = p.NST, slot_bytes = p.slot_bytes, erow_bytes = p.erow_bytes;
 
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
@@ -182,21 +184,20 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
     const int m = Tb >> 1;
     const float *lp_b = p.lp + (int64_t)b * p.sb;
     const int32_t *tg = p.targets + p.tgt_off[b];
-    const int rdir = GRAD ? 1 - dir : dir;                     // direction whose rows this launch steps through frames with
+    const int rdir = GRAD ? 1 - dir : dir;                     // direction whose rows this launch steps through
     const int nrows = rdir ? Tb - m : m;                       // frames this CTA handles
     auto frame_of = [&](int rho) { return rdir ? Tb - 1 - rho : rho; };   // frame of local row rho of direction rdir
 
-    const Smem sm = smem_map(NST, slot_bytes, erow_bytes, V, p.Lmax, P_pad, GRAD);
+    const Smem sm = smem_map(NST, slot_bytes, erow_bytes, V, p.Lmax, K, GRAD);
     uint64_t *raw_full = reinterpret_cast<uint64_t *>(smem + sm.bars);
-    uint64_t *raw_empty = raw_full + 4;
-    uint64_t *post_full = raw_full + 16, *post_empty = post_full + 2 * C;
-    double *xchg = reinterpret_cast<double *>(smem + sm.xchg);     // [2 kinds][2 buffers][MAXW + 2]
-    int *wmax = reinterpret_cast<int *>(smem + sm.wmax);          // [2][16]
+    uint64_t *raw_empty = raw_full + 4, *e_full = raw_full + 8, *e_empty = raw_full + 10;
+    uint64_t *post_full = raw_full + 12, *post_empty = post_full + 2 * C;
     unsigned char *raw = smem + sm.raw, *ering = smem + sm.ering;
     int *cid = reinterpret_cast<int *>(smem + sm.cid);
     int *occ_start = reinterpret_cast<int *>(smem + sm.occ_start);
     int *cursor = reinterpret_cast<int *>(smem + sm.cursor);      // counters, then the ascending list of used columns
     int *occ_pos = reinterpret_cast<int *>(smem + sm.occ_pos);
+    double *tile = reinterpret_cast<double *>(smem + sm.tile);    // [C][2K][32]
     float *wlab = reinterpret_cast<float *>(smem + sm.wlab);
     unsigned *blank_acc = reinterpret_cast<unsigned *>(smem + sm.blank_acc);
     const int WL = P_pad + 8;
@@ -222,18 +223,18 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
         }
     }
 
-    int wlive = L / (32 * K) + 1;                              // warps that own a live position (0..L)
-    wlive = wlive > W ? W : wlive;
-    const bool compute = warp < wlive;
-
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(&raw_full[s], 1);
-            mbar_init(&raw_empty[s], wlive + G);
+            mbar_init(&raw_empty[s], G > 0 ? G : 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&e_full[s], 1);
+            mbar_init(&e_empty[s], 1);
         }
         if (GRAD) {
             for (int s = 0; s < 2 * C; ++s) {
-                mbar_init(&post_full[s], wlive);
+                mbar_init(&post_full[s], 1);
                 blank_acc[s] = 0u;
             }
             mbar_init(&post_empty[0], G);
@@ -241,7 +242,6 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < 2 * 2 * (MAXW + 2); i += blockDim.x) xchg[i] = 0.0;
     // sentinel column of every emission-ring row: emission 0 -> the states beyond position L stay 0
     for (int i = tid; i < 2 * C; i += blockDim.x)
         *reinterpret_cast<double *>(ering + (size_t)i * erow_bytes + erow_bytes - 8) = 0.0;
@@ -328,38 +328,85 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
         }
     };
 
-    if (warp == W) {
-        // ================= producer: bulk copies of the raw fp32 rows, mbarriers only =================
-        for (int n = 0; n < n_seq; ++n) {
-            const int stage = n % NST, round = n / NST;
-            if (round > 0) mbar_wait(&raw_empty[stage], (uint32_t)((round - 1) & 1));
+    if (warp == 1) {
+        // ================= helper: bulk copies of the raw rows + conversion into the fp64 emission ring =================
+        auto issue = [&](int n) {
             int row0, i0, nr;
             seq_rows(n, row0, i0, nr);
+            const int stage = n % NST;
             if (lane == 0) {
                 uint32_t total = 0;
                 for (int i = i0; i < nr; ++i) {
                     const uintptr_t a = reinterpret_cast<uintptr_t>(lp_b + (int64_t)frame_of(row0 + i) * p.st);
                     total += (uint32_t)(((a + 4 * V + 15) & ~(uintptr_t)15) - (a & ~(uintptr_t)15));
                 }
-                if (total == 0) {
-                    mbar_arrive(&raw_full[stage]);
-                } else {
-                    mbar_arrive_expect_tx(&raw_full[stage], total);
-                    for (int i = i0; i < nr; ++i) {
-                        const uintptr_t a = reinterpret_cast<uintptr_t>(lp_b + (int64_t)frame_of(row0 + i) * p.st);
-                        const uintptr_t a0 = a & ~(uintptr_t)15;
-                        bulk_g2s(raw + ((size_t)stage * C + i) * slot_bytes, reinterpret_cast<const void *>(a0),
-                                 (uint32_t)(((a + 4 * V + 15) & ~(uintptr_t)15) - a0), &raw_full[stage]);
-                    }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
+                mbar_arrive_expect_tx(&raw_full[stage], total);
+                for (int i = i0; i < nr; ++i) {
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(lp_b + (int64_t)frame_of(row0 + i) * p.st);
+                    const uintptr_t a0 = a & ~(uintptr_t)15;
+                    bulk_g2s(raw + ((size_t)stage * C + i) * slot_bytes, reinterpret_cast<const void *>(a0),
+                             (uint32_t)(((a + 4 * V + 15) & ~(uintptr_t)15) - a0), &raw_full[stage]);
                 }
             }
             __syncwarp();
+        };
+        for (int n = 0; n < NST && n < n_seq; ++n) issue(n);
+        bool low = false;
+        for (int n = 0; n < n_seq; ++n) {
+            const int stage = n % NST, round = n / NST;
+            int row0, i0, nr;
+            seq_rows(n, row0, i0, nr);
+            mbar_wait(&raw_full[stage], (uint32_t)(round & 1));
+            if (n >= 2) mbar_wait(&e_empty[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
+            // per-slot source offset and row normaliser: slot i in lane i
+            int my_off = 0;
+            float my_zl = 0.f;
+            if (lane >= i0 && lane < nr) {
+                const int t = frame_of(row0 + lane);
+                const float *src = lp_b + (int64_t)t * p.st;
+                my_off = (stage * C + lane) * slot_bytes + (int)(reinterpret_cast<uintptr_t>(src) & 15);
+                if (LOGITS) my_zl = __ldg(p.zl + (int64_t)t * p.B + b);
+            }
+            unsigned char *edst = ering + (size_t)(n & 1) * C * erow_bytes;
+            // row by row, two rows at a time; a lane owns the columns c = lane + 32 j of the used-column list (their
+            // vocabulary indices are loop-invariant), two of them per pass: four independent conversion chains in flight
+            for (int c0 = 0; c0 < np; c0 += 64) {
+                const int ca = c0 + lane, cb = c0 + 32 + lane;
+                const bool oka = ca < np, okb = cb < np;
+                const int va = 4 * cursor[oka ? ca : 0], vb = 4 * cursor[okb ? cb : 0];
+                for (int i = i0; i < nr; i += 2) {
+                    const bool two = i + 1 < nr;
+                    const int off0 = __shfl_sync(FULL, my_off, i), off1 = __shfl_sync(FULL, my_off, two ? i + 1 : i);
+                    const float z0 = __shfl_sync(FULL, my_zl, i), z1 = __shfl_sync(FULL, my_zl, two ? i + 1 : i);
+                    const float x00 = *reinterpret_cast<const float *>(raw + off0 + va);
+                    const float x01 = *reinterpret_cast<const float *>(raw + off0 + vb);
+                    const float x10 = *reinterpret_cast<const float *>(raw + off1 + va);
+                    const float x11 = *reinterpret_cast<const float *>(raw + off1 + vb);
+                    const double r00 = exp_to_double(x00, z0, low), r01 = exp_to_double(x01, z0, low);
+                    const double r10 = exp_to_double(x10, z1, low), r11 = exp_to_double(x11, z1, low);
+                    double *d0 = reinterpret_cast<double *>(edst + (size_t)i * erow_bytes);
+                    double *d1 = reinterpret_cast<double *>(edst + (size_t)(i + 1) * erow_bytes);
+                    if (oka) d0[ca] = r00;
+                    if (okb) d0[cb] = r01;
+                    if (two && oka) d1[ca] = r10;
+                    if (two && okb) d1[cb] = r11;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e_full[n & 1]);
+            if (n + NST < n_seq) {
+                if (GRAD) mbar_wait(&raw_empty[stage], (uint32_t)(round & 1));   // the gradient warps read the raw rows too
+                issue(n + NST);
+            }
         }
+        if (__any_sync(FULL, low) && lane == 0) atomicOr(&p.flags[b], 1);
         return;
     }
-    if (GRAD && warp >= W + 1) {
+
+    if (GRAD && warp >= 2) {
         // ================= gradient warps: consume the posterior ring (as in ctc_lattice_kernel) =================
-        const int gwarp = warp - (W + 1);
+        const int gwarp = warp - 2;
         const bool vec_ok = (V & 3) == 0 && ((p.gst | p.gsb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0;
         unsigned present = 0;
         {
@@ -371,10 +418,7 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
             float rsum = 0.f;
             const int q1 = occ_start[cc + 1];
             for (int q = occ_start[cc]; q < q1; ++q) rsum += w[q];
-            if (cc == p.blank) {
-                rsum += (float)blank_acc[slot] * (1.0f / 1073741824.0f);
-                blank_acc[slot] = 0u;
-            }
+            if (cc == p.blank) rsum += (float)blank_acc[slot] * (1.0f / 1073741824.0f);
             return rsum;
         };
         for (int n = 0; n < n_seq; ++n) {
@@ -431,32 +475,37 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
         }
         return;
     }
-    if (!compute) return;   // recursion warps beyond position L
 
-    // ================= recursion warps =================
-    const int nbar = wlive * 32;
-    const int q0 = (warp * 32 + lane) * K;                     // my first position
+    // ================= recursion warp =================
+    const int q0 = lane * K;                                   // my first position
     const int eoff_blank = 8 * cid[p.blank];
-    // static tables of a direction D at my positions: emission offset of the label state, skip factor
-    auto tables = [&](int D, int (&eoff)[K], double (&sk)[K]) {
+    // static tables of a direction D at my positions: emission offset of the label state, skip bit
+    auto tables = [&](int D, int (&eoff)[K]) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int q = q0 + k, li = D ? q - 1 : q;
             eoff[k] = sentinel_off;
-            sk[k] = 0.0;
             if (q <= L && li >= 0 && li < L) {
                 int l = tg[li];
                 l = l < 0 ? 0 : (l >= V ? V - 1 : l);
                 eoff[k] = 8 * cid[l];
-                const int lo = D ? li + 1 : li - 1;
-                if (lo >= 0 && lo < L) {
-                    int l2 = tg[lo];
-                    l2 = l2 < 0 ? 0 : (l2 >= V ? V - 1 : l2);
-                    if (l2 != l) sk[k] = 1.0;
-                }
             }
         }
     };
+    // skip factor of position q: labels q-1 and q both exist and differ -- the SAME condition for alpha (label q may
+    // be entered from label q-1) and for beta (label q-1 may continue into label q): one table for both directions
+    double sk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int q = q0 + k;
+        sk[k] = 0.0;
+        if (q >= 1 && q < L) {
+            int l1 = tg[q - 1], l2 = tg[q];
+            l1 = l1 < 0 ? 0 : (l1 >= V ? V - 1 : l1);
+            l2 = l2 < 0 ? 0 : (l2 >= V ? V - 1 : l2);
+            if (l1 != l2) sk[k] = 1.0;
+        }
+    }
     auto load_row = [&](const double *row, double (&bb)[K], double (&ll)[K]) -> int {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -475,7 +524,7 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
                 row[P_pad + q] = ll[k];
             }
         }
-        if (tid == 0) row[2 * P_pad] = (double)E;
+        if (lane == 0) row[2 * P_pad] = (double)E;
     };
     auto start_row = [&](int D, double (&bb)[K], double (&ll)[K]) {
 #pragma unroll
@@ -484,126 +533,70 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
             ll[k] = 0.0;
         }
     };
-    // cross-warp carry exchange of a direction D through xchg[kind][buffer][slot]: warp w writes its boundary label
-    // state into slot w + 1 - D ... and reads slot w (D = 0: from warp w-1; guard 0 at slot 0) or w + 1 (D = 1: from
-    // warp w+1; guard 0 at slot wlive)
-    auto xslot_out = [&](int D) { return D ? warp : warp + 1; };
-    auto xslot_in = [&](int D) { return D ? warp + 1 : warp; };
-    // ---- emission conversion by the recursion warps: row (slot) i of sequence element n -> emission ring half n & 1
-    const int rt = warp * 32 + lane, NT = wlive * 32;
-    bool low = false;
-    auto convert_row = [&](int n, int i, int row0) {
-        const int t = frame_of(row0 + i);
-        const float *src = lp_b + (int64_t)t * p.st;
-        const unsigned char *rowb = raw + ((size_t)(n % NST) * C + i) * slot_bytes + (reinterpret_cast<uintptr_t>(src) & 15);
-        const float zl2 = LOGITS ? __ldg(p.zl + (int64_t)t * p.B + b) : 0.f;
-        double *dst = reinterpret_cast<double *>(ering + ((size_t)(n & 1) * C + i) * erow_bytes);
-        for (int c = rt; c < np; c += NT)
-            dst[c] = exp_to_double(*reinterpret_cast<const float *>(rowb + 4 * cursor[c]), zl2, low);
+    // lane-to-lane carry of direction D: the boundary label state of the neighbour lane, 0 at the end of the chain
+    auto carry_in = [&](int D, const double (&ll)[K]) -> double {
+        const double nb = D ? __shfl_down_sync(FULL, ll[0], 1) : __shfl_up_sync(FULL, ll[K - 1], 1);
+        return lane == (D ? 31 : 0) ? 0.0 : nb;
     };
-    // the first chunk / tile is converted up front (the only conversion on the critical path)
-    if (n_seq > 0) {
-        int row0, i0, nr;
-        seq_rows(0, row0, i0, nr);
-        mbar_wait(&raw_full[0], 0u);
-        for (int i = i0; i < nr; ++i) convert_row(0, i, row0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[0]);
-        named_bar_sync(1, wlive * 32);
-    }
     double *ck_base = p.ck + ((int64_t)b * 2) * p.NCK * p.ck_row;
     double *fr_base = p.fr + ((int64_t)b * 2) * p.ck_row;
 
     if (!GRAD) {
         // ---------------- forward: one direction, checkpoint every C rows, frontier at the end ----------------
-        const int D = dir;
         int eoff[K];
-        double sk[K], bs[K], ls[K];
-        tables(D, eoff, sk);
-        start_row(D, bs, ls);
+        double bs[K], ls[K];
+        tables(dir, eoff);
+        start_row(dir, bs, ls);
         int E = 0;
-        double *xq = xchg;                                      // kind 0
-        const int so = xslot_out(D), si = xslot_in(D);
-        const int edge = D ? 31 : 0, outlane = D ? 0 : 31;
-        int par = 0;
-        Scale2 fix;
-        fix.f1 = fix.f2 = 1.0;
-        double *ck_dir = ck_base + (int64_t)D * p.NCK * p.ck_row;
+        double *ck_dir = ck_base + (int64_t)dir * p.NCK * p.ck_row;
+        auto nop = [](int, double, double, double, double) {};
         for (int n = 0; n < n_seq; ++n) {
-            const int stage = n % NST, round = n / NST;
             int row0, i0, nr;
             seq_rows(n, row0, i0, nr);
-            (void)stage; (void)round;
-            int nrow0 = 0, ni0 = 0, nnr = 0;                     // the next chunk: converted while this one runs
-            if (n + 1 < n_seq) {
-                seq_rows(n + 1, nrow0, ni0, nnr);
-                mbar_wait(&raw_full[(n + 1) % NST], (uint32_t)(((n + 1) / NST) & 1));
-            }
+            mbar_wait(&e_full[n & 1], (uint32_t)((n >> 1) & 1));
             const unsigned char *er = ering + (size_t)(n & 1) * C * erow_bytes;
-            auto frame = [&](const int f, const int nfr) {
-                if (f >= ni0 && f < nnr) convert_row(n + 1, f, nrow0);
-                const double eb = *reinterpret_cast<const double *>(er + f * erow_bytes + eoff_blank);
-                double el[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) el[k] = *reinterpret_cast<const double *>(er + f * erow_bytes + eoff[k]);
-                double xin = xq[par * (MAXW + 2) + si];
-                if (f == 0) xin = xin * fix.f1 * fix.f2;
-                const double nb = D ? __shfl_down_sync(FULL, ls[0], 1) : __shfl_up_sync(FULL, ls[K - 1], 1);
-                const double cin = lane == edge ? xin : nb;
-                double pre_b[K], pre_l[K], cs[K];
-                if (D) step<1>(bs, ls, eb, el, sk, cin, pre_b, pre_l, cs); else step<0>(bs, ls, eb, el, sk, cin, pre_b, pre_l, cs);
-                if (lane == outlane) xq[(par ^ 1) * (MAXW + 2) + so] = D ? ls[0] : ls[K - 1];
-                par ^= 1;
-                if (f == nfr - 1) {
-                    const int h = __reduce_max_sync(FULL, hi_max(bs, ls));
-                    if (lane == 0) wmax[(n & 1) * 16 + warp] = h;
-                }
-                named_bar_sync(1, nbar);
+            auto frame = [&](const int f) {
+                const unsigned char *erow = er + f * erow_bytes;
+                const double eb = *reinterpret_cast<const double *>(erow + eoff_blank);
+                if (dir) step<K, 1>(bs, ls, eb, erow, eoff, sk, carry_in(1, ls), nop);
+                else step<K, 0>(bs, ls, eb, erow, eoff, sk, carry_in(0, ls), nop);
             };
-            if (nr == C) {
-#pragma unroll
-                for (int f = 0; f < C; ++f) frame(f, C);
-            } else {
+            // (not unrolled over the frames: a frame is already 13 x ~10 instructions, and eight copies of it cost
+            //  instruction-cache misses -- "no_instruction" was the second stall reason of the unrolled version)
 #pragma unroll 1
-                for (int f = 0; f < nr; ++f) frame(f, nr);
-                for (int f = nr; f < nnr; ++f) convert_row(n + 1, f, nrow0);   // (cannot happen: only the last chunk is partial)
-            }
-            if (n + 1 < n_seq) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[(n + 1) % NST]);
-            }
-            // re-scale the row to a maximum of ~2^TARGET (every warp computes the same factor)
-            int M = 0;
-            for (int w = 0; w < wlive; ++w) M = max(M, wmax[(n & 1) * 16 + w]);
+            for (int f = 0; f < nr; ++f) frame(f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e_empty[n & 1]);
+            // re-scale the row to a maximum of ~2^TARGET (the warp owns the whole row: one integer REDUX)
+            const int M = __reduce_max_sync(FULL, hi_max<K>(bs, ls));
             int d = 0;
             if (M >= 0x7ff00000) {
-                if (tid == 0) atomicOr(&p.flags[b], 1);         // inf / NaN: let the log-domain kernels decide
+                if (lane == 0) atomicOr(&p.flags[b], 1);        // inf / NaN: let the log-domain kernels decide
             } else if (M >= 0x00100000) {
                 d = TARGET - ((M >> 20) - 1023);
             }
-            fix = make_scale(d);
             if (d != 0) {
+                const Scale2 sc = make_scale(d);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    bs[k] = bs[k] * fix.f1 * fix.f2;
-                    ls[k] = ls[k] * fix.f1 * fix.f2;
+                    bs[k] = bs[k] * sc.f1 * sc.f2;
+                    ls[k] = ls[k] * sc.f1 * sc.f2;
                 }
                 E -= d;
             }
             if (p.save && nr == C) store_row(ck_dir + (int64_t)(n + 1) * p.ck_row, bs, ls, E);
         }
-        store_row(fr_base + (int64_t)D * p.ck_row, bs, ls, E);
-        if (__any_sync(FULL, low) && lane == 0) atomicOr(&p.flags[b], 1);
+        store_row(fr_base + (int64_t)dir * p.ck_row, bs, ls, E);
         return;
     }
 
-    // ---------------- backward: recompute direction R = 1 - dir tile by tile, run direction dir live ----------------
+    // ---------------- backward: recompute direction DR = 1 - dir tile by tile, run direction dir live ----------------
     if (nrows == 0) return;
     const int DL = dir, DR = 1 - dir;
     int eoffL[K], eoffR[K], wl_off[K];
-    double skL[K], skR[K], lb[K], ll[K], rb[K], rl[K];
-    tables(DL, eoffL, skL);
-    tables(DR, eoffR, skR);
+    double lb[K], ll[K];
+    tables(DL, eoffL);
+    tables(DR, eoffR);
 #pragma unroll
     for (int k = 0; k < K; ++k) {   // slot of my live label state in the label-sorted posterior buffer
         const int q = q0 + k, li = DL ? q - 1 : q;
@@ -614,73 +607,56 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
     const double Epd = floor(log2P);
     const double invPm = 1.0 / exp2(log2P - Epd);
     const int Ep = (int)Epd;
-    double *xL = xchg, *xR = xchg + 2 * (MAXW + 2);
-    const int soL = xslot_out(DL), siL = xslot_in(DL), soR = xslot_out(DR), siR = xslot_in(DR);
-    const int edgeL = DL ? 31 : 0, outL = DL ? 0 : 31, edgeR = DR ? 31 : 0, outR = DR ? 0 : 31;
-    int parL = 0, parR = 0, prevER = 0;
+    int prevER = 0;
     const double *ck_dir = ck_base + (int64_t)DR * p.NCK * p.ck_row;
-    // the live frontier's boundary state for the first live step
-    if (lane == outL) xL[parL * (MAXW + 2) + soL] = DL ? ll[0] : ll[K - 1];
-    Scale2 fixL;
+    double *tl = tile + lane;                                   // my column of the tile: entry (i, kk) at (i * 2K + kk) * 32
     bool bad = false;
     for (int n = 0; n < n_seq; ++n) {
-        const int stage = n % NST, round = n / NST;
         int row0, i0, nr;
         seq_rows(n, row0, i0, nr);
         const int j = nrows / C - n;
-        (void)stage; (void)round;
-        int nrow0 = 0, ni0 = 0, nnr = 0;                         // the next tile: converted during this tile's B phase
-        if (n + 1 < n_seq) {
-            seq_rows(n + 1, nrow0, ni0, nnr);
-            mbar_wait(&raw_full[(n + 1) % NST], (uint32_t)(((n + 1) / NST) & 1));
-        }
+        mbar_wait(&e_full[n & 1], (uint32_t)((n >> 1) & 1));
         const unsigned char *er = ering + (size_t)(n & 1) * C * erow_bytes;
-        // ---- R phase: rows row0 .. row0 + nr - 1 of direction DR from checkpoint j (or the virtual start row)
-        int ER = 0;
-        if (j > 0) ER = load_row(ck_dir + (int64_t)j * p.ck_row, rb, rl); else start_row(DR, rb, rl);
-        // the live direction moves into this tile's scaling: live_hat = live_true * 2^(ER) / P
+        // ---- R phase: rows row0 .. row0 + nr - 1 of direction DR from checkpoint j (or the virtual start row);
+        //      the aligned copy of every row (blank state, and the label state the other direction pairs it with =
+        //      the carry this position receives) goes to my column of the tile
         {
-            const int s = n == 0 ? EL0 + ER - Ep : ER - prevER;
-            fixL = make_scale(s);
-            const double extra = n == 0 ? invPm : 1.0;
+            double rb[K], rl[K];
+            int ER = 0;
+            if (j > 0) ER = load_row(ck_dir + (int64_t)j * p.ck_row, rb, rl); else start_row(DR, rb, rl);
+            // the live direction moves into this tile's scaling: live_hat = live_true * 2^(ER) / P
+            {
+                const Scale2 sc = make_scale(n == 0 ? EL0 + ER - Ep : ER - prevER);
+                const double f1 = n == 0 ? sc.f1 * invPm : sc.f1;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                lb[k] = lb[k] * fixL.f1 * fixL.f2 * extra;
-                ll[k] = ll[k] * fixL.f1 * fixL.f2 * extra;
+                for (int k = 0; k < K; ++k) {
+                    lb[k] = lb[k] * f1 * sc.f2;
+                    ll[k] = ll[k] * f1 * sc.f2;
+                }
+                prevER = ER;
             }
-            fixL.f1 *= extra;
-            prevER = ER;
-        }
-        if (lane == outR) xR[parR * (MAXW + 2) + soR] = DR ? rl[0] : rl[K - 1];
-        named_bar_sync(1, nbar);
-        double Rb[C][K], Rc[C][K];
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            if (i < nr) {
-                const double xin = xR[parR * (MAXW + 2) + siR];
-                const double nb = DR ? __shfl_down_sync(FULL, rl[0], 1) : __shfl_up_sync(FULL, rl[K - 1], 1);
-                const double cin = lane == edgeR ? xin : nb;
-#pragma unroll
-                for (int k = 0; k < K; ++k) Rb[i][k] = rb[k];
-                if (i + 1 < nr) {
-                    const double eb = *reinterpret_cast<const double *>(er + (i + 1) * erow_bytes + eoff_blank);
-                    double el[K], pre_b[K], pre_l[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) el[k] = *reinterpret_cast<const double *>(er + (i + 1) * erow_bytes + eoffR[k]);
-                    if (DR) step<1>(rb, rl, eb, el, skR, cin, pre_b, pre_l, Rc[i]); else step<0>(rb, rl, eb, el, skR, cin, pre_b, pre_l, Rc[i]);
-                    if (lane == outR) xR[(parR ^ 1) * (MAXW + 2) + soR] = DR ? rl[0] : rl[K - 1];
-                    parR ^= 1;
-                    named_bar_sync(1, nbar);
-                } else {
-                    // last row of the tile: only its aligned copy (the carries the next step would have fetched)
-                    if (DR) {
-                        Rc[i][K - 1] = cin;
-#pragma unroll
-                        for (int k = K - 2; k >= 0; --k) Rc[i][k] = rl[k + 1];
+#pragma unroll 1
+            for (int i = 0; i < C; ++i) {
+                if (i < nr) {
+                    const double cin = carry_in(DR, rl);
+                    double *ti = tl + (size_t)i * 2 * K * 32;
+                    if (i + 1 < nr) {
+                        const unsigned char *erow = er + (i + 1) * erow_bytes;
+                        const double eb = *reinterpret_cast<const double *>(erow + eoff_blank);
+                        auto keep = [&](int k, double b_old, double carry, double, double) {
+                            ti[k * 32] = b_old;
+                            ti[(K + k) * 32] = carry;
+                        };
+                        if (DR) step<K, 1>(rb, rl, eb, erow, eoffR, sk, cin, keep);
+                        else step<K, 0>(rb, rl, eb, erow, eoffR, sk, cin, keep);
                     } else {
-                        Rc[i][0] = cin;
+                        // last row of the tile: only its aligned copy (the carries the next step would have fetched)
 #pragma unroll
-                        for (int k = 1; k < K; ++k) Rc[i][k] = rl[k - 1];
+                        for (int k = 0; k < K; ++k) {
+                            ti[k * 32] = rb[k];
+                            const double c = DR ? (k == K - 1 ? cin : rl[k + 1 < K ? k + 1 : k]) : (k == 0 ? cin : rl[k > 0 ? k - 1 : 0]);
+                            ti[(K + k) * 32] = c;
+                        }
                     }
                 }
             }
@@ -688,49 +664,37 @@ __global__ void __launch_bounds__(GRAD ? (MAXW + 1 + 4) * 32 : (MAXW + 1) * 32, 
         // ---- B phase: the live direction over the tile's rows, last row first
         if (n >= 2) mbar_wait(&post_empty[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
         const int pbuf = (n & 1) * C;
-        bool first_live = true;
-#pragma unroll
+#pragma unroll 1
         for (int i = C - 1; i >= 0; --i) {
-            if (i >= ni0 && i < nnr) convert_row(n + 1, i, nrow0);
             if (i >= i0 && i < nr) {
-                const double eb = *reinterpret_cast<const double *>(er + i * erow_bytes + eoff_blank);
-                double el[K], pre_b[K], pre_l[K], cs[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) el[k] = *reinterpret_cast<const double *>(er + i * erow_bytes + eoffL[k]);
-                double xin = xL[parL * (MAXW + 2) + siL];
-                if (first_live) xin = xin * fixL.f1 * fixL.f2;   // the seam value was published in the previous scaling
-                first_live = false;
-                const double nb = DL ? __shfl_down_sync(FULL, ll[0], 1) : __shfl_up_sync(FULL, ll[K - 1], 1);
-                const double cin = lane == edgeL ? xin : nb;
-                if (DL) step<1>(lb, ll, eb, el, skL, cin, pre_b, pre_l, cs); else step<0>(lb, ll, eb, el, skL, cin, pre_b, pre_l, cs);
-                if (lane == outL) xL[(parL ^ 1) * (MAXW + 2) + soL] = DL ? ll[0] : ll[K - 1];
-                parL ^= 1;
-                // posteriors of my states at this frame: (live state before its emission) x (recomputed state)
+                const unsigned char *erow = er + i * erow_bytes;
+                const double eb = *reinterpret_cast<const double *>(erow + eoff_blank);
+                const double *ti = tl + (size_t)i * 2 * K * 32;
                 float *wl = wlab + (pbuf + i) * WL;
                 float sbl = 0.f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    sbl += (float)(pre_b[k] * Rb[i][k]);
-                    wl[wl_off[k]] = (float)(pre_l[k] * Rc[i][k]);
-                }
+                // posteriors of my states at this frame: (live state before its emission) x (recomputed state)
+                auto post = [&](int k, double, double, double A, double t) {
+                    sbl += (float)(A * ti[k * 32]);
+                    wl[wl_off[k]] = (float)(t * ti[(K + k) * 32]);
+                };
+                const double cin = carry_in(DL, ll);
+                if (DL) step<K, 1>(lb, ll, eb, erow, eoffL, sk, cin, post);
+                else step<K, 0>(lb, ll, eb, erow, eoffL, sk, cin, post);
                 const unsigned fx = __float2uint_rn(fminf(sbl, 3.5f) * 1073741824.0f);
                 const unsigned tot = __reduce_add_sync(FULL, fx);
                 bad = bad || !(sbl <= 3.0e38f);                 // inf / NaN: the live direction left the range of fp64
                 __syncwarp();
                 if (lane == 0) {
-                    atomicAdd(&blank_acc[pbuf + i], tot);
+                    blank_acc[pbuf + i] = tot;
                     mbar_arrive(&post_full[pbuf + i]);
                 }
-                named_bar_sync(1, nbar);
             } else {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&post_full[pbuf + i]);   // unused slot of a partial tile: keep the phases in step
             }
         }
-        if (n + 1 < n_seq) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[(n + 1) % NST]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&e_empty[n & 1]);
     }
     if (__any_sync(FULL, bad) && lane == 0) atomicOr(&p.flags[b], 2);
 }
@@ -802,21 +766,37 @@ __global__ void __launch_bounds__(256) ctc_lin_join_kernel(const Params p) {
         if (badt) {
             p.nll[b] = QNAN;                                    // label outside the vocabulary (see ctc_join_kernel)
             p.nll2[b] = 0.0;
+            p.flags[b] = 0;                                     // (decided here: nothing to hand back)
         } else if (!feasible) {
             p.nll[b] = INF;
             p.nll2[b] = 0.0;
-        } else if (!(S > 0.0) || !(S < 1.0e300)) {
-            atomicOr(&p.flags[b], 1);                           // zero, inf or NaN: the log-domain kernels decide
-            p.nll[b] = QNAN;
-            p.nll2[b] = 0.0;
+            p.flags[b] = 0;
         } else {
-            const double l2 = log2(S);
-            // mismatch of the two frontiers, log2(alpha_max beta_max / P) at the join frame
-            const double mism = (double)(((HA >> 20) - 1023) + ((HB >> 20) - 1023)) - l2;
-            if (mism > 1000.0) atomicOr(&p.flags[b], 1);
-            const double logp2 = l2 + Ea + Eb;
-            p.nll[b] = (float)(-logp2 * 0.6931471805599453);
-            p.nll2[b] = -logp2;
+            bool hand_back = (p.flags[b] & 1) != 0;             // set by the forward kernel (emission range, inf / NaN)
+            if (!(S > 0.0) || !(S < 1.0e300)) {
+                hand_back = true;                               // zero, inf or NaN: the log-domain kernels decide
+                p.nll[b] = QNAN;
+                p.nll2[b] = 0.0;
+            } else {
+                const double l2 = log2(S);
+                // mismatch of the two frontiers, log2(alpha_max beta_max / P) at the join frame
+                const double mism = (double)(((HA >> 20) - 1023) + ((HB >> 20) - 1023)) - l2;
+                if (mism > 1000.0) hand_back = true;
+                const double logp2 = l2 + Ea + Eb;
+                p.nll[b] = (float)(-logp2 * 0.6931471805599453);
+                p.nll2[b] = -logp2;
+            }
+            if (hand_back) {
+                // a row block for the log-domain kernels' stored half lattices; none left: NaN likelihood (loud)
+                const int sl = atomicAdd(p.slot_counter, 1);
+                if (sl < p.n_slots) {
+                    p.slot[b] = sl;
+                    p.flags[b] = 1;
+                } else {
+                    p.flags[b] = 4;                             // neither path owns it: the backward fills NaN
+                    p.nll[b] = QNAN;
+                }
+            }
         }
     }
 }

@@ -98,6 +98,8 @@ struct CtcParams {
     int NCH;        // table slots per (utterance, direction): one per forward chunk, the last one for the frontier
     float *nll;     // [B] out / in
     int *abort_word;  // 0 until a seam poll of the wavefront forward gave up (watchdog); then every nll of the call is NaN
+    const int *slot;  // [B] or nullptr: row block of utterance b in `rows` (linear-domain mode: only the utterances handed
+                      // back get one, see ctc_lin.cuh); nullptr: block b
     const int *mask;  // [B] or nullptr: when set, only the utterances with bit 0 set are processed (the ones the linear-domain
                       // kernels of ctc_lin.cuh handed back, see there)
     int *nan_flag;    // [B] set by the forward kernels when an emission the lattice uses is NaN (fmax-based log-sum-exp
@@ -206,7 +208,6 @@ ctc_lattice_kernel(const CtcParams p) {
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (backward in time)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = c.W;
-    const bool compute = warp < W;
     constexpr int NPROD = GRAD ? 2 : 1;  // producer warps
     const bool producer = warp >= W && warp < W + NPROD;
     const int PW = (GRAD && SPLIT) ? c.PW : 0;           // posterior warps (0: the recursion warps do it)
@@ -222,6 +223,9 @@ ctc_lattice_kernel(const CtcParams p) {
     int L = p.tgt_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int m = Tb >> 1;
+    // recursion warps (and their posterior warps) whose 32K pairs all lie beyond pair L of THIS utterance have
+    // nothing to compute: they leave before the time loop, the barriers below count the live ones only
+    const int wl = (L / (32 * K) + 1) < W ? (L / (32 * K) + 1) : W;
     const int n1 = dir ? Tb - m : m;        // frames this direction owns in forward()
     const int tau0 = GRAD ? n1 : 0;         // first direction-local step of this launch
     const int nsteps = GRAD ? Tb - n1 : n1;
@@ -232,6 +236,8 @@ ctc_lattice_kernel(const CtcParams p) {
     const int32_t *tg = p.targets + p.tgt_off[b];
     const int t_first = dir ? Tb - 1 - tau0 : tau0;  // frame of step 0
     const int dt = dir ? -1 : 1;
+    const bool compute = warp < wl;
+    const bool dead = (warp < W && warp >= wl) || (is_post && rw >= wl);
 
     uint64_t *em_full = reinterpret_cast<uint64_t *>(smem + kBarEmFull);
     uint64_t *em_empty = reinterpret_cast<uint64_t *>(smem + kBarEmEmpty);
@@ -290,7 +296,7 @@ ctc_lattice_kernel(const CtcParams p) {
     }
 
     const int n_consumers = W + (GRAD ? c.G : 0) + PW;   // every warp but the producers
-    const int n_em = W + (GRAD ? c.G : 0);               // warps that read the emission ring
+    const int n_em = wl + (GRAD ? c.G : 0);              // warps that read the emission ring
     if (tid == 0) {
         for (int s = 0; s < c.stages; ++s) {
             mbar_init(&em_full[s], 1);
@@ -298,11 +304,11 @@ ctc_lattice_kernel(const CtcParams p) {
         }
         for (int s = 0; s < c.or_stages; ++s) {
             mbar_init(&or_full[s], 1);
-            mbar_init(&or_empty[s], W);
+            mbar_init(&or_empty[s], wl);
         }
         if (GRAD) {
             for (int s = 0; s < 2 * CH; ++s) {
-                mbar_init(&post_full[s], W);
+                mbar_init(&post_full[s], wl);
                 blank_acc[s] = 0u;
             }
             mbar_init(&post_empty[0], c.G);
@@ -476,7 +482,7 @@ ctc_lattice_kernel(const CtcParams p) {
             const int Co = c.or_chunk, No = c.or_stages;
             const int or_nchunks = (nsteps + Co - 1) / Co;
             int or_stage = 0, or_round = 0, or_left = nsteps;
-            const float *or_src = p.rows + ((int64_t)b * p.T + t_first) * row_elems;
+            const float *or_src = p.rows + ((int64_t)(p.slot ? p.slot[b] : b) * p.T + t_first) * row_elems;
             const int64_t or_step = (int64_t)dt * row_elems;
             for (int n = 0; n < or_nchunks; ++n) {
                 if (or_round > 0) mbar_wait(&or_empty[or_stage], (uint32_t)((or_round - 1) & 1));
@@ -496,7 +502,7 @@ ctc_lattice_kernel(const CtcParams p) {
     }
 
     // ================= recursion and gradient warps ==========================================
-    const int nbar = W * 32;  // the per-frame barrier is among the recursion warps only
+    const int nbar = wl * 32;  // the per-frame barrier is among the live recursion warps only
     const int slot_bytes = c.slot_bytes;
     const unsigned char *em_base = ring.slots;
     const int Co = c.or_chunk, No = c.or_stages, or_nslots = Co * No;
@@ -521,7 +527,9 @@ ctc_lattice_kernel(const CtcParams p) {
         return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
     };
 
-    if (compute) {
+    if (dead) {
+        // nothing: straight to the common tail (frames beyond the utterance)
+    } else if (compute) {
         // ---------------- recursion warps: chunk-unrolled time loop ----------------
         auto run = [&](auto dir_tag) {
             constexpr int DIR = decltype(dir_tag)::value;
@@ -533,7 +541,7 @@ ctc_lattice_kernel(const CtcParams p) {
             // row pointers: pair (pbase + 32k) -> blank at [pbase+32k], label at [P_pad+1-DIR+pbase+32k]
             const bool save = !GRAD && p.rows != nullptr;
             const int lab_delta = P_pad + 1 - DIR;
-            float *sb = save ? p.rows + ((int64_t)b * p.T + t_first) * row_elems + pbase : nullptr;  // my blank states
+            float *sb = save ? p.rows + ((int64_t)(p.slot ? p.slot[b] : b) * p.T + t_first) * row_elems + pbase : nullptr;  // my blank states
             float *sl = sb + lab_delta;                                                                // my label states
             double *soff = reinterpret_cast<double *>(sb - pbase + 2 * P_pad + 2);                    // the row's offset
             const unsigned char *or_row = or_slots;
@@ -678,7 +686,7 @@ ctc_lattice_kernel(const CtcParams p) {
                 if (!first_chunk) {
                     // re-centre on the row maximum published at the end of the previous chunk
                     float mx = wmax[0];
-                    for (int w = 1; w < W; ++w) mx = fmaxf(mx, wmax[w]);
+                    for (int w = 1; w < wl; ++w) mx = fmaxf(mx, wmax[w]);
                     mx = floorf(mx);  // integer amounts: the subtraction is exact, every stored offset an integer
                     if (mx > kNegTest) {
 #pragma unroll
@@ -931,7 +939,7 @@ ctc_lattice_kernel(const CtcParams p) {
             }
         }
     } else if (dir == 0) {
-        const int nthr = n_consumers * 32, me = compute ? tid : tid - 32 * NPROD;  // every warp but the producers
+        const int nthr = n_consumers * 32, me = warp < W ? tid : tid - 32 * NPROD;  // every warp but the producers
         for (int t = Tb; t < (int)p.T; ++t) {  // frames beyond the utterance: exact zeros
             float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
             for (int cc = me; cc < V; cc += nthr) g[cc] = 0.f;
@@ -1092,7 +1100,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
     const int blank_off = 4 * p.blank;
     const unsigned a15_0 = (unsigned)(reinterpret_cast<uintptr_t>(first_row) & 15);
     const unsigned a15_step = (unsigned)((step_elems * 4) & 15);
-    float *row_out = SAVE ? p.rows + ((int64_t)b * p.T + t_first) * row_elems : nullptr;
+    float *row_out = SAVE ? p.rows + ((int64_t)(p.slot ? p.slot[b] : b) * p.T + t_first) * row_elems : nullptr;
     const int64_t row_step = (int64_t)dt * row_elems;
     const unsigned char *em_base = ring.slots, *em_chunk = em_base;
     int em_stage = 0, em_phase = 0, remaining = nsteps, sslot = 0, step0 = 0;
@@ -1567,13 +1575,21 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
-// Linear-domain kernels (ctc_lin.cuh): used when the longest target fits 8 recursion warps of 64 positions.
-// SSAK_CTC_LINEAR=0 switches them off (everything then runs in the log domain).
+// Linear-domain kernels (ctc_lin.cuh): used when the longest target fits one warp at <= 16 positions per lane.
+// Opt-in (SSAK_CTC_LINEAR=1): exact to fp64 rounding and free of the stored lattice, but measured slower than the
+// log-domain kernels on B200 (one recursion warp per direction issues ~0.3 instructions per cycle).
 static bool lin_eligible(int64_t Lmax) {
-    return Lmax + 1 <= 32 * lin::K * lin::MAXW && env_int("SSAK_CTC_LINEAR", 1) != 0;
+    return Lmax + 1 <= 32 * lin::MAXK && env_int("SSAK_CTC_LINEAR", 0) != 0;
 }
+// row blocks kept for utterances the linear-domain kernels hand back to the log-domain ones (fp64 range, see
+// ctc_lin.cuh): every utterance of a small batch, 1/8 of a large one (beyond: NaN likelihood, loud)
+static inline int64_t lin_slots(int64_t B) { return B <= 32 ? B : std::max<int64_t>(32, B / 8); }
 static inline int lin_nck(int64_t T) { return (int)((T / 2 + 1) / lin::C) + 2; }
-static inline int lin_ppad(int64_t Lmax) { return (int)((Lmax + 1 + 32 * lin::K - 1) / (32 * lin::K)) * 32 * lin::K; }
+static inline int lin_k(int64_t Lmax) {   // positions per lane: the instantiated size that covers Lmax + 1 positions
+    const int need = (int)((Lmax + 1 + 31) / 32);
+    return need <= 4 ? 4 : (need <= 7 ? 7 : (need <= 10 ? 10 : (need <= 13 ? 13 : 16)));
+}
+static inline int lin_ppad(int64_t Lmax) { return 32 * lin_k(Lmax); }
 
 struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, lin_fr, lin_ck, rows, total; };
 static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
@@ -1581,8 +1597,9 @@ static WsLayout ws_layout(int64_t T, int64_t B, int64_t Lmax, int row_elems, boo
     WsLayout w;
     size_t o = 0;
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
-    // abort word, then nan_flag[B], then the linear-domain kernels' flags[B]: one memset
-    w.abort_word = o; o += 256 + 2 * align_up((size_t)B * sizeof(int), 256);
+    // abort word (+ the slot counter of the linear-domain mode at +4), then nan_flag[B], then the linear-domain
+    // kernels' flags[B] and slot[B]: one memset
+    w.abort_word = o; o += 256 + 3 * align_up((size_t)B * sizeof(int), 256);
     w.lin_fr = w.lin_ck = o;
     if (lin_eligible(Lmax)) {
         const size_t ck_row = 2 * (size_t)lin_ppad(Lmax) + 2;
@@ -1593,7 +1610,9 @@ static WsLayout ws_layout(int64_t T, int64_t B, int64_t Lmax, int row_elems, boo
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
     w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
     w.tabs = o;   o += align_up((size_t)B * 2 * tab_slots(T) * 16 * sizeof(float), 256);
-    w.rows = o;   if (saved) o += align_up((size_t)B * (size_t)T * row_elems * sizeof(float), 256);
+    // log-domain half lattices: one row block per utterance -- in the linear-domain mode only for the few utterances
+    // that may be handed back (lin_slots)
+    w.rows = o;   if (saved) o += align_up((size_t)(lin_eligible(Lmax) ? lin_slots(B) : B) * (size_t)T * row_elems * sizeof(float), 256);
     w.total = o + 256;
     return w;
 }
@@ -1624,6 +1643,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->abort_word = reinterpret_cast<int *>(ws + w.abort_word);
     p->nan_flag = reinterpret_cast<int *>(ws + w.abort_word + 256);
     p->mask = nullptr;
+    p->slot = nullptr;
     p->NCH = tab_slots(T);
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
     p->zero_inf = 0;
@@ -1649,45 +1669,52 @@ static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin::Par
     q->lp = p.lp; q->T = p.T; q->B = p.B; q->V = p.V; q->st = p.st; q->sb = p.sb;
     q->targets = p.targets; q->tgt_off = p.tgt_off; q->in_len = p.in_len; q->tgt_len = p.tgt_len;
     q->Lmax = p.Lmax; q->blank = p.blank; q->zl = p.zl;
-    q->P_pad = lin_ppad(p.Lmax);
-    q->W = q->P_pad / (32 * lin::K);
+    q->K = lin_k(p.Lmax);
+    q->P_pad = 32 * q->K;
     q->ck_row = 2 * q->P_pad + 2;
     q->NCK = lin_nck(p.T);
     q->fr = reinterpret_cast<double *>(ws + w.lin_fr);
     q->ck = reinterpret_cast<double *>(ws + w.lin_ck);
     q->nll2 = p.nll2; q->nll = p.nll;
     q->flags = reinterpret_cast<int *>(ws + w.abort_word + 256 + align_up((size_t)p.B * sizeof(int), 256));
-    q->nan_flag = p.nan_flag;
+    q->slot = reinterpret_cast<int *>(ws + w.abort_word + 256 + 2 * align_up((size_t)p.B * sizeof(int), 256));
+    q->slot_counter = reinterpret_cast<int *>(ws + w.abort_word + 4);
+    q->n_slots = (int)lin_slots(p.B);
     q->grad_out = p.grad_out; q->grad = p.grad; q->gst = p.gst; q->gsb = p.gsb; q->zero_inf = p.zero_inf;
     q->save = saved ? 1 : 0;
-    q->G = 4;
-    q->NST = 3;
+    q->G = 2;
     q->slot_bytes = ring_slot_bytes(p.V);
     q->ncol_max = (int)std::min<int64_t>(p.V, (int64_t)p.Lmax + 1);
     q->erow_bytes = 8 * (q->ncol_max + 1);
-    *smem_fwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, false).total;
-    *smem_bwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, true).total;
-    if (*smem_bwd > (size_t)kMaxDynSmem) {   // large vocabulary: two ring stages
-        q->NST = 2;
-        *smem_fwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, false).total;
-        *smem_bwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->P_pad, true).total;
+    // raw-row ring: as deep as fits next to two resident CTAs per SM (small vocabularies: 4 stages)
+    for (q->NST = 4; q->NST >= 2; --q->NST) {
+        *smem_fwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->K, false).total;
+        *smem_bwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->K, true).total;
+        if (*smem_bwd <= (size_t)(q->NST > 2 ? 110 * 1024 : kMaxDynSmem)) break;
     }
-    return *smem_bwd <= (size_t)kMaxDynSmem;
+    return q->NST >= 2 && *smem_bwd <= (size_t)kMaxDynSmem;
 }
 
 template <bool GRAD>
 static int launch_lin(const lin::Params &q, size_t smem_bytes, cudaStream_t s) {
-    dim3 grid((unsigned)q.B, 2), block((q.W + 1 + (GRAD ? q.G : 0)) * 32);
-    cudaError_t e;
-    if (q.zl) {
-        e = ensure_max_smem<lin::ctc_lin_kernel<GRAD, true>>();
-        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
-        lin::ctc_lin_kernel<GRAD, true><<<grid, block, smem_bytes, s>>>(q);
-    } else {
-        e = ensure_max_smem<lin::ctc_lin_kernel<GRAD, false>>();
-        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
-        lin::ctc_lin_kernel<GRAD, false><<<grid, block, smem_bytes, s>>>(q);
+    dim3 grid((unsigned)q.B, 2), block((2 + (GRAD ? q.G : 0)) * 32);
+#define SSAK_LIN2(KK, ZZ)                                                                      \
+    {                                                                                          \
+        cudaError_t e = ensure_max_smem<lin::ctc_lin_kernel<KK, GRAD, ZZ>>();                  \
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
+        lin::ctc_lin_kernel<KK, GRAD, ZZ><<<grid, block, smem_bytes, s>>>(q);                  \
     }
+#define SSAK_LIN(KK) case KK: if (q.zl) SSAK_LIN2(KK, true) else SSAK_LIN2(KK, false) break;
+    switch (q.K) {
+        SSAK_LIN(4)
+        SSAK_LIN(7)
+        SSAK_LIN(10)
+        SSAK_LIN(13)
+        SSAK_LIN(16)
+        default: return SSAK_ERR_UNSUPPORTED;
+    }
+#undef SSAK_LIN
+#undef SSAK_LIN2
     return check_launch();
 }
 
@@ -1719,7 +1746,7 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         if (rc != SSAK_OK) return rc;
     }
     {
-        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + 2 * align_up((size_t)B * sizeof(int), 256), s);
+        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + 3 * align_up((size_t)B * sizeof(int), 256), s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
     }
     // Linear-domain kernels first (no stored lattice); the utterances they hand back (flags, see ctc_lin.cuh) are
@@ -1733,6 +1760,7 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         rc = check_launch();
         if (rc != SSAK_OK) return rc;
         p.mask = q.flags;
+        p.slot = q.slot;
     }
     rc = launch_forward_wave(p, s);
     if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
@@ -1762,6 +1790,7 @@ static int backward_impl(const float *grad_out, const float *x, int64_t T, int64
         rc = launch_lin<true>(q, smem_b, s);
         if (rc != SSAK_OK) return rc;
         p.mask = q.flags;
+        p.slot = q.slot;
     }
     return launch_lattice<true>(p, s);
 }

@@ -185,7 +185,7 @@ def run_reference(args, rank):
 def time_kernels(lib, dev, lp_d, tg32, off, il32, tl32, Lmax, iters, flush, logits=False):
     """CUDA-event time of the forward launch group and of the backward launch group, separately."""
     T, B, V = lp_d.shape
-    ws_bytes = lib.ssak_ctc_loss_workspace_bytes(T, B, Lmax, 1)
+    ws_bytes = lib.ssak_ctc_loss_workspace_bytes_v(T, B, V, Lmax, 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     nll = torch.empty(B, dtype=torch.float32, device=dev)
     go = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
@@ -415,7 +415,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": loss_roofline(name, V, int(il.sum()), t_fwd, t_bwd, hbm, hbm_src, ws_bytes),
             "clocks": sampler.summary(),
         }
-        out["gpu_launches"] = launches_per_step(lib) * len(dev_b) * args.steps
+        out["gpu_launches"] = sum(launches_per_step(lib, x.shape[1], V, int(t.max())) for x, _, _, t in dev_b) * args.steps
         if world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             slp, stg, sil, stl, scells, sn = cpu_sample(name, lp, tg, il, tl)
@@ -436,12 +436,9 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(out))
 
 
-def launches_per_step(lib):
-    """Kernels of ours per loss call (forward group + backward group), as the library reports them."""
-    try:
-        return int(lib.ssak_ctc_loss_launches_per_step())
-    except AttributeError:
-        return 4     # lattice fwd, join, reduce, lattice bwd
+def launches_per_step(lib, B, V, Lmax):
+    """Kernels of ours per loss call (forward group + backward group + the reduction), as the library reports them."""
+    return int(lib.ssak_ctc_loss_launches(B, V, Lmax, 0)) + 1
 
 
 def _timed_ms(fn, flush, n=7, warm=3):

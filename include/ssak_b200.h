@@ -80,6 +80,20 @@ SSAK_API int ssak_b200_last_cuda_error(void);
 /* Workspace size for forward(+backward).  save_for_backward == 0: join rows only. */
 SSAK_API size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t max_target_len,
                                               int save_for_backward);
+/* The same with the vocabulary size known.  For V <= 128, max_target_len <= 415 and batches that fill the GPU
+ * (B >= 2 x SM count) the throughput kernels run (one warp per utterance and direction, no stored lattice:
+ * checkpoints every 4 frames), and the workspace is ~3x smaller than what the V-agnostic query above must reserve.
+ * Either size is accepted by forward / backward. */
+SSAK_API size_t ssak_ctc_loss_workspace_bytes_v(int64_t T, int64_t B, int64_t V, int64_t max_target_len,
+                                                int save_for_backward);
+/* Diagnostics: which kernel family computed each utterance in the last forward (+ backward) call on this workspace:
+ * flags_out[b] (device, int32) = 0: throughput kernels; bit 0: recomputed by the log-domain kernels since forward();
+ * bit 1: since backward() (the throughput kernels' self-check failed); bit 2: nobody (NaN). */
+SSAK_API int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_t B, int64_t V, int64_t max_target_len,
+                                      int32_t save_for_backward, int32_t *flags_out, ssak_stream_t stream);
+/* Kernels of this library launched by one forward + backward pair of calls on such a shape (bookkeeping for
+ * benchmarks; logits != 0: the ssak_ctc_logits_* pair). */
+SSAK_API int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len, int32_t logits);
 
 /* 1 when the loss kernels cover the shape, else 0 (max_target_len > 4095, T > 300000, or rows of V floats that do
  * not fit the shared-memory emission ring: V > ~2040).  A caller that replaces a generic operator

@@ -18,6 +18,9 @@ SIGNATURES = {
     "ssak_b200_strerror": (C.c_char_p, [C.c_int]),
     "ssak_b200_last_cuda_error": (C.c_int, []),
     "ssak_ctc_loss_workspace_bytes": (_sz, [_i64, _i64, _i64, C.c_int]),
+    "ssak_ctc_loss_workspace_bytes_v": (_sz, [_i64, _i64, _i64, _i64, C.c_int]),
+    "ssak_ctc_loss_launches": (C.c_int, [_i64, _i64, _i64, _i32]),
+    "ssak_ctc_loss_path_flags": (C.c_int, [_p, _i64, _i64, _i64, _i64, _i32, _p, _p]),
     "ssak_ctc_loss_supported": (C.c_int, [_i64, _i64, _i64, _i64]),
     "ssak_ctc_loss_forward": (C.c_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i32, _i32,
                                         _p, _p, _sz, _p]),

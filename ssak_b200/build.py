@@ -14,10 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libssak_b200.so")
-SOURCES = ["capi.cu", "ctc_loss.cu", "ctc_align.cu", "ctc_greedy.cu", "host_api.cu"]
+SOURCES = ["capi.cu", "ctc_loss.cu", "ctc_lin32.cu", "ctc_align.cu", "ctc_greedy.cu", "host_api.cu"]
 # per-file extra flags: the aligner must reproduce the reference's fp32 add/max sequence bit for
 # bit, so FMA contraction is disabled there (it has no multiplications, this is insurance).
-EXTRA = {"ctc_align.cu": ["-fmad=false"]}
+# The block-floating-point loss kernels flush denormals (their self-check relies on a clean flush threshold).
+EXTRA = {"ctc_align.cu": ["-fmad=false"], "ctc_lin32.cu": ["-ftz=true"]}
 BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", INCLUDE]
 

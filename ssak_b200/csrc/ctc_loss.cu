@@ -50,6 +50,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "ctc_lin32.h"
 
 namespace ssak {
 
@@ -98,10 +99,12 @@ struct CtcParams {
     int NCH;        // table slots per (utterance, direction): one per forward chunk, the last one for the frontier
     float *nll;     // [B] out / in
     int *abort_word;  // 0 until a seam poll of the wavefront forward gave up (watchdog); then every nll of the call is NaN
-    const int *slot;  // [B] or nullptr: row block of utterance b in `rows` (linear-domain mode: only the utterances handed
-                      // back get one, see ctc_lin.cuh); nullptr: block b
-    const int *mask;  // [B] or nullptr: when set, only the utterances with bit 0 set are processed (the ones the linear-domain
-                      // kernels of ctc_lin.cuh handed back, see there)
+    const int *slot;  // [B] or nullptr: row block of utterance b in `rows` (throughput mode: only the utterances handed
+                      // back get one, see ctc_lin32.cu); nullptr: block b
+    const int *mask;  // [B] or nullptr: when set, only the utterances with one of `mask_bits` set (and bit 2 clear) are
+                      // processed: the ones the throughput kernels of ctc_lin32.cu handed back (flags, see there)
+    int mask_bits;
+    int join_keeps_nll;   // the join kernel leaves nll[b] alone (backward-time recomputation: nll is the caller's input)
     int *nan_flag;    // [B] set by the forward kernels when an emission the lattice uses is NaN (fmax-based log-sum-exp
                       // would swallow it): the join kernel then returns a NaN likelihood, as torch does
     const float *grad_out;
@@ -217,7 +220,23 @@ ctc_lattice_kernel(const CtcParams p) {
     const int rw = is_post ? warp - post0 : warp;        // the recursion warp whose state group this warp handles
     const unsigned FULL = 0xffffffffu;
 
-    if (p.mask && !(p.mask[b] & 1)) return;
+    if (p.mask) {
+        const int fl = p.mask[b];
+        if (GRAD && (fl & 4)) {
+            // handed back, but no row block was left: nobody computed this utterance -- NaN gradient (loud)
+            if (dir == 0) {
+                int Tn = p.in_len[b];
+                Tn = Tn < 0 ? 0 : (Tn > (int)p.T ? (int)p.T : Tn);
+                for (int t = 0; t < (int)p.T; ++t) {
+                    float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
+                    const float v = t < Tn ? __int_as_float(0x7fc00000) : 0.f;
+                    for (int cc = tid; cc < p.V; cc += blockDim.x) g[cc] = v;
+                }
+            }
+            return;
+        }
+        if (!(fl & p.mask_bits) || (fl & 4)) return;
+    }
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[b];
@@ -992,7 +1011,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
     const int W = wc.W;
     const float EMPTY = __uint_as_float(kSeamEmptyBits);
 
-    if (p.mask && !(p.mask[b] & 1)) return;
+    if (p.mask && (!(p.mask[b] & p.mask_bits) || (p.mask[b] & 4))) return;
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[b];
@@ -1285,7 +1304,7 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
 __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     __shared__ float red_m[8], red_s[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (p.mask && !(p.mask[b] & 1)) return;
+    if (p.mask && (!(p.mask[b] & p.mask_bits) || (p.mask[b] & 4))) return;
     int L = p.tgt_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int P_pad = p.cfg.P_pad, row_elems = p.cfg.row_elems;
@@ -1350,7 +1369,8 @@ __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
         const double off_b = *reinterpret_cast<const double *>(fb + 2 * P_pad + 2);
         const double logp2 = (double)M + (double)log2f(S) + off_a + off_b + (double)Da + (double)Db;
         if ((p.abort_word && *p.abort_word != 0) || p.nan_flag[b] != 0) bad = 1;
-        p.nll[b] = bad ? __int_as_float(0x7fc00000) : (dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453));
+        if (!p.join_keeps_nll)
+            p.nll[b] = bad ? __int_as_float(0x7fc00000) : (dead ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453));
         p.nll2[b] = -logp2;
     }
 }
@@ -1487,9 +1507,6 @@ __global__ void ctc_shard_grad_scale_kernel(const float *gscale, const float *gr
     if (b < B) out[b] = gscale[b] * (grad_loss[0] * inv_den[0]);
 }
 
-}  // namespace ssak
-#include "ctc_lin.cuh"
-namespace ssak {
 
 // ---------------------------------------------------------------------------- launchers
 template <bool GRAD>
@@ -1575,44 +1592,46 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     return check_launch();
 }
 
-// Linear-domain kernels (ctc_lin.cuh): used when the longest target fits one warp at <= 16 positions per lane.
-// Opt-in (SSAK_CTC_LINEAR=1): exact to fp64 rounding and free of the stored lattice, but measured slower than the
-// log-domain kernels on B200 (one recursion warp per direction issues ~0.3 instructions per cycle).
-static bool lin_eligible(int64_t Lmax) {
-    return Lmax + 1 <= 32 * lin::MAXK && env_int("SSAK_CTC_LINEAR", 0) != 0;
+// Throughput kernels (ctc_lin32.cu: one warp per (utterance, direction), linear domain, block floating point, no
+// stored lattice): used when they cover the shape (V <= 128, targets up to 415 labels) AND the batch fills the GPU --
+// a chain is one warp, so below ~2 chains per SM sub-partition the latency-tuned log-domain kernels (several warps
+// per utterance) are faster (B = 64: 0.42 vs 1.1 ms; B = 256 ragged: 1.15 vs ~1.05 ms; B = 1024: 4.1 vs 2.8 ms).
+// SSAK_CTC_LIN32=1 forces them wherever they are valid, =0 disables them.
+static int lin_k(int64_t Lmax, int64_t V, int64_t B) {
+    const int mode = env_int("SSAK_CTC_LIN32", -1);
+    if (mode == 0) return 0;
+    if (mode < 0 && B < 2 * (int64_t)device_sm_count()) return 0;
+    return lin32::lanes_k(Lmax, V);
 }
-// row blocks kept for utterances the linear-domain kernels hand back to the log-domain ones (fp64 range, see
-// ctc_lin.cuh): every utterance of a small batch, 1/8 of a large one (beyond: NaN likelihood, loud)
+// row blocks kept for utterances the throughput kernels hand back to the log-domain ones (fp32 range, see
+// ctc_lin32.cu): every utterance of a small batch, 1/8 of a large one (beyond: NaN likelihood / gradient, loud)
 static inline int64_t lin_slots(int64_t B) { return B <= 32 ? B : std::max<int64_t>(32, B / 8); }
-static inline int lin_nck(int64_t T) { return (int)((T / 2 + 1) / lin::C) + 2; }
-static inline int lin_k(int64_t Lmax) {   // positions per lane: the instantiated size that covers Lmax + 1 positions
-    const int need = (int)((Lmax + 1 + 31) / 32);
-    return need <= 4 ? 4 : (need <= 7 ? 7 : (need <= 10 ? 10 : (need <= 13 ? 13 : 16)));
-}
-static inline int lin_ppad(int64_t Lmax) { return 32 * lin_k(Lmax); }
 
 struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, lin_fr, lin_ck, rows, total; };
 static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
-static WsLayout ws_layout(int64_t T, int64_t B, int64_t Lmax, int row_elems, bool saved) {
+// V < 0: the vocabulary is not known (ssak_ctc_loss_workspace_bytes): room for either kernel family
+static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row_elems, bool saved) {
     WsLayout w;
     size_t o = 0;
+    const int K = lin_k(Lmax, V < 0 ? 1 : V, B);
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
-    // abort word (+ the slot counter of the linear-domain mode at +4), then nan_flag[B], then the linear-domain
-    // kernels' flags[B] and slot[B]: one memset
+    // abort word (+ the slot counter of the throughput mode at +4), then nan_flag[B], then the throughput kernels'
+    // flags[B] and slot[B]: one memset
     w.abort_word = o; o += 256 + 3 * align_up((size_t)B * sizeof(int), 256);
     w.lin_fr = w.lin_ck = o;
-    if (lin_eligible(Lmax)) {
-        const size_t ck_row = 2 * (size_t)lin_ppad(Lmax) + 2;
-        w.lin_fr = o; o += align_up((size_t)B * 2 * ck_row * sizeof(double), 256);
+    if (K > 0) {
+        const size_t ck_row = (size_t)lin32::ck_row_elems(K);
+        w.lin_fr = o; o += align_up((size_t)B * 2 * ck_row * sizeof(float), 256);
         w.lin_ck = o;
-        if (saved) o += align_up((size_t)B * 2 * lin_nck(T) * ck_row * sizeof(double), 256);
+        if (saved) o += align_up((size_t)B * 2 * lin32::n_checkpoints(T) * ck_row * sizeof(float), 256);
     }
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
     w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
     w.tabs = o;   o += align_up((size_t)B * 2 * tab_slots(T) * 16 * sizeof(float), 256);
-    // log-domain half lattices: one row block per utterance -- in the linear-domain mode only for the few utterances
+    // log-domain half lattices: one row block per utterance -- in the throughput mode only for the few utterances
     // that may be handed back (lin_slots)
-    w.rows = o;   if (saved) o += align_up((size_t)(lin_eligible(Lmax) ? lin_slots(B) : B) * (size_t)T * row_elems * sizeof(float), 256);
+    const int64_t blocks = (K > 0 && V >= 0) ? lin_slots(B) : B;
+    w.rows = o;   if (saved) o += align_up((size_t)blocks * (size_t)T * row_elems * sizeof(float), 256);
     w.total = o + 256;
     return w;
 }
@@ -1629,7 +1648,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     if (T > 300000) return SSAK_ERR_UNSUPPORTED;  // re-centring offsets are kept exact as fp32 integers (< 2^24)
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     if (!choose_cfg(Lmax, B, (int)V, &p->cfg)) return SSAK_ERR_UNSUPPORTED;
-    const WsLayout w = ws_layout(T, B, Lmax, p->cfg.row_elems, saved);
+    const WsLayout w = ws_layout(T, B, V, Lmax, p->cfg.row_elems, saved);
     if (workspace_bytes < w.total) return SSAK_ERR_WORKSPACE;
     p->lp = log_probs; p->T = T; p->B = B; p->V = (int)V; p->st = st; p->sb = sb;
     p->targets = targets; p->tgt_off = tgt_off; p->in_len = in_len; p->tgt_len = tgt_len;
@@ -1643,6 +1662,8 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->abort_word = reinterpret_cast<int *>(ws + w.abort_word);
     p->nan_flag = reinterpret_cast<int *>(ws + w.abort_word + 256);
     p->mask = nullptr;
+    p->mask_bits = 1;
+    p->join_keeps_nll = 0;
     p->slot = nullptr;
     p->NCH = tab_slots(T);
     p->nll = nullptr; p->grad_out = nullptr; p->grad = nullptr; p->gst = p->gsb = 0;
@@ -1658,64 +1679,42 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
                                                 int save_for_backward) {
     CtcCfg c;
     if (T < 0 || T > 300000 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
-    return ws_layout(T, B, max_target_len, c.row_elems, save_for_backward != 0).total;
+    return ws_layout(T, B, -1, max_target_len, c.row_elems, save_for_backward != 0).total;
 }
 
-// Fill the parameters of the linear-domain kernels from the log-domain ones (same problem, same workspace).
-static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin::Params *q, size_t *smem_fwd, size_t *smem_bwd) {
-    if (!lin_eligible(p.Lmax)) return false;
-    const WsLayout w = ws_layout(p.T, p.B, p.Lmax, p.cfg.row_elems, saved);
+/* The same with the vocabulary size known: the throughput kernels (V <= 128, targets up to 415 labels) keep
+ * checkpoints instead of half lattices, ~8x less workspace. */
+extern "C" size_t ssak_ctc_loss_workspace_bytes_v(int64_t T, int64_t B, int64_t V, int64_t max_target_len,
+                                                  int save_for_backward) {
+    CtcCfg c;
+    if (T < 0 || T > 300000 || B <= 0 || V <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, (int)V, &c))
+        return 0;
+    return ws_layout(T, B, V, max_target_len, c.row_elems, save_for_backward != 0).total;
+}
+
+// Fill the parameters of the throughput kernels from the log-domain ones (same problem, same workspace).
+static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin32::Params *q) {
+    const int K = lin_k(p.Lmax, p.V, p.B);
+    if (K == 0) return false;
+    const WsLayout w = ws_layout(p.T, p.B, p.V, p.Lmax, p.cfg.row_elems, saved);
     char *ws = reinterpret_cast<char *>(workspace);
     q->lp = p.lp; q->T = p.T; q->B = p.B; q->V = p.V; q->st = p.st; q->sb = p.sb;
     q->targets = p.targets; q->tgt_off = p.tgt_off; q->in_len = p.in_len; q->tgt_len = p.tgt_len;
     q->Lmax = p.Lmax; q->blank = p.blank; q->zl = p.zl;
-    q->K = lin_k(p.Lmax);
-    q->P_pad = 32 * q->K;
-    q->ck_row = 2 * q->P_pad + 2;
-    q->NCK = lin_nck(p.T);
-    q->fr = reinterpret_cast<double *>(ws + w.lin_fr);
-    q->ck = reinterpret_cast<double *>(ws + w.lin_ck);
+    q->K = K;
+    q->ck_row = lin32::ck_row_elems(K);
+    q->NCK = lin32::n_checkpoints(p.T);
+    q->fr = reinterpret_cast<float *>(ws + w.lin_fr);
+    q->ck = reinterpret_cast<float *>(ws + w.lin_ck);
     q->nll2 = p.nll2; q->nll = p.nll;
     q->flags = reinterpret_cast<int *>(ws + w.abort_word + 256 + align_up((size_t)p.B * sizeof(int), 256));
     q->slot = reinterpret_cast<int *>(ws + w.abort_word + 256 + 2 * align_up((size_t)p.B * sizeof(int), 256));
     q->slot_counter = reinterpret_cast<int *>(ws + w.abort_word + 4);
-    q->n_slots = (int)lin_slots(p.B);
+    q->n_slots = saved ? (int)lin_slots(p.B) : (int)p.B;   // (no rows are stored without save_for_backward)
     q->grad_out = p.grad_out; q->grad = p.grad; q->gst = p.gst; q->gsb = p.gsb; q->zero_inf = p.zero_inf;
     q->save = saved ? 1 : 0;
-    q->G = 2;
-    q->slot_bytes = ring_slot_bytes(p.V);
-    q->ncol_max = (int)std::min<int64_t>(p.V, (int64_t)p.Lmax + 1);
-    q->erow_bytes = 8 * (q->ncol_max + 1);
-    // raw-row ring: as deep as fits next to two resident CTAs per SM (small vocabularies: 4 stages)
-    for (q->NST = 4; q->NST >= 2; --q->NST) {
-        *smem_fwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->K, false).total;
-        *smem_bwd = (size_t)lin::smem_map(q->NST, q->slot_bytes, q->erow_bytes, p.V, p.Lmax, q->K, true).total;
-        if (*smem_bwd <= (size_t)(q->NST > 2 ? 110 * 1024 : kMaxDynSmem)) break;
-    }
-    return q->NST >= 2 && *smem_bwd <= (size_t)kMaxDynSmem;
-}
-
-template <bool GRAD>
-static int launch_lin(const lin::Params &q, size_t smem_bytes, cudaStream_t s) {
-    dim3 grid((unsigned)q.B, 2), block((2 + (GRAD ? q.G : 0)) * 32);
-#define SSAK_LIN2(KK, ZZ)                                                                      \
-    {                                                                                          \
-        cudaError_t e = ensure_max_smem<lin::ctc_lin_kernel<KK, GRAD, ZZ>>();                  \
-        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                \
-        lin::ctc_lin_kernel<KK, GRAD, ZZ><<<grid, block, smem_bytes, s>>>(q);                  \
-    }
-#define SSAK_LIN(KK) case KK: if (q.zl) SSAK_LIN2(KK, true) else SSAK_LIN2(KK, false) break;
-    switch (q.K) {
-        SSAK_LIN(4)
-        SSAK_LIN(7)
-        SSAK_LIN(10)
-        SSAK_LIN(13)
-        SSAK_LIN(16)
-        default: return SSAK_ERR_UNSUPPORTED;
-    }
-#undef SSAK_LIN
-#undef SSAK_LIN2
-    return check_launch();
+    q->mass_tol = 1e-6f * (float)env_int("SSAK_LIN32_TOL_PPM", 20);
+    return true;
 }
 
 /* 1 when the kernels cover the shape, 0 otherwise (max_target_len > 4095, T > 300000, B <= 0, or a vocabulary
@@ -1726,6 +1725,36 @@ extern "C" int ssak_ctc_loss_supported(int64_t T, int64_t B, int64_t V, int64_t 
     if (T < 0 || T > 300000 || B <= 0 || V <= 0 || V > (1 << 20) || max_target_len < 0) return 0;
     if (!choose_cfg(max_target_len, B, (int)V, &c)) return 0;
     return smem_bytes_for(c, (int)V, (int)max_target_len, true) <= (size_t)kMaxDynSmem ? 1 : 0;
+}
+
+/* Diagnostics: which kernel family computed each utterance in the last forward (+ backward) call on this workspace.
+ * flags_out[b] (device, int32): 0 throughput kernels; bit 0: handed to the log-domain kernels by forward(); bit 1: by
+ * backward() (its self-check failed); bit 2: nobody (no row block left: NaN).  All zeros when the shape is not
+ * covered by the throughput kernels. */
+extern "C" int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_t B, int64_t V, int64_t max_target_len,
+                                        int32_t save_for_backward, int32_t *flags_out, ssak_stream_t stream) {
+    CtcCfg c;
+    if (!workspace || !flags_out || B <= 0 || V <= 0 || !choose_cfg(max_target_len, B, (int)V, &c))
+        return SSAK_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (lin_k(max_target_len, V, B) == 0) {
+        e = cudaMemsetAsync(flags_out, 0, (size_t)B * sizeof(int32_t), s);
+    } else {
+        const WsLayout w = ws_layout(T, B, V, max_target_len, c.row_elems, save_for_backward != 0);
+        const char *ws = reinterpret_cast<const char *>(workspace);
+        e = cudaMemcpyAsync(flags_out, ws + w.abort_word + 256 + align_up((size_t)B * sizeof(int), 256),
+                            (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    }
+    if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
+    return SSAK_OK;
+}
+
+// kernels of ours per forward + backward call pair (what bench.py reports as gpu_launches)
+extern "C" int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len, int32_t logits) {
+    // throughput mode: memset excluded; forward: [row lse] lin32 fwd + lin32 join + masked log-domain fwd + join;
+    // backward: lin32 bwd + masked log-domain fwd + join + bwd.  Log-domain mode: fwd + join, bwd.
+    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B) > 0 ? 8 : 3);
 }
 
 static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,
@@ -1749,17 +1778,14 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + 3 * align_up((size_t)B * sizeof(int), 256), s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
     }
-    // Linear-domain kernels first (no stored lattice); the utterances they hand back (flags, see ctc_lin.cuh) are
+    // Throughput kernels first (no stored lattice); the utterances they hand back (flags, see ctc_lin32.cu) are
     // then recomputed by the log-domain kernels below, launched over the same grid with a mask.
-    lin::Params q;
-    size_t smem_f = 0, smem_b = 0;
-    if (lin_params(p, workspace, save_for_backward != 0, &q, &smem_f, &smem_b)) {
-        rc = launch_lin<false>(q, smem_f, s);
-        if (rc != SSAK_OK) return rc;
-        lin::ctc_lin_join_kernel<<<(unsigned)B, 256, 0, s>>>(q);
-        rc = check_launch();
+    lin32::Params q;
+    if (lin_params(p, workspace, save_for_backward != 0, &q)) {
+        rc = lin32::launch_forward(q, s);
         if (rc != SSAK_OK) return rc;
         p.mask = q.flags;
+        p.mask_bits = 1;
         p.slot = q.slot;
     }
     rc = launch_forward_wave(p, s);
@@ -1784,13 +1810,23 @@ static int backward_impl(const float *grad_out, const float *x, int64_t T, int64
     p.grad_out = grad_out; p.grad = grad; p.gst = g_stride_t; p.gsb = g_stride_b;
     p.zero_inf = zero_infinity;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    lin::Params q;
-    size_t smem_f = 0, smem_b = 0;
-    if (lin_params(p, workspace, true, &q, &smem_f, &smem_b)) {
-        rc = launch_lin<true>(q, smem_b, s);
+    lin32::Params q;
+    if (lin_params(p, workspace, true, &q)) {
+        rc = lin32::launch_backward(q, s);
         if (rc != SSAK_OK) return rc;
+        // utterances whose self-check failed in this call (flag bit 1): the log-domain forward first (their half
+        // lattices were never stored), then the log-domain backward for them and for the ones forward() handed back
         p.mask = q.flags;
         p.slot = q.slot;
+        p.mask_bits = 2;
+        p.join_keeps_nll = 1;
+        rc = launch_forward_wave(p, s);
+        if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
+        if (rc != SSAK_OK) return rc;
+        ctc_join_kernel<<<(unsigned)B, 256, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != SSAK_OK) return rc;
+        p.mask_bits = 3;
     }
     return launch_lattice<true>(p, s);
 }

@@ -128,7 +128,7 @@ extern "C" int ssak_ctc_loss_host(ssak_context_t *ctx, const float *log_probs_ho
         int64_t lm = 0;
         for (int64_t b = b0s[i]; b < b0s[i + 1]; ++b) lm = std::max<int64_t>(lm, target_lengths_host[b]);
         lmaxs[i] = lm;
-        wsb[i] = ssak_ctc_loss_workspace_bytes(T, b0s[i + 1] - b0s[i], lm, want_grad);
+        wsb[i] = ssak_ctc_loss_workspace_bytes_v(T, b0s[i + 1] - b0s[i], V, lm, want_grad);
         if (wsb[i] == 0) return SSAK_ERR_UNSUPPORTED;
         ws_total += align_up(wsb[i], 256);
     }

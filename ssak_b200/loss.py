@@ -65,7 +65,7 @@ class _CTCLossFunction(torch.autograd.Function):
         dev = log_probs.device
         save = bool(ctx.needs_input_grad[0])
         _require_supported(T, B, V, max_target_len)
-        ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, max_target_len, int(save))
+        ws_bytes = L.ssak_ctc_loss_workspace_bytes_v(T, B, V, max_target_len, int(save))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         red = _RED_CODE[reduction]
@@ -280,7 +280,7 @@ def _aten_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, z
     L = _lib.lib()
     T, B, V = lp.shape
     _require_supported(T, B, V, lmax)
-    ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, lmax, 1)
+    ws_bytes = L.ssak_ctc_loss_workspace_bytes_v(T, B, V, lmax, 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lp.device)
     nll = torch.empty(B, dtype=torch.float32, device=lp.device)
     with torch.cuda.device(lp.device):

@@ -114,7 +114,7 @@ class _ShardedCTCFunction(torch.autograd.Function):
         T, B, V = log_probs.shape
         dev = log_probs.device
         _require_supported(T, B, V, max_target_len)
-        ws_bytes = L.ssak_ctc_loss_workspace_bytes(T, B, max_target_len, 1)
+        ws_bytes = L.ssak_ctc_loss_workspace_bytes_v(T, B, V, max_target_len, 1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         gscale = torch.empty(B, dtype=torch.float32, device=dev)

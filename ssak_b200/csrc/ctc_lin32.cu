@@ -48,10 +48,11 @@ constexpr int TOP = 96;             // re-scaled lane maximum ~ 2^TOP
 constexpr int WIN = 12;             // hysteresis of the re-scaling: lane maxima stay within [2^(TOP-WIN), 2^(TOP+4))
 constexpr int DMAX = 16;            // a lane's exponent is at most DMAX below its upstream neighbour's
 constexpr int EZERO = -(1 << 24);   // exponent wish of a lane that holds only zeros
+constexpr int MC = 4;               // copies of the posterior-mass vector (lanes 8c .. 8c+7 add into copy c)
 constexpr int FIX = 30;             // posteriors are accumulated in 2^-FIX fixed point (integer adds: order-independent)
 constexpr int GMIN = -120;          // smallest exponent of the tile scale 2^(E_live + E_other - E_P)
 constexpr int GMAX = 127 - (TOP + DMAX + 2 * C + 2);   // largest exponent of tile scale x 2^FIX: tile entries stay finite
-constexpr int FWD_WARPS = 14, BWD_WARPS = 12;   // resident one-warp CTAs per SM the register budgets are set for
+constexpr int FWD_WARPS = 16, BWD_WARPS = 12;   // resident one-warp CTAs per SM the register budgets are set for
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float pow2f(int e) {   // 2^e: 0 below 2^-126, 2^127 above
@@ -60,31 +61,33 @@ __device__ __forceinline__ float pow2f(int e) {   // 2^e: 0 below 2^-126, 2^127 
 }
 
 struct WarpSmem {
-    int yring, tile, mass, total;   // byte offsets inside a warp's slice
+    int ring, tile, mass, total;   // byte offsets inside a warp's slice
 };
-__host__ __device__ inline int vp_of(int V) { return (V + 4) & ~3; }        // ring row stride: V columns + a zero column
+constexpr int FWD_DEPTH = 4, BWD_DEPTH = 2;   // chunks / tiles of emission rows in shared memory (the one in use + look-ahead)
+__host__ __device__ inline int nv_of(int V) { return V <= 64 ? 2 : 4; }      // vocabulary columns per lane (instantiated: 2, 4)
 __host__ __device__ inline WarpSmem smem_map(int K, int V, bool grad) {
     WarpSmem m;
     int o = 0;
-    m.yring = o; o += C * vp_of(V) * 4;
+    m.ring = o;  o += (grad ? BWD_DEPTH : FWD_DEPTH) * C * (32 * nv_of(V) + 4) * 4;
     m.tile = o;  if (grad) o += C * 2 * K * 32 * 4;
-    m.mass = o;  if (grad) o += ((V + 1) * 4 + 15) & ~15;
+    m.mass = o;  if (grad) o += (MC * (V + 1) * 4 + 15) & ~15;
     m.total = (o + 127) & ~127;
     return m;
 }
 
-// ---- static tables of direction D at a lane's positions ----
-// D = 0 (alpha): position q = (blank q, label q);  D = 1 (beta): position q = (label q-1 [in l], blank q).
-// lab[k]: vocabulary index of the position's label state, V (the zero column / the dump slot) when it does not exist.
+// The label state of position q = q0 + k is label q (D = 0) or label q - 1 (D = 1), and it exists iff that index is in
+// [0, L): ONE table labs[i] = byte offset (4 x vocabulary index) of label q0 - 1 + i, i = 0 .. K, serves both
+// directions (position k of direction D reads labs[k + 1 - D]); labels that do not exist point at the zero column
+// of the emission ring / the dump slot of the posterior mass, offset 4 V.
 template <int K>
-__device__ __forceinline__ void make_labels(int D, int q0, int L, int V, const int32_t *tg, int (&lab)[K]) {
+__device__ __forceinline__ void make_labels(int q0, int L, int V, const int32_t *tg, int (&labs)[K + 1]) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int q = q0 + k, li = D ? q - 1 : q;
-        lab[k] = V;
-        if (q <= L && li >= 0 && li < L) {
+    for (int i = 0; i <= K; ++i) {
+        const int li = q0 - 1 + i;
+        labs[i] = 4 * V;
+        if (li >= 0 && li < L) {
             const int l = tg[li];
-            lab[k] = l < 0 ? 0 : (l >= V ? V - 1 : l);     // (memory safety; the join kernel turns the likelihood into NaN)
+            labs[i] = 4 * (l < 0 ? 0 : (l >= V ? V - 1 : l));   // (memory safety; the join kernel turns the likelihood into NaN)
         }
     }
 }
@@ -116,13 +119,13 @@ __device__ __forceinline__ void make_skip(int q0, int L, int V, const int32_t *t
 //   entry, label posteriors added to mass[label] in fixed point.
 template <int K, int D, int MODE>
 __device__ __forceinline__ void step(float (&a)[K], float (&l)[K], const float ebp, const unsigned char *yrow,
-                                     const int (&eoff)[K], const float (&sk)[K], const float cin, float *tl,
+                                     const int (&labs)[K + 1], const float (&sk)[K], const float cin, float *tl,
                                      unsigned *mass, float &sbl) {
     float carry = cin;
 #pragma unroll
     for (int kk = 0; kk < K; ++kk) {
         const int k = D ? K - 1 - kk : kk;
-        const float el = *reinterpret_cast<const float *>(yrow + eoff[k]);
+        const float el = *reinterpret_cast<const float *>(yrow + labs[k + 1 - D]);
         const float A = fmaf(a[k], ebp, carry);
         const float t = fmaf(sk[k], carry, fmaf(a[k], ebp, l[k]));
         if (MODE == 1) {
@@ -131,7 +134,7 @@ __device__ __forceinline__ void step(float (&a)[K], float (&l)[K], const float e
         }
         if (MODE == 2) {
             sbl = fmaf(A, tl[k * 32], sbl);
-            atomicAdd(reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(mass) + eoff[k]),
+            atomicAdd(reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(mass) + labs[k + 1 - D]),
                       __float2uint_rn(t * tl[(K + k) * 32]));
         }
         carry = l[k];
@@ -230,39 +233,62 @@ __device__ __forceinline__ bool chain_of(const Params &p, Chain &c) {
     return true;
 }
 
-// Emission staging: the warp converts its own rows.  Raw values are fetched into registers one chunk ahead (the
-// global-memory latency hides behind a whole chunk of recursion), converted (one MUFU.EX2 per column) and stored into
-// the warp's ring of C rows right before the chunk that needs them.  NV = columns per lane (V <= 32 NV).
-template <int NV>
+// Emission staging: the warp converts its own rows.  Raw rows travel global -> shared with cp.async (LDGSTS: no
+// registers, no scoreboard -- completion is counted per commit group) into a ring of DEPTH chunks, DEPTH - 1 chunks
+// ahead of their use; right before a chunk runs, its rows are converted (one MUFU.EX2 per column) into the warp's
+// ring of C emission rows.  NV = columns per lane (V <= 32 NV); raw row stride = 32 NV + 4 floats (the spare ones
+// hold the zero column [V] the non-existent states read, and the row normaliser of the logits entry points [RS-1]).
+// The conversion happens IN PLACE: a ring row first holds log-probabilities, then emissions.
+__host__ __device__ inline int raw_stride(int nv) { return 32 * nv + 4; }
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NV, int DEPTH>
 struct Stage {
-    float raw[C][NV];
-    float zr[C];
-    // slot i <-> frame t0 + i*dt, slots [i0, nr)
-    __device__ __forceinline__ void fetch(const float *lp_b, int64_t st, const float *zl_b, int64_t zstep, int lane, int V,
-                                          int t0, int dt, int i0, int nr) {
+    static constexpr int RS = 32 * NV + 4;
+    float *ring;      // [DEPTH][C][RS]
+    __device__ __forceinline__ void init(int lane, int V) {   // the zero column of every row
+        for (int r = lane; r < DEPTH * C; r += 32) ring[r * RS + V] = 0.f;
+    }
+    __device__ __forceinline__ const float *row(int s, int i) const { return ring + (size_t)(s * C + i) * RS; }
+    // slot i of ring stage s <-> frame t0 + i*dt, slots [i0, nr); always commits a group (possibly empty)
+    __device__ __forceinline__ void issue(int s, const float *lp_b, int64_t st, const float *zl_b, int64_t zstep, int lane,
+                                          int V, int t0, int dt, int i0, int nr) {
         const float *src = lp_b + (int64_t)t0 * st + lane;
         const int64_t step = (int64_t)dt * st;
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            const bool on = i >= i0 && i < nr;
-            zr[i] = (zl_b != nullptr && on) ? __ldg(zl_b + (int64_t)(t0 + i * dt) * zstep) : 0.f;
-#pragma unroll
-            for (int j = 0; j < NV; ++j)
-                raw[i][j] = (on && lane + 32 * j < V) ? __ldg(src + 32 * j) : __int_as_float(0xff800000);
-            src += step;
-        }
-    }
-    // -> ring rows i0 .. nr-1; returns the largest scaled emission seen (log2 units; > 0: not a probability)
-    __device__ __forceinline__ float convert(float *yring, int VP, int lane, int V, int i0, int nr) {
-        float xmax = -1.f;
+        float *dst = ring + (size_t)s * C * RS + lane;
 #pragma unroll
         for (int i = 0; i < C; ++i) {
             if (i >= i0 && i < nr) {
 #pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    if (lane + 32 * j < V) cp_async4(dst + i * RS + 32 * j, src + 32 * j);
+                if (zl_b != nullptr && lane == 0) cp_async4(dst + i * RS + RS - 1, zl_b + (int64_t)(t0 + i * dt) * zstep);
+            }
+            src += step;
+        }
+        cp_async_commit();
+    }
+    // rows i0 .. nr-1 of ring stage s: log-probabilities -> emissions; returns the largest scaled emission seen
+    // (log2 units; > 0: not a probability).  The caller has waited for the stage's group and synchronised the warp.
+    __device__ __forceinline__ float convert(int s, int lane, int V, int i0, int nr, bool logits) {
+        float *src = ring + (size_t)s * C * RS + lane;
+        float xmax = -1.f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            if (i >= i0 && i < nr) {
+                const float z = logits ? src[i * RS + RS - 1 - lane] : 0.f;
+#pragma unroll
                 for (int j = 0; j < NV; ++j) {
-                    const float xs = fmaf(raw[i][j], kLog2e, zr[i]);
-                    xmax = fmaxf(xmax, xs);
-                    if (lane + 32 * j < V) yring[i * VP + lane + 32 * j] = ex2_approx(xs);
+                    if (lane + 32 * j < V) {
+                        const float xs = fmaf(src[i * RS + 32 * j], kLog2e, z);
+                        xmax = fmaxf(xmax, xs);
+                        src[i * RS + 32 * j] = ex2_approx(xs);
+                    }
                 }
             }
         }
@@ -278,24 +304,20 @@ __global__ void __launch_bounds__(32, FWD_WARPS) lin32_forward_kernel(const Para
     Chain ch;
     if (!chain_of(p, ch)) return;
     const int b = ch.b, dir = ch.dir, Tb = ch.Tb, L = ch.L;
-    const int V = p.V, VP = vp_of(V);
+    const int V = p.V;
     const int nrows = dir ? Tb - ch.m : ch.m;
     const float *lp_b = p.lp + (int64_t)b * p.sb;
     const float *zl_b = p.zl ? p.zl + b : nullptr;
     const int32_t *tg = p.targets + p.tgt_off[b];
     const WarpSmem sm = smem_map(K, V, false);
-    float *yring = reinterpret_cast<float *>(smem + (size_t)warp * sm.total + sm.yring);
     const int q0 = lane * K;
     const bool live = q0 <= L;
-    if (lane < C) yring[lane * VP + V] = 0.f;               // the zero column of every ring row
 
     auto run = [&](auto dtag) {
         constexpr int D = decltype(dtag)::value;
-        int eoff[K];
+        int labs[K + 1];
         float sk[K], as[K], ls[K];
-        make_labels<K>(D, q0, L, V, tg, eoff);
-#pragma unroll
-        for (int k = 0; k < K; ++k) eoff[k] *= 4;
+        make_labels<K>(q0, L, V, tg, labs);
         make_skip<K>(q0, L, V, tg, sk);
         start_row<K>(D, q0, L, as, ls);
         const int eoff_blank = 4 * p.blank;
@@ -305,37 +327,39 @@ __global__ void __launch_bounds__(32, FWD_WARPS) lin32_forward_kernel(const Para
         float *ck_dir = p.ck + ((int64_t)b * 2 + D) * p.NCK * p.ck_row;
         const int n_seq = (nrows + C - 1) / C;
         const int tf = D ? Tb - 1 : 0, dt = D ? -1 : 1;      // frame of row 0, direction of time
-        auto fetch = [&](Stage<NV> &stg, int n) {
-            if (n < n_seq)
-                stg.fetch(lp_b, p.st, zl_b, p.B, lane, V, tf + dt * n * C, dt, 0, nrows - n * C < C ? nrows - n * C : C);
+        Stage<NV, FWD_DEPTH> stg;
+        stg.ring = reinterpret_cast<float *>(smem + (size_t)warp * sm.total + sm.ring);
+        stg.init(lane, V);
+        const bool logits = zl_b != nullptr;
+        auto issue = [&](int n) {                            // chunk n into ring stage n % DEPTH (empty group beyond the end)
+            const int left = nrows - n * C;
+            stg.issue(n % FWD_DEPTH, lp_b, p.st, zl_b, p.B, lane, V, tf + dt * n * C, dt, 0, left < 0 ? 0 : (left < C ? left : C));
         };
-        auto chunk = [&](Stage<NV> &stg, int n) {
+#pragma unroll
+        for (int n = 0; n < FWD_DEPTH - 1; ++n) issue(n);
+        for (int n = 0; n < n_seq; ++n) {
             const int row0 = n * C, nr = nrows - row0 < C ? nrows - row0 : C;
             __syncwarp();                                    // every lane is done with the previous chunk's rows
-            xmax = fmaxf(xmax, stg.convert(yring, VP, lane, V, 0, nr));
-            fetch(stg, n + 2);                               // two chunks ahead: one chunk of recursion does not cover
-            __syncwarp();                                    // the DRAM latency of these scattered 200-byte rows
+            issue(n + FWD_DEPTH - 1);                        // (into the stage chunk n - 1 was converted from)
+            cp_async_wait<FWD_DEPTH - 1>();                  // my copies of chunk n have landed ...
+            __syncwarp();                                    // ... and so have everybody's
+            xmax = fmaxf(xmax, stg.convert(n % FWD_DEPTH, lane, V, 0, nr, logits));
+            __syncwarp();
             // (not unrolled over the frames: copies of the frame body per frame and direction overflow the
             //  instruction cache -- every warp is at its own place in the loop)
 #pragma unroll 1
             for (int i = 0; i < nr; ++i) {
-                const unsigned char *yrow = reinterpret_cast<const unsigned char *>(yring + i * VP);
+                const unsigned char *yrow = reinterpret_cast<const unsigned char *>(stg.row(n % FWD_DEPTH, i));
                 const float eb = *reinterpret_cast<const float *>(yrow + eoff_blank);
-                step<K, D, 0>(as, ls, ebp, yrow, eoff, sk, carry_in<K, D>(ls, f), nullptr, nullptr, dummy);
+                step<K, D, 0>(as, ls, ebp, yrow, labs, sk, carry_in<K, D>(ls, f), nullptr, nullptr, dummy);
                 ebp = eb;
             }
             if (nr == C) {
                 ok = rescale<K, D>(as, ls, E, f, lane, EZERO, false) && ok;
                 if (p.save) store_row<K>(ck_dir + (int64_t)(n + 1) * p.ck_row, as, ls, ebp, E, lane, live);
             }
-        };
-        Stage<NV> sA, sB;
-        fetch(sA, 0);
-        fetch(sB, 1);
-        for (int n = 0; n < n_seq; n += 2) {
-            chunk(sA, n);
-            if (n + 1 < n_seq) chunk(sB, n + 1);
         }
+        cp_async_wait<0>();
         store_row<K>(p.fr + ((int64_t)b * 2 + D) * p.ck_row, as, ls, ebp, E, lane, live);
         // a partial last chunk is not re-scaled: check its states here
         unsigned h = 0;
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
     Chain ch;
     if (!chain_of(p, ch)) return;
     const int b = ch.b, dir = ch.dir, Tb = ch.Tb, L = ch.L;
-    const int V = p.V, VP = vp_of(V);
+    const int V = p.V;
     if (p.flags[b] & 5) return;                                // the log-domain kernels own this utterance (or nobody)
     const float nll = p.nll[b];
     const float gs = p.grad_out[b];
@@ -484,22 +508,20 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
     const int32_t *tg = p.targets + p.tgt_off[b];
     const WarpSmem sm = smem_map(K, V, true);
     unsigned char *mine = smem + (size_t)warp * sm.total;
-    float *yring = reinterpret_cast<float *>(mine + sm.yring);
     float *tile = reinterpret_cast<float *>(mine + sm.tile);       // [C][2K][32]
-    unsigned *mass = reinterpret_cast<unsigned *>(mine + sm.mass); // [V + 1] label posterior mass of the frame, fixed point
+    // [MC][V + 1] label posterior mass of the frame in fixed point (integer adds: the sum does not depend on their
+    // order); MC copies so that the ~L/V states of a label rarely meet in one shared-memory atomic (9 -> ~3 passes)
+    unsigned *mass = reinterpret_cast<unsigned *>(mine + sm.mass);
+    unsigned *mass_mine = mass + (lane / (32 / MC)) * (V + 1);
     const int q0 = lane * K;
     const bool live = q0 <= L;
-    if (lane < C) yring[lane * VP + V] = 0.f;
-    for (int cc = lane; cc <= V; cc += 32) mass[cc] = 0u;
+    for (int cc = lane; cc < MC * (V + 1); cc += 32) mass[cc] = 0u;
 
     auto run = [&](auto dtag) {
         constexpr int DL = decltype(dtag)::value, DR = 1 - DL;
-        int eoffL[K], eoffR[K];
+        int labs[K + 1];
         float sk[K], la[K], ll[K], ra[K], rl[K];
-        make_labels<K>(DL, q0, L, V, tg, eoffL);
-        make_labels<K>(DR, q0, L, V, tg, eoffR);
-#pragma unroll
-        for (int k = 0; k < K; ++k) { eoffL[k] *= 4; eoffR[k] *= 4; }
+        make_labels<K>(q0, L, V, tg, labs);
         make_skip<K>(q0, L, V, tg, sk);
         const int eoff_blank = 4 * p.blank;
         int EL = 0, ER = 0;
@@ -530,25 +552,32 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                 rescale<K, DR>(ra, rl, ER, fdummy, lane, EZERO, true);
             }
         };
-        Stage<NV> stg;
+        Stage<NV, BWD_DEPTH> stg;
+        stg.ring = reinterpret_cast<float *>(mine + sm.ring);
+        stg.init(lane, V);
+        const bool logits = zl_b != nullptr;
         bool bad = false;
         float xmax = -1.f;
-        if (n_seq > 0) {
+        auto issue = [&](int n) {                               // tile n into ring stage n % DEPTH (empty group beyond the end)
             int j, row0, i0, nr;
-            geometry(0, j, row0, i0, nr);
-            stg.fetch(lp_b, p.st, zl_b, p.B, lane, V, frame_of(row0), dt, i0, nr);
-            load_ck(j);
-        }
+            geometry(n, j, row0, i0, nr);
+            if (n >= n_seq) nr = 0;
+            stg.issue(n % BWD_DEPTH, lp_b, p.st, zl_b, p.B, lane, V, frame_of(row0), dt, i0, nr);
+        };
+#pragma unroll
+        for (int n = 0; n < BWD_DEPTH - 1; ++n) issue(n);
+        if (n_seq > 0) load_ck(nrows / C);
         for (int n = 0; n < n_seq; ++n) {
             int j, row0, i0, nr;
             geometry(n, j, row0, i0, nr);
             __syncwarp();                                       // the previous tile is done with the ring
-            xmax = fmaxf(xmax, stg.convert(yring, VP, lane, V, i0, nr));
-            if (n + 1 < n_seq) {
-                int j2, r2, i2, n2;
-                geometry(n + 1, j2, r2, i2, n2);
-                stg.fetch(lp_b, p.st, zl_b, p.B, lane, V, frame_of(r2), dt, i2, n2);
-            }
+            issue(n + BWD_DEPTH - 1);
+            cp_async_wait<BWD_DEPTH - 1>();
+            __syncwarp();
+            xmax = fmaxf(xmax, stg.convert(n % BWD_DEPTH, lane, V, i0, nr, logits));
+            // (L2 look-ahead for the checkpoint of the tile three tiles on: one instruction, no registers)
+            if (j - 4 >= 1 && lane * 32 < p.ck_row)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ck_dir + (int64_t)(j - 4) * p.ck_row + lane * 32));
             __syncwarp();
             // ---- the live direction moves into this tile's scaling; the tile scale 2^(EL + ER - Ep) / mantissa(P)
             //      must be representable: EL >= GMIN - ER + Ep wherever DR holds anything
@@ -579,9 +608,9 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
             float ebpR = 1.f;
 #pragma unroll 1
             for (int i = 0; i + 1 < nr; ++i) {
-                const unsigned char *yrow = reinterpret_cast<const unsigned char *>(yring + (i + 1) * VP);
+                const unsigned char *yrow = reinterpret_cast<const unsigned char *>(stg.row(n % BWD_DEPTH, i + 1));
                 const float eb = *reinterpret_cast<const float *>(yrow + eoff_blank);
-                step<K, DR, 1>(ra, rl, ebpR, yrow, eoffR, sk, carry_in<K, DR>(rl, fR), tl + i * 2 * K * 32, nullptr, dummy);
+                step<K, DR, 1>(ra, rl, ebpR, yrow, labs, sk, carry_in<K, DR>(rl, fR), tl + i * 2 * K * 32, nullptr, dummy);
                 ebpR = eb;
             }
             {
@@ -595,17 +624,18 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                     ti[(K + k) * 32] = c;
                 }
             }
-            // the next tile's checkpoint travels while the live direction works (ra / rl are dead until then)
+            // the next tile's checkpoint travels while the live direction works (ra / rl are dead until then; at 14
+            // resident warps and 128 registers -- no room for this -- the kernel was 15 % slower)
             if (n + 1 < n_seq) load_ck(j - 1);
             // ---- B phase: the live direction over the tile's rows, last row first; every frame's posteriors go
             //      straight into its gradient row
 #pragma unroll 1
             for (int i = nr - 1; i >= i0; --i) {
-                const float *yrowf = yring + i * VP;
+                const float *yrowf = stg.row(n % BWD_DEPTH, i);
                 const unsigned char *yrow = reinterpret_cast<const unsigned char *>(yrowf);
                 const float eb = *reinterpret_cast<const float *>(yrow + eoff_blank);
                 float sbl = 0.f;
-                step<K, DL, 2>(la, ll, ebpL, yrow, eoffL, sk, carry_in<K, DL>(ll, fL), tl + i * 2 * K * 32, mass, sbl);
+                step<K, DL, 2>(la, ll, ebpL, yrow, labs, sk, carry_in<K, DL>(ll, fL), tl + i * 2 * K * 32, mass_mine, sbl);
                 ebpL = eb;
                 sbl *= i == 0 ? 1.f : eb;                       // (slot 0: the checkpoint's true blank states)
                 bad = bad || !(sbl <= 3.0e38f);                 // inf / NaN
@@ -620,8 +650,13 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                     const int cc = lane + 32 * jj;
                     mi[jj] = 0u;
                     if (cc < V) {
-                        mi[jj] = mass[cc] + (cc == p.blank ? blank_mass : 0u);
-                        mass[cc] = 0u;
+                        unsigned msum = cc == p.blank ? blank_mass : 0u;
+#pragma unroll
+                        for (int c2 = 0; c2 < MC; ++c2) {
+                            msum += mass[c2 * (V + 1) + cc];
+                            mass[c2 * (V + 1) + cc] = 0u;
+                        }
+                        mi[jj] = msum;
                     }
                     tot += mi[jj];
                 }
@@ -636,6 +671,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                 __syncwarp();                                   // mass[] is clean for the next frame
             }
         }
+        cp_async_wait<0>();
         bad = bad || xmax > 0.01f;
         if (__any_sync(FULL, bad) && lane == 0) {
             // hand the utterance to the log-domain kernels (they redo its forward in this call): first flagger
@@ -675,7 +711,7 @@ static int launch(const Params &p, cudaStream_t s) {
     const int per_cta = 1;
     const unsigned grid = (unsigned)(2 * p.B);
     const size_t smem_bytes = per_cta * per_warp;
-    const int nv = p.V <= 64 ? 2 : 4;                       // vocabulary columns per lane (instantiated: 2, 4)
+    const int nv = nv_of(p.V);
 #define SSAK_L32B(KK, NN)                                                                          \
     {                                                                                              \
         if (GRAD) {                                                                                \

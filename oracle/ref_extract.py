@@ -152,3 +152,26 @@ def pack_words(word_spans, words, num_frames, ratio, utt_id, wavid, spk, start, 
     return {"text": files["f_text"].getvalue(), "utt2spk": files["f_utt2spk"].getvalue(),
             "utt2dur": files["f_utt2dur"].getvalue(), "segments": files["f_segments"].getvalue(),
             "warnings": len(warnings)}
+
+
+def resume_point(dirout):
+    """Run the reference's own resume block (tools/align_audio_transcript.py:160-177, with its get_last_line) on an
+    output folder -> last_id (None for a fresh or empty folder).  Raises what the reference raises."""
+    import re
+    import textwrap
+    with open(_TOOL_PY, "r", encoding="utf-8") as f:
+        src = f.read()
+    lines = src.split("\n")
+    first = next(i for i, l in enumerate(lines) if l.strip() == "last_id = None")
+    last = next(i for i in range(first, len(lines)) if lines[i].strip().startswith("os.makedirs(dirout"))
+    tree = ast.parse(src, filename=_TOOL_PY)
+    gll = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_last_line"]
+
+    class _Log:
+        def warning(self, m):
+            pass
+
+    ns = {"os": os, "re": re, "logger": _Log(), "dirout": dirout}
+    exec(compile(ast.Module(body=gll, type_ignores=[]), _TOOL_PY, "exec"), ns)
+    exec(compile(textwrap.dedent("\n".join(lines[first:last])), _TOOL_PY + ":resume", "exec"), ns)
+    return ns["last_id"]

@@ -332,3 +332,49 @@ def compute_alignment_from_emission(emission, transcript, labels, blank_id, add_
     n_tok = len(char_segments) + (2 if add_before_after else 0)
     trellis = Trellis(emission.shape[0], n_tok - (2 if add_before_after else 0), None)   # :367 drops the sentinels
     return list(labels)[: emission.shape[1]], emission, trellis, char_segments, word_segments
+
+
+def compute_alignment(audio, transcript, model, add_before_after=None, first_as_garbage=False, plot=False, verbose=False,
+                      *, compute_log_probas=None, get_model_vocab=None, decode_log_probas=None):
+    """The reference's entry point, same signature and return value (align_transcriptions.py:294-402; callers:
+    tools/align_audio_transcript.py:335, tools/get_word_positions.py:33):
+        labels, emission, trellis, char_segments, word_segments = compute_alignment(audio, transcript, model)
+    The model-side front end stays with the reference -- `ssak.infer.general.compute_log_probas`,
+    `get_model_vocab` and (for transcript=None) `decode_log_probas` are imported from the reference package when it is
+    installed, or passed in as callables (any `model` object goes straight through to them).  Everything from the
+    emission on runs on the GPU aligner.  `plot` is accepted for signature compatibility (plots stay with the
+    reference: align_transcriptions.py:176-292)."""
+    if compute_log_probas is None or get_model_vocab is None:
+        try:
+            from ssak.infer import general as _general     # the reference package
+        except ImportError as err:
+            raise ImportError("compute_alignment(audio, transcript, model) needs the reference's model front end: install "
+                              "ssak, or pass compute_log_probas= and get_model_vocab= callables") from err
+        compute_log_probas = compute_log_probas or _general.compute_log_probas
+        get_model_vocab = get_model_vocab or _general.get_model_vocab
+        decode_log_probas = decode_log_probas or _general.decode_log_probas
+    emission = compute_log_probas(model, audio)                                          # :304
+    if not emission.is_cuda:
+        emission = emission.cuda()
+    if transcript is None:                                                               # :306-308
+        if decode_log_probas is None:
+            raise ValueError("transcript=None needs decode_log_probas")
+        transcript = decode_log_probas(model, emission)
+        print("Transcript:", transcript)
+    labels, blank_id = get_model_vocab(model)                                            # :330
+    out = compute_alignment_from_emission(emission, transcript, labels, blank_id, add_before_after, first_as_garbage)
+    if verbose:
+        for w in out[4]:
+            print(w)
+    return out
+
+
+def word_positions(audios, annotations, model, sample_rate, **front_end):
+    """tools/get_word_positions.py:14-43: one dict per word with start / end in seconds and the confidence."""
+    for audio, transcript in zip(audios, annotations):
+        _, _, trellis, _, word_segments = compute_alignment(audio, transcript, model, **front_end)
+        ratio = len(audio) / (trellis.size(0) * sample_rate)                             # :34 (T + 1 rows, like the reference)
+        all_words = transcript.split()
+        assert len(all_words) == len(word_segments)
+        for word, segment in zip(all_words, word_segments):
+            yield {"word": word, "start": segment.start * ratio, "end": segment.end * ratio, "conf": segment.score}

@@ -343,7 +343,10 @@ def run_ours(args, rank, world, local_rank):
     # the timed region can be shorter than nvidia-smi's sampling period: keep the same work running for ~0.3 s more
     # so that the clock / throttle samples are taken under this load (every rank runs the same fixed number of
     # steps: the sharded step contains a collective)
-    n_soak = max(2, min(600, int(0.3 / max(t_dev / args.steps, 1e-4))))
+    t_soak = torch.tensor([t_dev / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_soak, op=dist.ReduceOp.MAX)       # (a count derived from the local clock differs between ranks)
+    n_soak = max(2, min(600, int(0.3 / max(t_soak.item(), 1e-4))))
     for _ in range(n_soak):
         step()
     torch.cuda.synchronize()

@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(128) lin32_join_kernel(const Params p) {
                 const int sl = atomicAdd(p.slot_counter, 1);
                 if (sl < p.n_slots) {
                     p.slot[b] = sl;
+                    p.slot_b[sl] = b;
                     p.flags[b] = 1;
                 } else {
                     p.flags[b] = 4;                             // nobody owns it: backward() fills NaN
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
             const int old = atomicOr(&p.flags[b], 2);
             if (!(old & 2)) {
                 const int sl = atomicAdd(p.slot_counter, 1);
-                if (sl < p.n_slots) p.slot[b] = sl; else atomicOr(&p.flags[b], 4);
+                if (sl < p.n_slots) { p.slot[b] = sl; p.slot_b[sl] = b; } else atomicOr(&p.flags[b], 4);
             }
         }
     };
@@ -689,6 +690,21 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
             float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
             for (int cc = lane; cc < V; cc += 32) g[cc] = 0.f;
         }
+    }
+}
+
+// Utterances that were handed back when no row block was left (flag bit 2): nobody computed them -- NaN gradient
+// (loud).  One warp per utterance; runs after everything else of backward().
+__global__ void __launch_bounds__(256) lin32_orphan_kernel(const Params p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= p.B || !(p.flags[b] & 4)) return;
+    int Tb = p.in_len[b];
+    Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
+    for (int t = 0; t < (int)p.T; ++t) {
+        float *g = p.grad + (int64_t)t * p.gst + b * p.gsb;
+        const float v = t < Tb ? __int_as_float(0x7fc00000) : 0.f;
+        for (int cc = lane; cc < p.V; cc += 32) g[cc] = v;
     }
 }
 
@@ -745,6 +761,11 @@ int launch_forward(const Params &p, cudaStream_t s) {
 }
 
 int launch_backward(const Params &p, cudaStream_t s) { return launch<true>(p, s); }
+
+int launch_orphans(const Params &p, cudaStream_t s) {
+    lin32_orphan_kernel<<<(unsigned)((p.B + 7) / 8), 256, 0, s>>>(p);
+    return check_launch();
+}
 
 }  // namespace lin32
 }  // namespace ssak

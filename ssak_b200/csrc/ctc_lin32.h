@@ -31,6 +31,8 @@ struct Params {
     int *flags;                 // [B] bit 0: handed to the log-domain kernels by forward(); bit 1: by backward();
                                 //     bit 2: nobody owns it (no row block left): NaN gradient
     int *slot;                  // [B] row block of a handed-back utterance in the log-domain kernels' `rows`
+    int *slot_b;                // [n_slots] the utterance that owns row block i (the masked log-domain launches run one
+                                //     CTA pair per row block)
     int *slot_counter;
     int n_slots;
     const float *grad_out;
@@ -50,6 +52,7 @@ inline int n_checkpoints(int64_t T) { return (int)((T / 2 + 1) / C) + 2; }
 // forward: recursion kernel + join kernel (nll, nll2, flags, slots).  backward: recursion + gradient kernel.
 int launch_forward(const Params &p, cudaStream_t s);
 int launch_backward(const Params &p, cudaStream_t s);
+int launch_orphans(const Params &p, cudaStream_t s);   // NaN gradient for the utterances nobody owns (after the fallback launches)
 
 }  // namespace lin32
 }  // namespace ssak

@@ -104,6 +104,9 @@ struct CtcParams {
     const int *mask;  // [B] or nullptr: when set, only the utterances with one of `mask_bits` set (and bit 2 clear) are
                       // processed: the ones the throughput kernels of ctc_lin32.cu handed back (flags, see there)
     int mask_bits;
+    const int *slot_b;      // [n_slots] utterance that owns row block i: a masked launch has one CTA pair per ROW BLOCK
+    const int *slot_count;  // row blocks handed out so far (may exceed n_slots: the late ones got none)
+    int n_slots;
     int join_keeps_nll;   // the join kernel leaves nll[b] alone (backward-time recomputation: nll is the caller's input)
     int *nan_flag;    // [B] set by the forward kernels when an emission the lattice uses is NaN (fmax-based log-sum-exp
                       // would swallow it): the join kernel then returns a NaN likelihood, as torch does
@@ -200,6 +203,20 @@ static size_t smem_bytes_for(const CtcCfg &c, int V, int Lmax, bool grad) {
     return align_up(o, 16);
 }
 
+// The utterance of this CTA: blockIdx.x -- or, in a masked launch (grid = row blocks, not utterances: a launch over
+// all B x 2 CTAs cost ~100 us at B = 1024 just to find out that nothing was handed back), the utterance that owns
+// row block blockIdx.x; -1: nothing to do.
+__device__ __forceinline__ int utterance_of_cta(const CtcParams &p) {
+    int b = blockIdx.x;
+    if (p.mask) {
+        if (b >= *p.slot_count) return -1;
+        b = p.slot_b[b];
+        const int fl = p.mask[b];
+        if (!(fl & p.mask_bits) || (fl & 4)) return -1;
+    }
+    return b;
+}
+
 // ------------------------------------------------------------------------------ kernel
 // Warp roles: [0, W) recursion; W emission producer; backward only: W+1 lattice-row producer, then G gradient warps.
 template <int K, bool GRAD, int CH, bool LOGITS, bool SPLIT>
@@ -207,7 +224,8 @@ __global__ void __launch_bounds__(K == 8 ? (GRAD ? 704 : 544) : (GRAD ? (SPLIT ?
 ctc_lattice_kernel(const CtcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const CtcCfg &c = p.cfg;
-    const int b = blockIdx.x;
+    const int b = utterance_of_cta(p);
+    if (b < 0) return;
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (backward in time)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = c.W;
@@ -220,23 +238,6 @@ ctc_lattice_kernel(const CtcParams p) {
     const int rw = is_post ? warp - post0 : warp;        // the recursion warp whose state group this warp handles
     const unsigned FULL = 0xffffffffu;
 
-    if (p.mask) {
-        const int fl = p.mask[b];
-        if (GRAD && (fl & 4)) {
-            // handed back, but no row block was left: nobody computed this utterance -- NaN gradient (loud)
-            if (dir == 0) {
-                int Tn = p.in_len[b];
-                Tn = Tn < 0 ? 0 : (Tn > (int)p.T ? (int)p.T : Tn);
-                for (int t = 0; t < (int)p.T; ++t) {
-                    float *g = p.grad + (int64_t)t * p.gst + (int64_t)b * p.gsb;
-                    const float v = t < Tn ? __int_as_float(0x7fc00000) : 0.f;
-                    for (int cc = tid; cc < p.V; cc += blockDim.x) g[cc] = v;
-                }
-            }
-            return;
-        }
-        if (!(fl & p.mask_bits) || (fl & 4)) return;
-    }
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[b];
@@ -1005,13 +1006,13 @@ struct FwdWaveCfg {
 template <int K, int CH, bool LOGITS, bool SAVE>
 __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel(const CtcParams p, const FwdWaveCfg wc) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int b = blockIdx.x, dir = blockIdx.y;
+    const int b = utterance_of_cta(p), dir = blockIdx.y;
+    if (b < 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const int W = wc.W;
     const float EMPTY = __uint_as_float(kSeamEmptyBits);
 
-    if (p.mask && (!(p.mask[b] & p.mask_bits) || (p.mask[b] & 4))) return;
     int Tb = p.in_len[b];
     Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[b];
@@ -1303,8 +1304,8 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
 //   log P = off_a + off_b + lse_s( lse(alpha[s], alpha[s-1], skip ? alpha[s-2]) + beta_m[s] )
 __global__ void __launch_bounds__(256) ctc_join_kernel(const CtcParams p) {
     __shared__ float red_m[8], red_s[8];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (p.mask && (!(p.mask[b] & p.mask_bits) || (p.mask[b] & 4))) return;
+    const int b = utterance_of_cta(p), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b < 0) return;
     int L = p.tgt_len[b];
     L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     const int P_pad = p.cfg.P_pad, row_elems = p.cfg.row_elems;
@@ -1514,7 +1515,7 @@ static int launch_lattice(const CtcParams &p, cudaStream_t stream) {
     const CtcCfg &c = p.cfg;
     const size_t smem_bytes = smem_bytes_for(c, p.V, p.Lmax, GRAD);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)p.B, 2), block((c.W + (GRAD ? 2 + c.G + c.PW : 1)) * 32);
+    dim3 grid((unsigned)(p.mask ? p.n_slots : p.B), 2), block((c.W + (GRAD ? 2 + c.G + c.PW : 1)) * 32);
 #define SSAK_LAUNCH4(KK, CC, ZZ, SP)                                                           \
     {                                                                                          \
         auto kern = ctc_lattice_kernel<KK, GRAD, CC, ZZ, SP>;                                  \
@@ -1573,7 +1574,7 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
     wc.stages = stages;
     const size_t smem_bytes = (size_t)fwd_wave_smem(wc.W, wc.stages, wc.chunk, wc.slot_bytes).total;
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)p.B, 2), block((wc.W + 1) * 32);
+    dim3 grid((unsigned)(p.mask ? p.n_slots : p.B), 2), block((wc.W + 1) * 32);
 #define SSAK_FW4(KK, CC, ZZ, SS)                                                               \
     {                                                                                          \
         auto kern = ctc_forward_wave_kernel<KK, CC, ZZ, SS>;                                   \
@@ -1616,8 +1617,8 @@ static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row
     const int K = lin_k(Lmax, V < 0 ? 1 : V, B);
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
     // abort word (+ the slot counter of the throughput mode at +4), then nan_flag[B], then the throughput kernels'
-    // flags[B] and slot[B]: one memset
-    w.abort_word = o; o += 256 + 3 * align_up((size_t)B * sizeof(int), 256);
+    // flags[B], slot[B] and slot_b[n_slots <= B]: one memset
+    w.abort_word = o; o += 256 + 4 * align_up((size_t)B * sizeof(int), 256);
     w.lin_fr = w.lin_ck = o;
     if (K > 0) {
         const size_t ck_row = (size_t)lin32::ck_row_elems(K);
@@ -1663,6 +1664,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     p->nan_flag = reinterpret_cast<int *>(ws + w.abort_word + 256);
     p->mask = nullptr;
     p->mask_bits = 1;
+    p->slot_b = nullptr; p->slot_count = nullptr; p->n_slots = 0;
     p->join_keeps_nll = 0;
     p->slot = nullptr;
     p->NCH = tab_slots(T);
@@ -1709,6 +1711,7 @@ static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin32::P
     q->nll2 = p.nll2; q->nll = p.nll;
     q->flags = reinterpret_cast<int *>(ws + w.abort_word + 256 + align_up((size_t)p.B * sizeof(int), 256));
     q->slot = reinterpret_cast<int *>(ws + w.abort_word + 256 + 2 * align_up((size_t)p.B * sizeof(int), 256));
+    q->slot_b = reinterpret_cast<int *>(ws + w.abort_word + 256 + 3 * align_up((size_t)p.B * sizeof(int), 256));
     q->slot_counter = reinterpret_cast<int *>(ws + w.abort_word + 4);
     q->n_slots = saved ? (int)lin_slots(p.B) : (int)p.B;   // (no rows are stored without save_for_backward)
     q->grad_out = p.grad_out; q->grad = p.grad; q->gst = p.gst; q->gsb = p.gsb; q->zero_inf = p.zero_inf;
@@ -1754,7 +1757,7 @@ extern "C" int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_
 extern "C" int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len, int32_t logits) {
     // throughput mode: memset excluded; forward: [row lse] lin32 fwd + lin32 join + masked log-domain fwd + join;
     // backward: lin32 bwd + masked log-domain fwd + join + bwd.  Log-domain mode: fwd + join, bwd.
-    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B) > 0 ? 8 : 3);
+    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B) > 0 ? 9 : 3);
 }
 
 static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,
@@ -1775,7 +1778,7 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         if (rc != SSAK_OK) return rc;
     }
     {
-        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + 3 * align_up((size_t)B * sizeof(int), 256), s);
+        cudaError_t e = cudaMemsetAsync(p.abort_word, 0, 256 + 4 * align_up((size_t)B * sizeof(int), 256), s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
     }
     // Throughput kernels first (no stored lattice); the utterances they hand back (flags, see ctc_lin32.cu) are
@@ -1787,11 +1790,12 @@ static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t
         p.mask = q.flags;
         p.mask_bits = 1;
         p.slot = q.slot;
+        p.slot_b = q.slot_b; p.slot_count = q.slot_counter; p.n_slots = q.n_slots;
     }
     rc = launch_forward_wave(p, s);
     if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
     if (rc != SSAK_OK) return rc;
-    ctc_join_kernel<<<(unsigned)B, 256, 0, s>>>(p);
+    ctc_join_kernel<<<(unsigned)(p.mask ? p.n_slots : B), 256, 0, s>>>(p);
     return check_launch();
 }
 
@@ -1818,15 +1822,19 @@ static int backward_impl(const float *grad_out, const float *x, int64_t T, int64
         // lattices were never stored), then the log-domain backward for them and for the ones forward() handed back
         p.mask = q.flags;
         p.slot = q.slot;
+        p.slot_b = q.slot_b; p.slot_count = q.slot_counter; p.n_slots = q.n_slots;
         p.mask_bits = 2;
         p.join_keeps_nll = 1;
         rc = launch_forward_wave(p, s);
         if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
         if (rc != SSAK_OK) return rc;
-        ctc_join_kernel<<<(unsigned)B, 256, 0, s>>>(p);
+        ctc_join_kernel<<<(unsigned)(p.mask ? p.n_slots : B), 256, 0, s>>>(p);
         rc = check_launch();
         if (rc != SSAK_OK) return rc;
         p.mask_bits = 3;
+        rc = launch_lattice<true>(p, s);
+        if (rc != SSAK_OK) return rc;
+        return lin32::launch_orphans(q, s);
     }
     return launch_lattice<true>(p, s);
 }

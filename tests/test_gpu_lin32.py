@@ -218,6 +218,25 @@ def test_lin32_tiny_loss():
     _check(lp, tg, il, tl, "none", True)
 
 
+def test_lin32_more_hand_backs_than_row_blocks_is_loud():
+    """Row blocks for handed-back utterances exist for max(32, B/8) of them: beyond that the likelihood and the gradient
+    are NaN (never a silently wrong number); the ones that got a block still match torch."""
+    from ssak_b200.synth import ctc_batch
+    lp, tg, il, tl = ctc_batch(40, 60, 12, 3, 10, 905, Tmin=40)
+    lp = lp * 0.5 + 1.0                                   # 'log-probabilities' above 0: every utterance is handed back
+    fl, nll, grad = _path_flags(lp, tg, il, tl)
+    assert int((fl & 4).ne(0).sum()) == 8 and int((fl == 1).sum()) == 32, fl
+    y = lp.double().requires_grad_(True)
+    ref = F.ctc_loss(y, tg, il, tl, 0, "none", True)
+    ref.sum().backward()
+    for b in range(40):
+        if fl[b] & 4:
+            assert torch.isnan(nll[b]) and torch.isnan(grad[: int(il[b]), b]).all() and (grad[int(il[b]):, b] == 0).all()
+        else:
+            assert abs(float(nll[b]) - float(ref[b])) <= 1e-4 * abs(float(ref[b]))
+            assert (grad[:, b].double() - y.grad[:, b]).abs().max() <= 1e-3
+
+
 def test_log_domain_kernels_still_default_elsewhere_and_on_request(monkeypatch):
     """V > 128 or targets beyond 415 labels stay on the log-domain kernels; SSAK_CTC_LIN32=0 forces them."""
     from ssak_b200.synth import ctc_batch

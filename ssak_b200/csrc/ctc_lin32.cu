@@ -45,6 +45,8 @@ namespace ssak {
 namespace lin32 {
 
 constexpr int TOP = 96;             // re-scaled lane maximum ~ 2^TOP
+constexpr int DEAD_BIT = 1 << 30;   // marker in a checkpoint's exponent word: the lane's states were dropped (all zero)
+constexpr int ZDROP = 500;          // checkpoints drop lanes this many bits below the row's largest state
 constexpr int WIN = 12;             // hysteresis of the re-scaling: lane maxima stay within [2^(TOP-WIN), 2^(TOP+4))
 constexpr int DMAX = 16;            // a lane's exponent is at most DMAX below its upstream neighbour's
 constexpr int EZERO = -(1 << 24);   // exponent wish of a lane that holds only zeros
@@ -157,10 +159,11 @@ __device__ __forceinline__ float carry_in(const float (&l)[K], const float f) {
 // Returns false when a state is inf / NaN.
 template <int K, int D>
 __device__ __forceinline__ bool rescale(float (&a)[K], float (&l)[K], int &E, float &f, const int lane, const int Emin,
-                                        const bool force) {
+                                        const bool force, unsigned *hmax = nullptr) {
     unsigned h = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) h = max(h, max(__float_as_uint(a[k]), __float_as_uint(l[k])));   // states are >= 0
+    if (hmax) *hmax = h;
     const int e_own = (int)(h >> 23) - 127;
     // hysteresis: a lane whose maximum sits in [2^(TOP-WIN), 2^(TOP+4)) and whose exponent respects its lower bound
     // needs nothing; most chunks end here (peaky emissions move a lane by ~0.3 bits per frame)
@@ -180,6 +183,7 @@ __device__ __forceinline__ bool rescale(float (&a)[K], float (&l)[K], int &E, fl
         a[k] *= fac;
         l[k] *= fac;
     }
+    if (hmax) *hmax = __float_as_uint(__uint_as_float(h) * fac);   // (the lane maximum after the shift)
     E = v;
     const int vu = D ? __shfl_down_sync(FULL, v, 1) : __shfl_up_sync(FULL, v, 1);
     f = lane == (D ? 31 : 0) ? 0.f : pow2f(vu - v);
@@ -207,6 +211,33 @@ __device__ __forceinline__ void store_row(float *row, const float (&a)[K], const
     }
     __stcs(reinterpret_cast<int *>(row) + 2 * K * 32 + lane, E);
 }
+// Checkpoints only.  A lane whose largest state is more than 2^ZDROP below the row's largest cannot carry posterior
+// mass unless the other direction favours it by that factor (the self-check of backward() watches for exactly
+// that): it is ZEROED -- in the registers too, so that forward() and the recomputation of backward() continue from
+// the same row -- and only its exponent word is written, with bit 30 flipped as the marker (|E| < 2^29).  With peaky emissions ~3/4 of the
+// lanes go this way: the checkpoint stream, which bounded forward() (0.69 ms with, 0.39 ms without it at B = 1024),
+// shrinks accordingly.
+template <int K>
+__device__ __forceinline__ void store_checkpoint(float *row, float (&a)[K], float (&l)[K], float ebp, int E, unsigned h,
+                                                 int lane, bool live) {
+    const int x = h ? E + (int)(h >> 23) - 127 : EZERO;          // exponent of my largest state
+    const int xmax = __reduce_max_sync(FULL, x);
+    const bool dead = x < xmax - ZDROP;
+    if (dead) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) a[k] = l[k] = 0.f;
+    }
+    if (!live) return;
+    if (!dead) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            __stcs(row + k * 32 + lane, a[k] * ebp);
+            __stcs(row + (K + k) * 32 + lane, l[k]);
+        }
+    }
+    // (the exponent itself is still needed: the lane keeps receiving its neighbour's carry in that scale)
+    __stcs(reinterpret_cast<int *>(row) + 2 * K * 32 + lane, dead ? E ^ DEAD_BIT : E);
+}
 template <int K>
 __device__ __forceinline__ void load_row(const float *row, float (&a)[K], float (&l)[K], int &E, int lane, bool live) {
 #pragma unroll
@@ -215,6 +246,17 @@ __device__ __forceinline__ void load_row(const float *row, float (&a)[K], float 
         l[k] = live ? __ldcs(row + (K + k) * 32 + lane) : 0.f;
     }
     E = live ? __ldcs(reinterpret_cast<const int *>(row) + 2 * K * 32 + lane) : EZERO;
+}
+// a checkpoint lane that was dropped (exponent word with bit 30 flipped) left stale values in its slots: discard them
+// and restore the exponent.  Called where the row is first USED -- the loads of load_row are issued a tile earlier
+// and must not be waited for there.
+template <int K>
+__device__ __forceinline__ void drop_dead(float (&a)[K], float (&l)[K], int &E) {
+    if (((E >> 30) ^ (E >> 31)) & 1) {
+        E ^= DEAD_BIT;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a[k] = l[k] = 0.f;
+    }
 }
 
 struct Chain {
@@ -355,8 +397,9 @@ __global__ void __launch_bounds__(32, FWD_WARPS) lin32_forward_kernel(const Para
                 ebp = eb;
             }
             if (nr == C) {
-                ok = rescale<K, D>(as, ls, E, f, lane, EZERO, false) && ok;
-                if (p.save) store_row<K>(ck_dir + (int64_t)(n + 1) * p.ck_row, as, ls, ebp, E, lane, live);
+                unsigned h;
+                ok = rescale<K, D>(as, ls, E, f, lane, EZERO, false, &h) && ok;
+                if (p.save) store_checkpoint<K>(ck_dir + (int64_t)(n + 1) * p.ck_row, as, ls, ebp, E, h, lane, live);
             }
         }
         cp_async_wait<0>();
@@ -582,6 +625,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
             __syncwarp();
             // ---- the live direction moves into this tile's scaling; the tile scale 2^(EL + ER - Ep) / mantissa(P)
             //      must be representable: EL >= GMIN - ER + Ep wherever DR holds anything
+            drop_dead<K>(ra, rl, ER);                           // (first use of the checkpoint fetched a tile ago)
             {
                 const int Emin = ER > EZERO / 2 ? GMIN - ER + Ep : EZERO;
                 bad = !rescale<K, DL>(la, ll, EL, fL, lane, Emin, n == 0) || bad;

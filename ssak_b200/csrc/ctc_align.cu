@@ -54,6 +54,10 @@ struct AlignParams {
     AlignCfg cfg;
 };
 
+// throughput kernel (align_lane_kernel): frames per chunk, chunks of emission rows in shared memory
+constexpr int LANE_C = 4, LANE_DEPTH = 4;
+__host__ __device__ inline int lane_ring_bytes(int V) { return LANE_DEPTH * LANE_C * (32 * (V <= 64 ? 2 : 4) + 4) * 4; }
+
 static bool choose_barrier_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
     const int64_t P = Lmax + 1;
     c->S = 1;
@@ -148,7 +152,26 @@ static bool choose_wave_ring(int64_t B, int V, AlignCfg *c) {
     return stages >= c->W + 2;
 }
 
-static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
+// Throughput shape (align_lane_kernel): the decision bits are laid out as align_wave_kernel<8> with W = KL / 8
+// "virtual" warps, so the back-trace kernel and the workspace layout need nothing new.  V < 0: not known
+// (workspace query).  SSAK_ALIGN_LANE=1 forces it wherever it is valid, =0 disables it.
+static bool choose_lane_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c) {
+    const int mode = align_env_int("SSAK_ALIGN_LANE", -1);
+    if (mode == 0 || Lmax + 1 > 512 || V > 128 || B > 0x7fffffff) return false;
+    if (mode < 0 && B < 2 * (int64_t)device_sm_count()) return false;
+    c->K = 8;
+    c->W = Lmax + 1 <= 256 ? 1 : 2;
+    c->S = 1;
+    c->NW = 8 * c->W;
+    c->wave = 2;
+    c->chunk = LANE_C;
+    c->stages = LANE_DEPTH;
+    c->slot_bytes = 0;
+    return true;
+}
+
+static bool choose_align_cfg(int64_t Lmax, int64_t B, int V, AlignCfg *c, bool allow_lane = true) {
+    if (allow_lane && choose_lane_cfg(Lmax, B, V, c)) return true;
     if (align_env_int("SSAK_ALIGN_WAVE", 1) != 0 && choose_wave_shape(Lmax, B, c) && choose_wave_ring(B, V, c))
         return true;
     return choose_barrier_cfg(Lmax, B, V, c);
@@ -164,6 +187,7 @@ static int align_max_nw(int64_t Lmax, int64_t B, int *S_out) {
         nw = w.NW > nw ? w.NW : nw;
         *S_out = w.S;
     }
+    if (choose_lane_cfg(Lmax, B, 1, &a)) nw = a.NW > nw ? a.NW : nw;
     return nw;
 }
 
@@ -825,6 +849,151 @@ __global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p)
     if (ownsL) p.t_start[b] = best_t;
 }
 
+// ------------------------------------------------------------------------------ throughput forward kernel
+// Batches that fill the GPU (B >= 2 x SMs) with targets up to 511 tokens and V <= 128: ONE WARP per utterance,
+// one CTA per warp (the block scheduler hands an SM a new utterance the moment one finishes).  Lane l holds the KL
+// (8 or 16) CONSECUTIVE trellis states [KL l, KL l + KL) in registers, a frame needs one shuffle (the last state of
+// lane l-1) and nothing else: no seams, no polling, no mbarriers, no producer warp.  The warp stages its own emission
+// rows with cp.async (no registers, no scoreboard; completion counted per commit group) into a ring of
+// LANE_DEPTH chunks of 4 frames, column 0 comes from align_col0_kernel one chunk ahead.  Same arithmetic and the
+// same decision-bit layout as align_wave_kernel<8> (lane entries of 16 bits, 16 states per 32-bit word: a lane of
+// 16 states writes one word per frame, a coalesced 128-byte row), so align_backtrace_kernel<8> reads it unchanged.
+
+template <int KL, int NV>
+__global__ void __launch_bounds__(32, 16) align_lane_kernel(const AlignParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int RS = 32 * NV + 4, C = LANE_C, DEPTH = LANE_DEPTH;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+    int Tb = p.em_len[b];
+    Tb = Tb < 0 ? 0 : (Tb > (int)p.Tmax ? (int)p.Tmax : Tb);
+    int L = p.tok_len[b];
+    L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
+    if (L == 0 || Tb == 0) {  // reference: empty back-track loop -> "Failed to align"
+        if (lane == 0) p.t_start[b] = 0;
+        return;
+    }
+    const int V = p.V;
+    const float *em_b = p.em + (int64_t)b * p.sb;
+    const int32_t *tk = p.tokens + (int64_t)b * p.tok_stride;
+    float *ring = reinterpret_cast<float *>(smem);
+    const float *col0 = p.col0_eff + (int64_t)b * p.Tmax;
+
+    const int sbase = lane * KL;
+    int tok_off[KL];
+    float v[KL];
+    unsigned ownL[KL];       // all ones for the one register that holds state L
+#pragma unroll
+    for (int k = 0; k < KL; ++k) {
+        const int j = sbase + k;
+        int tkn = p.blank;
+        if (j >= 1 && j <= L) {
+            tkn = tk[j - 1];
+            tkn = tkn < 0 ? 0 : (tkn >= V ? V - 1 : tkn);
+        }
+        tok_off[k] = 4 * tkn;
+        v[k] = j == 0 ? (L >= Tb + 1 ? INF : 0.f) : -INF;  // trellis row 0 (:35, :41, :42)
+        ownL[k] = j == L ? 0xffffffffu : 0u;
+    }
+    const bool ownsL = L >= sbase && L < sbase + KL;
+    float best = -INF;  // trellis[0, L] with L >= 1
+    int best_t = 0;
+    const int blank_off = 4 * p.blank;
+    const unsigned zero_m = lane == 0 ? 0xffffffffu : 0u;  // the thread that owns trellis column 0
+    auto sel = [](unsigned m, float a, float bb) {
+        return __int_as_float((__float_as_int(a) & m) | (__float_as_int(bb) & ~m));
+    };
+    // decision bits: 16-bit entries (bit k: changed > stayed of the entry's k-th state, bit 8+k: changed < stayed)
+    using bp_t = typename std::conditional<KL == 16, uint32_t, uint16_t>::type;
+    constexpr int64_t bp_row = 32;                          // stores per frame (one per lane)
+    bp_t *bp_ptr = reinterpret_cast<bp_t *>(p.bp) + (int64_t)b * p.Tmax * bp_row + lane;
+
+    auto issue = [&](int n) {                               // chunk n -> ring stage n % DEPTH (empty group beyond the end)
+        const int t0 = n * C;
+        const float *src = em_b + (int64_t)t0 * p.st + lane;
+        float *dst = ring + (size_t)(n % DEPTH) * C * RS + lane;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            if (t0 + i < Tb) {
+#pragma unroll
+                for (int jv = 0; jv < NV; ++jv)
+                    if (lane + 32 * jv < V)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + i * RS + 32 * jv)),
+                                     "l"(src + 32 * jv) : "memory");
+            }
+            src += p.st;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunks = (Tb + C - 1) / C;
+#pragma unroll
+    for (int n = 0; n < DEPTH - 1; ++n) issue(n);
+    float c0_next = lane < C && lane < Tb ? __ldg(col0 + lane) : 0.f;   // column 0 of the rows of chunk 0, frame f in lane f
+    for (int n = 0; n < nchunks; ++n) {
+        const int t0 = n * C, nf = Tb - t0 < C ? Tb - t0 : C;
+        __syncwarp();                                       // every lane is done with the previous chunk's rows
+        issue(n + DEPTH - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        __syncwarp();
+        const float c0 = c0_next;
+        c0_next = (lane < C && t0 + C + lane < Tb) ? __ldg(col0 + t0 + C + lane) : 0.f;
+        const unsigned char *rows = reinterpret_cast<const unsigned char *>(ring + (size_t)(n % DEPTH) * C * RS);
+        // (not unrolled over the frames: the body is ~10 instructions x KL states already)
+#pragma unroll 1
+        for (int f = 0; f < nf; ++f) {
+            const unsigned char *row = rows + f * (RS * 4);
+            const float eb = *reinterpret_cast<const float *>(row + blank_off);
+            const float xin = __shfl_sync(FULL, c0, f);     // column 0 of this row (:37 / :39 / :42)
+            float prev = __shfl_up_sync(FULL, v[KL - 1], 1);
+            unsigned ng = 0, nl = 0, ng2 = 0, nl2 = 0;
+            float stayed_k[KL], chg_k[KL];
+#pragma unroll
+            for (int k = 0; k < KL; ++k) {
+                const float ek = *reinterpret_cast<const float *>(row + tok_off[k]);
+                // max(v+eb, v+ek) == v + max(eb, ek) bit for bit (rounding is monotonic): :48-49, :96-99
+                const float stayed = v[k] + fmaxf(eb, ek);
+                const float chg = prev + ek;               // :51
+                prev = v[k];
+                float nv = fmaxf(stayed, chg);
+                if (k == 0) nv = sel(zero_m, xin, nv);
+                v[k] = nv;
+                stayed_k[k] = stayed;
+                chg_k[k] = chg;
+            }
+            // sign bits as decision bits (see align_wave_kernel): a tie gives +0 both ways, (-inf) - (-inf) the positive
+            // canonical NaN, i.e. no bit, exactly like the comparisons
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                ng = __funnelshift_l(__float_as_uint(stayed_k[k] - chg_k[k]), ng, 1);
+                nl = __funnelshift_l(__float_as_uint(chg_k[k] - stayed_k[k]), nl, 1);
+            }
+            if (KL == 16) {
+#pragma unroll
+                for (int k = 15; k >= 8; --k) {
+                    ng2 = __funnelshift_l(__float_as_uint(stayed_k[k] - chg_k[k]), ng2, 1);
+                    nl2 = __funnelshift_l(__float_as_uint(chg_k[k] - stayed_k[k]), nl2, 1);
+                }
+                *bp_ptr = (bp_t)((ng | (nl << 8)) | ((ng2 | (nl2 << 8)) << 16));
+            } else {
+                *bp_ptr = (bp_t)(ng | (nl << 8));
+            }
+            bp_ptr += bp_row;
+            {   // first maximum of trellis[:, L] (:88); only the owner's comparison can be true
+                unsigned vb = 0;
+#pragma unroll
+                for (int k = 0; k < KL; ++k) vb |= __float_as_uint(v[k]) & ownL[k];
+                const float vl = __uint_as_float(vb);
+                const bool up = ownsL && vl > best;
+                best = up ? vl : best;
+                best_t = up ? t0 + f + 1 : best_t;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (ownsL) p.t_start[b] = best_t;
+}
+
 // Back-trace (:79-123) + merge_repeats (:141-157).  Warp 0 walks the "changed > stayed" bits from (t_start, L),
 // 32 frames per round: lane i fetches the bits of frame t-1-i for the states [j-63, j] (issued one round ahead,
 // the window covers wherever the current round ends) and compacts them into one 32-state window word; the walk
@@ -1089,12 +1258,15 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
         return SSAK_ERR_INVALID_ARGUMENT;
     if (first_as_garbage && !col0) return SSAK_ERR_INVALID_ARGUMENT;
     AlignParams p;
-    if (!choose_align_cfg(Lmax, B, (int)V, &p.cfg)) return SSAK_ERR_UNSUPPORTED;
+    // (the throughput kernel does not dump the trellis: a debugging request takes the other kernels)
+    if (!choose_align_cfg(Lmax, B, (int)V, &p.cfg, trellis_dump == nullptr)) return SSAK_ERR_UNSUPPORTED;
     if (workspace_bytes < ssak_align_workspace_bytes(B, Tmax, Lmax)) return SSAK_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
-    const bool wave = p.cfg.wave != 0;
-    const size_t smem_bytes = wave ? (size_t)wave_smem(p.cfg.W, p.cfg.stages, p.cfg.chunk, p.cfg.slot_bytes).total
-                                   : align_smem_bytes(p.cfg);
+    const bool lane_mode = p.cfg.wave == 2;
+    const bool wave = p.cfg.wave == 1;
+    const size_t smem_bytes = lane_mode ? (size_t)lane_ring_bytes((int)V)
+                              : wave ? (size_t)wave_smem(p.cfg.W, p.cfg.stages, p.cfg.chunk, p.cfg.slot_bytes).total
+                                     : align_smem_bytes(p.cfg);
     if (smem_bytes > 227 * 1024) return SSAK_ERR_UNSUPPORTED;
     p.em = emissions; p.B = B; p.Tmax = Tmax; p.V = (int)V; p.sb = em_stride_b; p.st = em_stride_t;
     p.tokens = tokens; p.tok_stride = tok_stride; p.Lmax = (int)Lmax;
@@ -1117,7 +1289,19 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
         if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }
     }
     bool wave_launched = false;
-    if (wave && B <= 65535) {
+    if (lane_mode) {
+        align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != SSAK_OK) return rc;
+        if (p.cfg.W == 2) {
+            if (V <= 64) align_lane_kernel<16, 2><<<(unsigned)B, 32, smem_bytes, s>>>(p);
+            else align_lane_kernel<16, 4><<<(unsigned)B, 32, smem_bytes, s>>>(p);
+        } else {
+            if (V <= 64) align_lane_kernel<8, 2><<<(unsigned)B, 32, smem_bytes, s>>>(p);
+            else align_lane_kernel<8, 4><<<(unsigned)B, 32, smem_bytes, s>>>(p);
+        }
+        wave_launched = true;
+    } else if (wave && B <= 65535) {
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned)p.cfg.S, (unsigned)B);
         lc.blockDim = dim3((p.cfg.W + 2) * 32);   // recursion warps, emission producer, column-0 warp

@@ -207,6 +207,34 @@ def test_align_kernel_shapes_agree(mode, monkeypatch):
     _check_batch(em, toks, el, tl, fag=True, tag=f"{mode}/ragged")
 
 
+@pytest.mark.parametrize("kind", ["random", "tie", "planted"])
+@pytest.mark.parametrize("fag", [False, True])
+def test_align_throughput_kernel(kind, fag, monkeypatch):
+    """align_lane_kernel (one warp per utterance; the default from B = 2 x SMs on, forced here): 8 and 16 states per
+    lane, V up to 128, ragged lengths, L > T, strided emissions -- bit-exact like the other kernels."""
+    from ssak_b200.synth import align_batch
+    monkeypatch.setenv("SSAK_ALIGN_LANE", "1")
+    total = 0
+    for seed, (B, T, V, Lmin, Lmax) in enumerate([(9, 60, 7, 1, 20), (6, 200, 50, 10, 70), (5, 97, 33, 1, 96),
+                                                   (4, 300, 50, 100, 140), (3, 700, 128, 250, 255), (3, 900, 50, 256, 400),
+                                                   (2, 1100, 97, 480, 511), (40, 90, 50, 5, 40)]):
+        em, toks, el, tl = align_batch(B, T, V, Lmin, Lmax, 300 + seed, Tmin=max(1, T // 2), kind=kind)
+        total += _check_batch(em, toks, el, tl, 0, fag, tag=f"lane/{kind}/{fag}/{seed}")
+    assert total > 0
+    if not fag:
+        em, toks, el, tl = align_batch(6, 40, 9, 1, 45, 7, kind=kind, blank=4)
+        el = torch.tensor([40, 3, 40, 12, 40, 40], dtype=torch.int32)
+        tl = torch.tensor([45, 5, 40, 12, 1, 0], dtype=torch.int32)
+        res = _run(em, toks, el, tl, blank=4)
+        assert res.status.cpu().tolist()[:2] == [1, 1] and int(res.status[5]) == 1
+        _check_batch(em, toks, el, tl, blank=4, res=res, tag="lane/edge")
+        import ssak_b200
+        em, toks, el, tl = align_batch(4, 150, 50, 20, 60, 21, Tmin=100, kind=kind)
+        em_tbv = em.transpose(0, 1).contiguous().cuda()
+        res = ssak_b200.forced_align(em_tbv.transpose(0, 1), toks, el, tl)
+        _check_batch(em, toks, el, tl, res=res, tag="lane/strided")
+
+
 def test_compute_alignments_batched_front_end():
     """compute_alignment from the emission onwards (align_transcriptions.py:310-402), batched: character ->
     token mapping with the loose fall-backs, sentinel character, word regrouping and score aggregation."""

@@ -7,26 +7,31 @@
 // the frames [0,m), chain (b,1) runs beta over [m,T_b), a join kernel forms log P; the backward call continues both
 // recursions over the other half, fused with the gradient.  What differs:
 //   * LINEAR domain: per (blank,label) position and frame  A = b + carry;  t = l + b + skip*carry;  b' = A*y_blank;
-//     l' = t*y_label -- 2 FADD + 1 FFMA + 2 FMUL and one shared-memory gather, NO transcendental.  The emissions
-//     y = exp(lp) are formed once per (frame, vocabulary column) by the warp itself (one MUFU.EX2 per column).
+//     l' = t*y_label -- with the blank state carried before its emission 3 FFMA + 1 FMUL and one shared-memory gather,
+//     NO transcendental.  The emissions y = exp(lp) are formed once per (frame, vocabulary column) by the warp itself
+//     (cp.async brings the raw rows into a shared-memory ring, one MUFU.EX2 per column converts them in place).
 //   * ONE WARP owns the whole lattice row of its chain: lane j holds the K <= 13 consecutive positions
 //     [jK, jK+K) in registers, a frame needs one shuffle (the lane-to-lane carry) and nothing else -- no barrier, no
-//     cross-warp exchange, no mbarrier, no polling.  Warps are independent workers; a CTA is just 10-16 of them, so
-//     the SM's four schedulers always have ready warps: this is the throughput regime (hundreds of utterances), the
-//     opposite of the latency-tuned kernels of ctc_loss.cu.
+//     cross-warp exchange, no mbarrier, no polling.  Warps are independent workers, ONE PER CTA (the block scheduler
+//     hands an SM a new chain the moment one finishes; 12-16 are resident per SM), so the SM's four schedulers always
+//     have ready warps: this is the throughput regime (hundreds of utterances), the opposite of the latency-tuned
+//     kernels of ctc_loss.cu.
 //   * BLOCK FLOATING POINT: fp32 mantissas with one integer exponent PER LANE.  Every C = 4 frames each lane moves
 //     its largest state to ~2^TOP by an exact power of two; the lane exponents go through a decaying prefix-max
 //     scan along the direction of flow (a lane is at most DMAX bits below its upstream neighbour, so the inflow
 //     cannot overflow it), and the carry crossing a lane boundary is multiplied by 2^(E_up - E_me).  States more than
-//     ~2^222 below their LANE's maximum flush to zero (-ftz): harmless unless such a state carries posterior mass,
+//     ~2^210 below their LANE's maximum flush to zero (-ftz): harmless unless such a state carries posterior mass,
 //     which needs the forward and the backward partial likelihoods of one lane to disagree by that factor (garbage
-//     transcripts).  Rounding is relative (no cancellation): the gradient is ~50x closer to the fp64 truth than any
-//     fp32 log-domain recursion (tools/proto_bfp.py: 2e-6 vs 1e-4 at T = 1500).
+//     transcripts).  Re-scaling has hysteresis (lane maxima stay in [2^84, 2^100)).  Rounding is relative (no
+//     cancellation): the gradient is 2e-7 .. 4e-7 from the fp64 truth at T = 1500, ~300x closer than an fp32 log-domain
+//     recursion (tools/proto_bfp.py is the numpy prototype the constants were chosen with).
 //   * NOTHING of the lattice is written per frame.  forward() stores one CHECKPOINT row every C frames (1 B per
-//     lattice cell); backward() recomputes the C rows of a tile from its checkpoint into a shared-memory tile
-//     private to the warp (already multiplied by 2^(E_live + E_other) / P), runs the live direction over the tile
-//     and multiplies: posterior = live state before its emission x tile entry.  Label posteriors go to a
-//     label-sorted buffer, the warp then writes the gradient rows of the tile's frames,
+//     lattice cell; lanes far below the row maximum are dropped); backward() recomputes the C rows of a tile from its
+//     checkpoint into a shared-memory tile private to the warp (already in posterior units: the recomputation starts
+//     from the checkpoint times 2^(E_live + E_other - E_P + 30) / mantissa(P)), runs the live direction over the tile
+//     and multiplies: posterior = live state before its emission x tile entry.  Label posteriors are added to a
+//     per-warp mass vector in 2^-30 fixed point (shared-memory integer atomics: the sum does not depend on their
+//     order), the blank ones through an integer warp reduction; the warp then writes the frame's gradient row,
 //         grad[t,b,v] = (y[v] - mass[v] / sum_v mass[v]) * grad_out[b],
 //     normalised by the frame's own total, so the common-mode drift of alpha_t beta_t against P cancels.
 //   * SELF-CHECK and hand-back.  sum_s posterior_t(s) = 1 at every frame; states lost to the fp32 range can only

@@ -81,7 +81,7 @@ SSAK_API int ssak_b200_last_cuda_error(void);
 SSAK_API size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t max_target_len,
                                               int save_for_backward);
 /* The same with the vocabulary size known.  For V <= 128, max_target_len <= 415 and batches that fill the GPU
- * (B >= 2 x SM count) the throughput kernels run (one warp per utterance and direction, no stored lattice:
+ * (B >= 1.5 x SM count) the throughput kernels run (one warp per utterance and direction, no stored lattice:
  * checkpoints every 4 frames), and the workspace is ~3x smaller than what the V-agnostic query above must reserve.
  * Either size is accepted by forward / backward. */
 SSAK_API size_t ssak_ctc_loss_workspace_bytes_v(int64_t T, int64_t B, int64_t V, int64_t max_target_len,

@@ -1595,13 +1595,14 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
 
 // Throughput kernels (ctc_lin32.cu: one warp per (utterance, direction), linear domain, block floating point, no
 // stored lattice): used when they cover the shape (V <= 128, targets up to 415 labels) AND the batch fills the GPU --
-// a chain is one warp, so below ~2 chains per SM sub-partition the latency-tuned log-domain kernels (several warps
-// per utterance) are faster (B = 64: 0.42 vs 1.1 ms; B = 256 ragged: 1.15 vs ~1.05 ms; B = 1024: 4.1 vs 2.8 ms).
+// a chain is one warp, so below ~3 chains per SM the latency-tuned log-domain kernels (several warps per utterance)
+// are faster (B = 64: 0.42 vs 1.1 ms; B = 256 ragged: 1.15 vs 1.06 ms of kernels, and 1.5e-4 vs 7e-7 of gradient
+// error on unpeaked emissions; B = 1024: 4.1 vs 2.4 ms).
 // SSAK_CTC_LIN32=1 forces them wherever they are valid, =0 disables them.
 static int lin_k(int64_t Lmax, int64_t V, int64_t B) {
     const int mode = env_int("SSAK_CTC_LIN32", -1);
     if (mode == 0) return 0;
-    if (mode < 0 && B < 2 * (int64_t)device_sm_count()) return 0;
+    if (mode < 0 && 2 * B < 3 * (int64_t)device_sm_count()) return 0;   // B >= 1.5 x SMs (222 on a B200)
     return lin32::lanes_k(Lmax, V);
 }
 // row blocks kept for utterances the throughput kernels hand back to the log-domain ones (fp32 range, see

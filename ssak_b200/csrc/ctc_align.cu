@@ -895,6 +895,8 @@ __global__ void __launch_bounds__(32, 16) align_lane_kernel(const AlignParams p)
         tok_off[k] = 4 * tkn;
         v[k] = j == 0 ? (L >= Tb + 1 ? INF : 0.f) : -INF;  // trellis row 0 (:35, :41, :42)
         ownL[k] = j == L ? 0xffffffffu : 0u;
+        // (opaque: otherwise the compiler re-derives the masks as predicates, an ISETP + SEL pair per state and frame)
+        asm volatile("" : "+r"(ownL[k]));
     }
     const bool ownsL = L >= sbase && L < sbase + KL;
     float best = -INF;  // trellis[0, L] with L >= 1

@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(320, 1) align_wave_kernel(const AlignParams p)
 // (8 or 16) CONSECUTIVE trellis states [KL l, KL l + KL) in registers, a frame needs one shuffle (the last state of
 // lane l-1) and nothing else: no seams, no polling, no mbarriers, no producer warp.  The warp stages its own emission
 // rows with cp.async (no registers, no scoreboard; completion counted per commit group) into a ring of
-// LANE_DEPTH chunks of 4 frames, column 0 comes from align_col0_kernel one chunk ahead.  Same arithmetic and the
+// LANE_DEPTH chunks of 4 frames and computes column 0 itself, 32 rows at a time.  Same arithmetic and the
 // same decision-bit layout as align_wave_kernel<8> (lane entries of 16 bits, 16 states per 32-bit word: a lane of
 // 16 states writes one word per frame, a coalesced 128-byte row), so align_backtrace_kernel<8> reads it unchanged.
 
@@ -878,8 +878,6 @@ __global__ void __launch_bounds__(32, 16) align_lane_kernel(const AlignParams p)
     const float *em_b = p.em + (int64_t)b * p.sb;
     const int32_t *tk = p.tokens + (int64_t)b * p.tok_stride;
     float *ring = reinterpret_cast<float *>(smem);
-    const float *col0 = p.col0_eff + (int64_t)b * p.Tmax;
-
     const int sbase = lane * KL;
     int tok_off[KL];
     float v[KL];
@@ -931,22 +929,44 @@ __global__ void __launch_bounds__(32, 16) align_lane_kernel(const AlignParams p)
     const int nchunks = (Tb + C - 1) / C;
 #pragma unroll
     for (int n = 0; n < DEPTH - 1; ++n) issue(n);
-    float c0_next = lane < C && lane < Tb ? __ldg(col0 + lane) : 0.f;   // column 0 of the rows of chunk 0, frame f in lane f
+    // Column 0 of the trellis (:37 / :39 / :42), 32 rows at a time, row 32 r + i + 1 in lane i: the fp64 running sum
+    // of the blank column rounded to fp32 per element (torch.cumsum on the CPU) -- strictly sequential, so the doubles
+    // are broadcast by independent shuffles and only the chain of adds is serial -- or the caller's vector
+    // (first_as_garbage), with the +inf sentinel.  The next block's inputs are fetched a block ahead.
+    const float *c0src = p.garbage && p.col0 ? p.col0 + (int64_t)b * p.Tmax : nullptr;
+    const float *blank_col = em_b + p.blank;
+    auto c0_load = [&](int tt) -> float { return tt < Tb ? (c0src ? __ldg(c0src + tt) : __ldg(blank_col + (int64_t)tt * p.st)) : 0.f; };
+    double c0_acc = 0.0;
+    float c0_in = c0_load(lane), c0 = 0.f;
     for (int n = 0; n < nchunks; ++n) {
         const int t0 = n * C, nf = Tb - t0 < C ? Tb - t0 : C;
         __syncwarp();                                       // every lane is done with the previous chunk's rows
         issue(n + DEPTH - 1);
         asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
         __syncwarp();
-        const float c0 = c0_next;
-        c0_next = (lane < C && t0 + C + lane < Tb) ? __ldg(col0 + t0 + C + lane) : 0.f;
+        if ((t0 & 31) == 0) {
+            const float x = c0_in;
+            c0_in = c0_load(t0 + 32 + lane);
+            float mine = x;
+            if (!c0src) {
+                const double xd = (double)x;
+                double mine_d = 0.0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    c0_acc += __shfl_sync(FULL, xd, i);
+                    mine_d = lane == i ? c0_acc : mine_d;
+                }
+                mine = (float)mine_d;
+            }
+            c0 = (t0 + lane + 1 >= Tb + 1 - L) ? INF : mine + 0.0f;  // (+0.0f: a -0.0 becomes +0.0)
+        }
         const unsigned char *rows = reinterpret_cast<const unsigned char *>(ring + (size_t)(n % DEPTH) * C * RS);
         // (not unrolled over the frames: the body is ~10 instructions x KL states already)
 #pragma unroll 1
         for (int f = 0; f < nf; ++f) {
             const unsigned char *row = rows + f * (RS * 4);
             const float eb = *reinterpret_cast<const float *>(row + blank_off);
-            const float xin = __shfl_sync(FULL, c0, f);     // column 0 of this row (:37 / :39 / :42)
+            const float xin = __shfl_sync(FULL, c0, (t0 + f) & 31);   // column 0 of this row
             float prev = __shfl_up_sync(FULL, v[KL - 1], 1);
             unsigned ng = 0, nl = 0, ng2 = 0, nl2 = 0;
             float stayed_k[KL], chg_k[KL];
@@ -1292,9 +1312,6 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     }
     bool wave_launched = false;
     if (lane_mode) {
-        align_col0_kernel<<<(unsigned)B, 32, 0, s>>>(p);
-        rc = check_launch();
-        if (rc != SSAK_OK) return rc;
         if (p.cfg.W == 2) {
             if (V <= 64) align_lane_kernel<16, 2><<<(unsigned)B, 32, smem_bytes, s>>>(p);
             else align_lane_kernel<16, 4><<<(unsigned)B, 32, smem_bytes, s>>>(p);

@@ -235,6 +235,78 @@ def test_align_throughput_kernel(kind, fag, monkeypatch):
         _check_batch(em, toks, el, tl, res=res, tag="lane/strided")
 
 
+def test_compute_alignment_adapter_and_word_positions():
+    """The reference's entry point with its own signature (align_transcriptions.py:294-308) on an injected model front
+    end, and tools/get_word_positions.py:14-43 on top of it: same segments as the from-emission variant and the oracle."""
+    import ssak_b200
+    from ssak_b200.synth import planted_emissions
+    labels = ["<pad>", " "] + list("abcdefghijklmnopqrstuvwxyz'")
+    dic = {c: i for i, c in enumerate(labels)}
+    g = torch.Generator().manual_seed(5)
+    transcript = "le chat dort"
+    toks = [dic[c] for c in transcript]
+    em = planted_emissions(90, len(labels), toks, g, 0)
+    audio = torch.zeros(90 * 320)                      # 20 ms frames at 16 kHz
+    model = object()
+    calls = []
+
+    def compute_log_probas(m, a):
+        calls.append(("lp", m is model, len(a)))
+        return em                                       # a CPU tensor, as the reference returns it
+
+    def get_model_vocab(m):
+        return labels, 0
+
+    out = ssak_b200.compute_alignment(audio, transcript, model, compute_log_probas=compute_log_probas,
+                                      get_model_vocab=get_model_vocab)
+    lab, emission, trellis, segs, words = out
+    assert lab == labels and emission.is_cuda and trellis.size(0) == 91 and calls == [("lp", True, 90 * 320)]
+    rc, ss, se, sc, _ = O.align(em.numpy(), toks, 0, False)
+    assert rc == 0 and [(x.start, x.end) for x in segs] == list(zip(ss.tolist(), se.tolist()))
+    assert [w.label for w in words] == transcript.split()
+    # transcript=None: decoded first (the reference prints it, :306-308)
+    out2 = ssak_b200.compute_alignment(audio, None, model, compute_log_probas=compute_log_probas,
+                                       get_model_vocab=get_model_vocab, decode_log_probas=lambda m, e: transcript)
+    assert [(x.start, x.end) for x in out2[3]] == [(x.start, x.end) for x in segs]
+    pos = list(ssak_b200.word_positions([audio], [transcript], model, 16000, compute_log_probas=compute_log_probas,
+                                        get_model_vocab=get_model_vocab))
+    ratio = len(audio) / (91 * 16000)
+    assert [p["word"] for p in pos] == transcript.split()
+    assert all(abs(p["start"] - w.start * ratio) < 1e-12 and abs(p["end"] - w.end * ratio) < 1e-12 and p["conf"] == w.score
+               for p, w in zip(pos, words))
+
+
+def test_windowed_long_audio_feeds_the_aligner():
+    """a long recording goes through the acoustic model in windows (140 s = 7000 frames at 20 ms,
+    ssak/infer/transformers_infer.py:259-265); the concatenated emissions -- seams included -- feed one long
+    alignment (the C3 shape, shortened): same spans as aligning the whole emission, and as the CPU oracle."""
+    import ssak_b200
+    from ssak_b200.synth import align_batch
+    em, toks, el, tl = align_batch(2, 17000, 50, 3800, 4200, 41, Tmin=16500)
+    outs = []
+    for b in range(2):
+        Tb = int(el[b])
+
+        def infer_sub(i, j, b=b):                       # 320 samples per frame
+            return em[b : b + 1, i // 320 : j // 320].cuda()
+
+        outs.append(ssak_b200.chunked_emission(infer_sub, Tb * 320, 7000 * 320)[0])
+        assert outs[-1].shape[0] == Tb
+    T = max(o.shape[0] for o in outs)
+    batch = torch.zeros(2, T, 50, device="cuda")
+    for b, o in enumerate(outs):
+        batch[b, : o.shape[0]] = o
+    res = ssak_b200.forced_align(batch, toks, el, tl)
+    whole = ssak_b200.forced_align(em.cuda(), toks, el, tl)
+    assert torch.equal(res.starts, whole.starts) and torch.equal(res.ends, whole.ends) and (res.status == 0).all()
+    Tb, Lb = int(el[0]), int(tl[0])
+    rc, ss, se, sc, t0 = O.align(em[0, :Tb].numpy(), toks[0, :Lb].tolist(), 0, False)
+    assert rc == 0 and res.starts[0, :Lb].cpu().tolist() == ss.tolist() and res.ends[0, :Lb].cpu().tolist() == se.tolist()
+    # greedy decode of the windowed emission (transformers_infer.py:84-85) equals the decode of the whole one
+    ids, _ = ssak_b200.decode_chunked(lambda i, j: em[0:1, i // 320 : j // 320].cuda(), Tb * 320, 7000 * 320)
+    assert ids == ssak_b200.ctc_greedy_decode(em[0:1, :Tb].cuda(), torch.ones(1), blank_id=0)[0]
+
+
 def test_compute_alignments_batched_front_end():
     """compute_alignment from the emission onwards (align_transcriptions.py:310-402), batched: character ->
     token mapping with the loose fall-backs, sentinel character, word regrouping and score aggregation."""

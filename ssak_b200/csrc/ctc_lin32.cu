@@ -757,9 +757,19 @@ __global__ void __launch_bounds__(256) lin32_orphan_kernel(const Params p) {
     }
 }
 
+}  // namespace lin32
+}  // namespace ssak
+#include "ctc_lin32_lv.cuh"
+namespace ssak {
+namespace lin32 {
+
 // ------------------------------------------------------------------------------------------------ host side
 int lanes_k(int64_t Lmax, int64_t V) {
-    if (V > MAXV || Lmax + 1 > 32 * MAXK) return 0;
+    if (V > MAXV) {   // large vocabularies: the gather kernels of ctc_lin32_lv.cuh
+        if (V > LV_MAXV || Lmax + 1 > 32 * LV_MAXK) return 0;
+        return (Lmax + 1 + 31) / 32 <= 4 ? 4 : 7;
+    }
+    if (Lmax + 1 > 32 * MAXK) return 0;
     const int need = (int)((Lmax + 1 + 31) / 32);
     // at least C positions per lane: the inflow into a lane needs K frames to reach the next lane, so it cannot
     // cascade (and overflow) between two re-scalings
@@ -771,11 +781,24 @@ static int launch(const Params &p, cudaStream_t s) {
     // ONE WARP PER CTA: warps never cooperate, and the block scheduler then hands a new chain to an SM the moment one
     // finishes (12-warp CTAs ran 171 CTAs on 148 SMs in two waves).  Residency is bounded by registers and by the
     // warp's slice of shared memory (~15 KB in backward).
-    const size_t per_warp = (size_t)smem_map(p.K, p.V, GRAD).total;
+    const bool lv = p.V > MAXV;
+    const size_t per_warp = lv ? (size_t)lv_smem_map(p.K, p.V, GRAD).total : (size_t)smem_map(p.K, p.V, GRAD).total;
     if (per_warp > (size_t)kMaxDynSmem) return SSAK_ERR_UNSUPPORTED;
     const int per_cta = 1;
     const unsigned grid = (unsigned)(2 * p.B);
     const size_t smem_bytes = per_cta * per_warp;
+    if (lv) {
+#define SSAK_LV(KK)                                                                                \
+    {                                                                                              \
+        cudaError_t e = GRAD ? ensure_max_smem<lv_backward_kernel<KK>>() : ensure_max_smem<lv_forward_kernel<KK>>(); \
+        if (e != cudaSuccess) { set_last_cuda_error(e); return SSAK_ERR_CUDA; }                    \
+        if (GRAD) lv_backward_kernel<KK><<<grid, 32, smem_bytes, s>>>(p);                          \
+        else lv_forward_kernel<KK><<<grid, 32, smem_bytes, s>>>(p);                                \
+    }
+        if (p.K == 4) SSAK_LV(4) else if (p.K == 7) SSAK_LV(7) else return SSAK_ERR_UNSUPPORTED;
+#undef SSAK_LV
+        return check_launch();
+    }
     const int nv = nv_of(p.V);
 #define SSAK_L32B(KK, NN)                                                                          \
     {                                                                                              \

@@ -10,7 +10,8 @@ namespace lin32 {
 
 constexpr int C = 4;            // frames per chunk = checkpoint spacing = rows per backward tile
 constexpr int MAXK = 13;        // positions per lane: targets up to 32 * 13 - 1 = 415 labels
-constexpr int MAXV = 128;       // vocabulary columns a warp converts per frame (4 per lane)
+constexpr int MAXV = 128;       // vocabulary columns a warp converts per frame (4 per lane); beyond: the gather kernels
+                                // (ctc_lin32_lv.cuh: V <= 2048, targets up to 223 labels)
 
 struct Params {
     const float *lp;            // log-probabilities, or raw logits when zl != nullptr

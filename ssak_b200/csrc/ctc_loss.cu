@@ -1599,11 +1599,23 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
 // are faster (B = 64: 0.42 vs 1.1 ms; B = 256 ragged: 1.15 vs 1.06 ms of kernels, and 1.5e-4 vs 7e-7 of gradient
 // error on unpeaked emissions; B = 1024: 4.1 vs 2.4 ms).
 // SSAK_CTC_LIN32=1 forces them wherever they are valid, =0 disables them.
-static int lin_k(int64_t Lmax, int64_t V, int64_t B) {
+// `aligned`: rows of log-probabilities 16-byte aligned and V % 4 == 0 (what the large-vocabulary kernels need for their
+// bulk copies); -1: not known (workspace queries).
+static int lin_k(int64_t Lmax, int64_t V, int64_t B, int aligned) {
     const int mode = env_int("SSAK_CTC_LIN32", -1);
     if (mode == 0) return 0;
     if (mode < 0 && 2 * B < 3 * (int64_t)device_sm_count()) return 0;   // B >= 1.5 x SMs (222 on a B200)
+    if (V > lin32::MAXV) {
+        // large vocabularies (ctc_lin32_lv.cuh): whole rows in a per-warp ring leave room for 7 chains per SM, so the
+        // gather kernels only pay off with many chains (B = 512, V = 1024 [C5]: 1.27 vs 1.22 ms; B = 1024: 2.25 vs
+        // 2.19 ms; B = 2048, T = 400, V = 512: 1.25 vs 2.11 ms)
+        if (aligned == 0 || (V & 3) != 0) return 0;
+        if (mode < 0 && B < 6 * (int64_t)device_sm_count()) return 0;
+    }
     return lin32::lanes_k(Lmax, V);
+}
+static inline int rows_aligned(const float *lp, int64_t st, int64_t sb, int64_t V) {
+    return ((reinterpret_cast<uintptr_t>(lp) & 15) == 0 && ((st | sb | V) & 3) == 0) ? 1 : 0;
 }
 // row blocks kept for utterances the throughput kernels hand back to the log-domain ones (fp32 range, see
 // ctc_lin32.cu): every utterance of a small batch, 1/8 of a large one (beyond: NaN likelihood / gradient, loud)
@@ -1611,11 +1623,13 @@ static inline int64_t lin_slots(int64_t B) { return B <= 32 ? B : std::max<int64
 
 struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, lin_fr, lin_ck, rows, total; };
 static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
-// V < 0: the vocabulary is not known (ssak_ctc_loss_workspace_bytes): room for either kernel family
-static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row_elems, bool saved) {
+// V < 0: the vocabulary is not known (ssak_ctc_loss_workspace_bytes); aligned < 0 with V > 128: the alignment of the
+// rows is not known (ssak_ctc_loss_workspace_bytes_v) -- in both cases room for either kernel family
+static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row_elems, bool saved, int aligned) {
     WsLayout w;
     size_t o = 0;
-    const int K = lin_k(Lmax, V < 0 ? 1 : V, B);
+    const int K = lin_k(Lmax, V < 0 ? 1 : V, B, aligned);
+    const bool either = K > 0 && (V < 0 || (V > lin32::MAXV && aligned < 0));
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
     // abort word (+ the slot counter of the throughput mode at +4), then nan_flag[B], then the throughput kernels'
     // flags[B], slot[B] and slot_b[n_slots <= B]: one memset
@@ -1632,7 +1646,7 @@ static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row
     w.tabs = o;   o += align_up((size_t)B * 2 * tab_slots(T) * 16 * sizeof(float), 256);
     // log-domain half lattices: one row block per utterance -- in the throughput mode only for the few utterances
     // that may be handed back (lin_slots)
-    const int64_t blocks = (K > 0 && V >= 0) ? lin_slots(B) : B;
+    const int64_t blocks = (K > 0 && !either) ? lin_slots(B) : B;
     w.rows = o;   if (saved) o += align_up((size_t)blocks * (size_t)T * row_elems * sizeof(float), 256);
     w.total = o + 256;
     return w;
@@ -1650,7 +1664,7 @@ static int fill_params(CtcParams *p, const float *log_probs, int64_t T, int64_t 
     if (T > 300000) return SSAK_ERR_UNSUPPORTED;  // re-centring offsets are kept exact as fp32 integers (< 2^24)
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return SSAK_ERR_INVALID_ARGUMENT;
     if (!choose_cfg(Lmax, B, (int)V, &p->cfg)) return SSAK_ERR_UNSUPPORTED;
-    const WsLayout w = ws_layout(T, B, V, Lmax, p->cfg.row_elems, saved);
+    const WsLayout w = ws_layout(T, B, V, Lmax, p->cfg.row_elems, saved, rows_aligned(log_probs, st, sb, V));
     if (workspace_bytes < w.total) return SSAK_ERR_WORKSPACE;
     p->lp = log_probs; p->T = T; p->B = B; p->V = (int)V; p->st = st; p->sb = sb;
     p->targets = targets; p->tgt_off = tgt_off; p->in_len = in_len; p->tgt_len = tgt_len;
@@ -1682,7 +1696,7 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes(int64_t T, int64_t B, int64_t ma
                                                 int save_for_backward) {
     CtcCfg c;
     if (T < 0 || T > 300000 || B <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, 64, &c)) return 0;
-    return ws_layout(T, B, -1, max_target_len, c.row_elems, save_for_backward != 0).total;
+    return ws_layout(T, B, -1, max_target_len, c.row_elems, save_for_backward != 0, -1).total;
 }
 
 /* The same with the vocabulary size known: the throughput kernels (V <= 128, targets up to 415 labels) keep
@@ -1692,14 +1706,15 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes_v(int64_t T, int64_t B, int64_t 
     CtcCfg c;
     if (T < 0 || T > 300000 || B <= 0 || V <= 0 || max_target_len < 0 || !choose_cfg(max_target_len, B, (int)V, &c))
         return 0;
-    return ws_layout(T, B, V, max_target_len, c.row_elems, save_for_backward != 0).total;
+    return ws_layout(T, B, V, max_target_len, c.row_elems, save_for_backward != 0, -1).total;
 }
 
 // Fill the parameters of the throughput kernels from the log-domain ones (same problem, same workspace).
 static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin32::Params *q) {
-    const int K = lin_k(p.Lmax, p.V, p.B);
+    const int al = rows_aligned(p.lp, p.st, p.sb, p.V);
+    const int K = lin_k(p.Lmax, p.V, p.B, al);
     if (K == 0) return false;
-    const WsLayout w = ws_layout(p.T, p.B, p.V, p.Lmax, p.cfg.row_elems, saved);
+    const WsLayout w = ws_layout(p.T, p.B, p.V, p.Lmax, p.cfg.row_elems, saved, al);
     char *ws = reinterpret_cast<char *>(workspace);
     q->lp = p.lp; q->T = p.T; q->B = p.B; q->V = p.V; q->st = p.st; q->sb = p.sb;
     q->targets = p.targets; q->tgt_off = p.tgt_off; q->in_len = p.in_len; q->tgt_len = p.tgt_len;
@@ -1742,10 +1757,8 @@ extern "C" int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_
         return SSAK_ERR_INVALID_ARGUMENT;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (lin_k(max_target_len, V, B) == 0) {
-        e = cudaMemsetAsync(flags_out, 0, (size_t)B * sizeof(int32_t), s);
-    } else {
-        const WsLayout w = ws_layout(T, B, V, max_target_len, c.row_elems, save_for_backward != 0);
+    {   // (the flag words sit at the same offset whichever kernels ran; forward() clears them)
+        const WsLayout w = ws_layout(T, B, V, max_target_len, c.row_elems, save_for_backward != 0, -1);
         const char *ws = reinterpret_cast<const char *>(workspace);
         e = cudaMemcpyAsync(flags_out, ws + w.abort_word + 256 + align_up((size_t)B * sizeof(int), 256),
                             (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
@@ -1758,7 +1771,7 @@ extern "C" int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_
 extern "C" int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len, int32_t logits) {
     // throughput mode: memset excluded; forward: [row lse] lin32 fwd + lin32 join + masked log-domain fwd + join;
     // backward: lin32 bwd + masked log-domain fwd + join + bwd.  Log-domain mode: fwd + join, bwd.
-    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B) > 0 ? 9 : 3);
+    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B, 1) > 0 ? 9 : 3);
 }
 
 static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,

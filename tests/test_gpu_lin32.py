@@ -89,7 +89,11 @@ def test_lin32_random_and_planted(reduction):
                                                            (3, 200, 50, 60, 90, True), (4, 64, 128, 3, 30, False),
                                                            (2, 90, 97, 40, 44, True), (3, 700, 50, 250, 330, True),
                                                            (2, 1100, 30, 400, 415, True), (3, 300, 50, 100, 127, False),
-                                                           (3, 300, 33, 128, 223, False), (40, 150, 50, 20, 60, True)]):
+                                                           (3, 300, 33, 128, 223, False), (40, 150, 50, 20, 60, True),
+                                                           # large vocabularies: the gather kernels (ctc_lin32_lv.cuh)
+                                                           (4, 64, 1024, 3, 30, False), (3, 200, 260, 60, 90, True),
+                                                           (2, 500, 2000, 150, 223, True), (5, 120, 200, 5, 40, True),
+                                                           (3, 90, 132, 100, 127, False)]):
         lp, tg, il, tl = ctc_batch(B, T, V, Lmin, Lmax, 800 + seed, Tmin=T // 2, planted=planted)
         _, grad = _check(lp, tg, il, tl, reduction)
         assert (grad[int(il[0]):, 0] == 0).all()
@@ -273,6 +277,32 @@ def test_lin32_from_logits_and_host_abi():
     ref.sum().backward()
     assert np.abs(nll - ref.detach().numpy()).max() <= 1e-5 * np.abs(ref.detach().numpy()).max()
     assert np.abs(grad - y.grad.numpy()).max() <= GRAD_ATOL
+
+
+def test_lin32_large_vocabulary_logits_strides_and_hand_back():
+    """The gather kernels (V > 128): logits entry point, HF's transposed view (strided rows: scalar gradient pass),
+    an utterance that has to be handed back."""
+    import ssak_b200
+    from ssak_b200.synth import ctc_batch
+    g = torch.Generator().manual_seed(9)
+    lp, tg, il, tl = ctc_batch(4, 140, 512, 10, 60, 840, Tmin=90)
+    logits = lp * 1.3 + 2.0 * torch.randn(140, 4, 1, generator=g) - 1.0
+    _check(logits, tg, il, tl, "mean", True, from_logits=True)
+    lpb = torch.randn(3, 70, 300, generator=g).log_softmax(-1)      # [B,T,V]
+    tg3 = torch.randint(1, 300, (3, 20), generator=g)
+    il3, tl3 = torch.tensor([70, 51, 33]), torch.tensor([20, 7, 12])
+    x = lpb.cuda().requires_grad_(True)
+    ssak_b200.ctc_loss(x.transpose(0, 1), tg3, il3, tl3, 0, "sum", True).backward()
+    y = lpb.double().requires_grad_(True)
+    F.ctc_loss(y.transpose(0, 1), tg3, il3, tl3, 0, "sum", zero_infinity=True).backward()
+    assert (x.grad.cpu().double() - y.grad).abs().max().item() <= GRAD_ATOL
+    lp2 = lp.clone()
+    lp2[:, 2] = lp2[:, 2] * 0.5 + 1.0                                # not log-probabilities: handed back
+    _check(lp2, tg, il, tl, "none", True, atol=1e-4)
+    fl, _, _ = _path_flags(lp2, tg, il, tl)
+    assert fl[2] != 0 and fl[0] == 0 and fl[1] == 0 and fl[3] == 0, fl
+    fl, _, _ = _path_flags(lp, tg, il, tl)
+    assert (fl == 0).all(), fl
 
 
 def test_lin32_workspace_is_small_and_full_size_c2():

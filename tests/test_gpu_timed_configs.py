@@ -159,10 +159,14 @@ def test_loss_random_emissions_256(monkeypatch):
     _loss_check("loss_random_B256_log_domain", lp, tg, il, tl, random_emissions=True)
 
 
-def test_loss_c5_512_v1024():
+def test_loss_c5_512_v1024(monkeypatch):
     from ssak_b200.synth import ctc_batch
     lp, tg, il, tl = ctc_batch(512, 750, 1024, 100, 200, 99, Tmin=600, planted=True)
     _loss_check("loss_c5_B512_V1024", lp, tg, il, tl)
+    # the large-vocabulary throughput kernels (ctc_lin32_lv.cuh; default from B = 6 x SMs on) at the same size
+    monkeypatch.setenv("SSAK_CTC_LIN32", "1")
+    _loss_check("loss_c5_B512_V1024_throughput_kernels", lp, tg, il, tl, atol=1e-5)
+    monkeypatch.delenv("SSAK_CTC_LIN32")
     # the logits entry point on the same shape (row normaliser + LOGITS kernels in the many-CTA regime)
     g = torch.Generator().manual_seed(3)
     logits = lp * 1.5 + 2.0 + torch.randn(750, 512, 1, generator=g)

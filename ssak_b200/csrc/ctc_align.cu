@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(32, 16) align_lane_kernel(const AlignParams p)
 // LK = 4 / 8: lane entries of the wavefront kernel (16 states per 32-bit word, "greater" in the low half of
 // every 2K-bit entry).
 template <int LK>
-__global__ void __launch_bounds__(256) align_backtrace_kernel(const AlignParams p) {
+__global__ void __launch_bounds__(1024) align_backtrace_kernel(const AlignParams p) {
     __shared__ int s_status, s_first;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -1433,8 +1433,12 @@ extern "C" int ssak_forced_align(const float *emissions, int64_t B, int64_t Tmax
     }
     rc = check_launch();
     if (rc != SSAK_OK) return rc;
-    if (!wave_launched) align_backtrace_kernel<0><<<(unsigned)B, 256, 0, s>>>(p);
-    else if (p.cfg.K <= 4) align_backtrace_kernel<4><<<(unsigned)B, 256, 0, s>>>(p);   // K = 1, 2 write the K = 4 layout
-    else align_backtrace_kernel<8><<<(unsigned)B, 256, 0, s>>>(p);
+    // One warp walks; the whole CTA then turns the path into per-frame probabilities and per-token means -- a pass
+    // of scattered loads over T frames.  Few long utterances (C3: 16 CTAs, 30000 frames each, 300 of the kernel's
+    // 830 us in that pass): 1024 threads per CTA keep four times as many loads in flight.
+    const unsigned bt_threads = (B <= device_sm_count() && Tmax >= 4096) ? 1024u : 256u;
+    if (!wave_launched) align_backtrace_kernel<0><<<(unsigned)B, bt_threads, 0, s>>>(p);
+    else if (p.cfg.K <= 4) align_backtrace_kernel<4><<<(unsigned)B, bt_threads, 0, s>>>(p);   // K = 1, 2 write the K = 4 layout
+    else align_backtrace_kernel<8><<<(unsigned)B, bt_threads, 0, s>>>(p);
     return check_launch();
 }

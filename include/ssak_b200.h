@@ -99,11 +99,26 @@ SSAK_API int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len
  * not fit the shared-memory emission ring: V > ~2040).  A caller that replaces a generic operator
  * (ssak_b200.install() over torch.nn.functional.ctc_loss) uses it to delegate what is not covered. */
 SSAK_API int ssak_ctc_loss_supported(int64_t T, int64_t B, int64_t V, int64_t max_target_len);
+/* 1 when forward(save_for_backward != 0) on such a shape returns a provisional likelihood that the matching backward
+ * call finalises (the throughput kernels; see ssak_ctc_loss_forward), else 0. */
+SSAK_API int ssak_ctc_loss_nll_is_provisional(int64_t B, int64_t V, int64_t max_target_len);
+/* grad[t,b,:] *= per_utterance[b] * scalar_a[0] * scalar_b[0] (device pointers, each may be NULL = 1); rows whose
+ * factor is exactly 1 are not touched.  For callers that run backward with a unit upstream gradient right after
+ * forward (to finalise the likelihood) and apply the real upstream gradient when autograd delivers it. */
+SSAK_API int ssak_ctc_grad_scale(float *grad, int64_t T, int64_t B, int64_t V, int64_t g_stride_t, int64_t g_stride_b,
+                                 const float *per_utterance, const float *scalar_a, const float *scalar_b,
+                                 ssak_stream_t stream);
 
 /* aten::_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank, zero_infinity)
  *   -> neg_log_likelihood[B] (fp32; +inf for an infeasible utterance -- zero_infinity is
  *      applied by the caller to the loss and by ssak_ctc_loss_backward to the gradient).
- * The second aten output (log_alpha) is replaced by the opaque workspace. */
+ * The second aten output (log_alpha) is replaced by the opaque workspace.
+ *   save_for_backward == 0: a forward-only call; always the log-domain kernels (unlimited range).
+ *   save_for_backward != 0: where ssak_ctc_loss_nll_is_provisional() says so (the throughput kernels: fp32 block
+ *      floating point), neg_log_likelihood is PROVISIONAL until the matching backward call has run on the same
+ *      buffers: backward verifies every frame (posterior mass = 1), recomputes the utterances that fail with the
+ *      log-domain kernels and REWRITES their neg_log_likelihood[b] (path flag bit 1).  Read the likelihood after
+ *      backward (ssak_b200.ctc_loss and ssak_ctc_loss_host do). */
 SSAK_API int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t B, int64_t V,
                                    int64_t lp_stride_t, int64_t lp_stride_b,
                                    const int32_t *targets, const int64_t *target_offsets,
@@ -120,6 +135,8 @@ SSAK_API int ssak_ctc_loss_forward(const float *log_probs, int64_t T, int64_t B,
  *                is written: (exp(lp) - posterior) * grad_out[b] for t < input_lengths[b],
  *                0 beyond (torch's convention: the gradient w.r.t. the logits that fed
  *                log_softmax)
+ *   neg_log_likelihood  the buffer the matching forward call wrote; entries of utterances whose provisional
+ *                likelihood failed the self-check are rewritten (see ssak_ctc_loss_forward)
  *   workspace    the one the matching forward call filled with save_for_backward != 0 */
 SSAK_API int ssak_ctc_loss_backward(const float *grad_out, const float *log_probs, int64_t T,
                                     int64_t B, int64_t V, int64_t lp_stride_t,

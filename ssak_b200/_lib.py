@@ -34,6 +34,8 @@ SIGNATURES = {
     "ssak_ctc_shard_pack": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "ssak_ctc_shard_finish": (C.c_int, [_p, _i32, _i64, _p, _p, _p]),
     "ssak_ctc_shard_grad_scale": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
+    "ssak_ctc_loss_nll_is_provisional": (C.c_int, [_i64, _i64, _i64]),
+    "ssak_ctc_grad_scale": (C.c_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "ssak_align_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ssak_forced_align": (C.c_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _p, _i32, _i32, _p,
                                     _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

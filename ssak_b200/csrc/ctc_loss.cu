@@ -1169,16 +1169,20 @@ __global__ void __launch_bounds__(K == 1 ? 544 : 288, 1) ctc_forward_wave_kernel
         float carry = sel(seam_m, xin, rk);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            // both updates over ONE common maximum: the three exponentials are independent, the dependent chain per
-            // frame is one log-sum-exp long instead of two (A = lse(ab, carry) then lse(al, A)).  A term more than
-            // 2^126 below the largest of the three is dropped -- it could not change an fp32 result anyway.
-            const float M = fmaxf(fmaxf(ab[k], carry), al[k]);
-            const float e_b = ex2_approx(ab[k] - M), e_c = ex2_approx(carry - M), e_l = ex2_approx(al[k] - M);
-            const float s_a = e_b + e_c;
-            const float s_l = e_l + sel(skip_m[k], s_a, e_b);
+            // One maximum PER SUM (a common maximum over the three terms flushes a whole sum to zero when the third
+            // term dominates by 2^126: with tight alignments, T_b ~ L_b + repeats, and peaky emissions exactly those
+            // states carry the likelihood).  The label sum takes the blank sum as (M_a, s_a) instead of waiting for
+            // its logarithm, so the dependent chain per frame stays one log-sum-exp long: 4 EX2 + 2 LG2 per pair.
+            const float M_a = fmaxf(ab[k], carry);
+            const float o = sel(skip_m[k], M_a, ab[k]);
+            const float M_l = fmaxf(al[k], o);
+            const float e_b = ex2_approx(ab[k] - M_a), e_c = ex2_approx(carry - M_a);
+            const float e_l = ex2_approx(al[k] - M_l), w = ex2_approx(o - M_l);
+            const float s_a = e_b + e_c;                                  // in [1, 2]
+            const float s_l = fmaf(sel(skip_m[k], s_a, 1.0f), w, e_l);    // in [1, 3]
             carry = al[k];
-            al[k] = (M + lg2_approx(s_l)) + el2[k];
-            ab[k] = fmaxf(M + lg2_approx(s_a), kNeg) + eb2;
+            al[k] = (M_l + lg2_approx(s_l)) + el2[k];
+            ab[k] = fmaxf(M_a + lg2_approx(s_a), kNeg) + eb2;
         }
         if (SAVE) {
             float *r = row_out + (int64_t)f * row_step;
@@ -1508,6 +1512,22 @@ __global__ void ctc_shard_grad_scale_kernel(const float *gscale, const float *gr
     if (b < B) out[b] = gscale[b] * (grad_loss[0] * inv_den[0]);
 }
 
+// grad[t,b,:] *= per_utt[b] * s1[0] * s2[0] (absent factors = 1); a row whose factor is exactly 1 is left alone, so the
+// usual case (upstream gradient 1) costs a launch and no memory traffic.  One warp per (t, b) row.
+__global__ void __launch_bounds__(256) ctc_grad_scale_kernel(float *grad, int64_t T, int64_t B, int V, int64_t gst,
+                                                             int64_t gsb, const float *per_utt, const float *s1,
+                                                             const float *s2) {
+    const int lane = threadIdx.x & 31;
+    const float common = (s1 ? s1[0] : 1.f) * (s2 ? s2[0] : 1.f);
+    if (!per_utt && common == 1.f) return;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < T * B; r += (int64_t)gridDim.x * 8) {
+        const int64_t t = r / B, b = r - t * B;
+        const float f = (per_utt ? per_utt[b] : 1.f) * common;
+        if (f == 1.f) continue;
+        float *g = grad + t * gst + b * gsb;
+        for (int v = lane; v < V; v += 32) g[v] *= f;
+    }
+}
 
 // ---------------------------------------------------------------------------- launchers
 template <bool GRAD>
@@ -1601,9 +1621,12 @@ static int launch_forward_wave(const CtcParams &p, cudaStream_t stream) {
 // SSAK_CTC_LIN32=1 forces them wherever they are valid, =0 disables them.
 // `aligned`: rows of log-probabilities 16-byte aligned and V % 4 == 0 (what the large-vocabulary kernels need for their
 // bulk copies); -1: not known (workspace queries).
-static int lin_k(int64_t Lmax, int64_t V, int64_t B, int aligned) {
+// `saved` == false (a forward-only call): never -- their likelihood is only verified by backward()'s self-check
+// (states lost to the fp32 range show up as posterior mass that does not sum to 1), so a forward() nobody follows
+// up must come from the log-domain kernels, whose range is unlimited.
+static int lin_k(int64_t Lmax, int64_t V, int64_t B, int aligned, bool saved) {
     const int mode = env_int("SSAK_CTC_LIN32", -1);
-    if (mode == 0) return 0;
+    if (mode == 0 || !saved) return 0;
     if (mode < 0 && 2 * B < 3 * (int64_t)device_sm_count()) return 0;   // B >= 1.5 x SMs (222 on a B200)
     if (V > lin32::MAXV) {
         // large vocabularies (ctc_lin32_lv.cuh): whole rows in a per-warp ring leave room for 7 chains per SM, so the
@@ -1628,7 +1651,7 @@ static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >=
 static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row_elems, bool saved, int aligned) {
     WsLayout w;
     size_t o = 0;
-    const int K = lin_k(Lmax, V < 0 ? 1 : V, B, aligned);
+    const int K = lin_k(Lmax, V < 0 ? 1 : V, B, aligned, saved);
     const bool either = K > 0 && (V < 0 || (V > lin32::MAXV && aligned < 0));
     w.nll2 = o;   o += align_up((size_t)B * sizeof(double), 256);
     // abort word (+ the slot counter of the throughput mode at +4), then nan_flag[B], then the throughput kernels'
@@ -1712,7 +1735,7 @@ extern "C" size_t ssak_ctc_loss_workspace_bytes_v(int64_t T, int64_t B, int64_t 
 // Fill the parameters of the throughput kernels from the log-domain ones (same problem, same workspace).
 static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin32::Params *q) {
     const int al = rows_aligned(p.lp, p.st, p.sb, p.V);
-    const int K = lin_k(p.Lmax, p.V, p.B, al);
+    const int K = lin_k(p.Lmax, p.V, p.B, al, saved);
     if (K == 0) return false;
     const WsLayout w = ws_layout(p.T, p.B, p.V, p.Lmax, p.cfg.row_elems, saved, al);
     char *ws = reinterpret_cast<char *>(workspace);
@@ -1771,7 +1794,7 @@ extern "C" int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_
 extern "C" int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len, int32_t logits) {
     // throughput mode: memset excluded; forward: [row lse] lin32 fwd + lin32 join + masked log-domain fwd + join;
     // backward: lin32 bwd + masked log-domain fwd + join + bwd.  Log-domain mode: fwd + join, bwd.
-    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B, 1) > 0 ? 9 : 3);
+    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B, 1, true) > 0 ? 9 : 3);
 }
 
 static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,
@@ -1838,7 +1861,9 @@ static int backward_impl(const float *grad_out, const float *x, int64_t T, int64
         p.slot = q.slot;
         p.slot_b = q.slot_b; p.slot_count = q.slot_counter; p.n_slots = q.n_slots;
         p.mask_bits = 2;
-        p.join_keeps_nll = 1;
+        // (the join rewrites nll[b] of these utterances: the throughput kernels' likelihood was provisional, and the
+        //  self-check that just failed says it may have lost states to the fp32 range)
+        p.join_keeps_nll = 0;
         rc = launch_forward_wave(p, s);
         if (rc == SSAK_ERR_UNSUPPORTED) rc = launch_lattice<false>(p, s);
         if (rc != SSAK_OK) return rc;
@@ -1938,5 +1963,22 @@ extern "C" int ssak_ctc_shard_grad_scale(const float *grad_scale, const float *g
     if (!grad_scale || !grad_loss || !inv_den || !grad_out || B <= 0) return SSAK_ERR_INVALID_ARGUMENT;
     ctc_shard_grad_scale_kernel<<<(unsigned)((B + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         grad_scale, grad_loss, inv_den, B, grad_out);
+    return check_launch();
+}
+
+extern "C" int ssak_ctc_loss_nll_is_provisional(int64_t B, int64_t V, int64_t max_target_len) {
+    if (B <= 0 || V <= 0 || max_target_len < 0) return 0;
+    return lin_k(max_target_len, V, B, 1, true) > 0 ? 1 : 0;
+}
+
+extern "C" int ssak_ctc_grad_scale(float *grad, int64_t T, int64_t B, int64_t V, int64_t g_stride_t, int64_t g_stride_b,
+                                   const float *per_utterance, const float *scalar_a, const float *scalar_b,
+                                   ssak_stream_t stream) {
+    if (!grad || T < 0 || B <= 0 || V <= 0) return SSAK_ERR_INVALID_ARGUMENT;
+    if (T == 0) return SSAK_OK;
+    const int64_t rows = T * B;
+    const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, 64 * (int64_t)device_sm_count());
+    ctc_grad_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        grad, T, B, (int)V, g_stride_t, g_stride_b, per_utterance, scalar_a, scalar_b);
     return check_launch();
 }

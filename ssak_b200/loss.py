@@ -53,9 +53,55 @@ def _padded_offsets(B: int, smax: int, device):
     return t
 
 
+def _launch_backward(L, from_logits, g, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank,
+                     zero_infinity, nll, ws, ws_bytes):
+    """One backward call of the C ABI -> gradient in log_probs' (dense) layout."""
+    T, B, V = log_probs.shape
+    # same (dense) layout as log_probs: HF hands in a transposed [B,T,V] buffer and its
+    # log_softmax backward reads the gradient in that layout
+    grad = torch.empty_like(log_probs)
+    if grad.stride(2) != 1:
+        grad = torch.empty((T, B, V), dtype=torch.float32, device=log_probs.device)
+    with torch.cuda.device(log_probs.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        bwd = L.ssak_ctc_logits_backward if from_logits else L.ssak_ctc_loss_backward
+        rc = bwd(g.data_ptr(), log_probs.data_ptr(), T, B, V, log_probs.stride(0),
+                 log_probs.stride(1), targets.data_ptr(), tgt_off.data_ptr(),
+                 in_len.data_ptr(), tgt_len.data_ptr(), max_target_len, blank,
+                 int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
+                 grad.stride(1), ws.data_ptr(), ws_bytes, stream)
+    _lib.check(rc, "ssak_ctc_logits_backward" if from_logits else "ssak_ctc_loss_backward")
+    return grad
+
+
+def _apply_upstream(ctx, grad, grad_loss, per_utterance: bool):
+    """Eager mode: `grad` was computed with a unit upstream gradient; apply the real one.  First call: in place
+    (rows whose factor is exactly 1 -- the usual case -- are not touched); later calls (retain_graph): out of place,
+    relative to what the first call applied."""
+    gl = grad_loss.detach().to(torch.float32).contiguous()
+    applied = getattr(ctx, "applied", None)
+    if applied is not None:
+        f = gl / applied
+        return grad * (f.view(1, -1, 1) if per_utterance else f)
+    L = _lib.lib()
+    T, B, V = grad.shape
+    with torch.cuda.device(grad.device):
+        rc = L.ssak_ctc_grad_scale(grad.data_ptr(), T, B, V, grad.stride(0), grad.stride(1),
+                                   gl.data_ptr() if per_utterance else None, None if per_utterance else gl.data_ptr(),
+                                   None, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ssak_ctc_grad_scale")
+    ctx.applied = gl
+    return grad
+
+
 class _CTCLossFunction(torch.autograd.Function):
     """aten::_ctc_loss + the reduction of aten::ctc_loss / aten::_ctc_loss_backward on libssak_b200.so.
-    forward: 3 launches (half lattices, join, reduction); backward: 1 launch (+ one scale)."""
+    forward: 3 launches (half lattices, join, reduction); backward: 1 launch (+ one scale).
+
+    Where the throughput kernels run (ssak_ctc_loss_nll_is_provisional: batches that fill the GPU) the likelihood
+    the forward call returns is provisional until the backward call has verified it, so BOTH calls run inside
+    forward() -- backward with the reduction's own weights as upstream gradient -- the loss is reduced from the
+    final likelihoods, and backward() only applies autograd's upstream gradient (no memory traffic when it is 1)."""
 
     @staticmethod
     def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity,
@@ -81,32 +127,30 @@ class _CTCLossFunction(torch.autograd.Function):
         rc = L.ssak_ctc_loss_reduce(nll.data_ptr(), tgt_len.data_ptr(), B, red, int(zero_infinity),
                                     loss.data_ptr(), _lib.ptr(gscale), stream)
         _lib.check(rc, "ssak_ctc_loss_reduce")
-        if save:
+        ctx.eager = save and bool(L.ssak_ctc_loss_nll_is_provisional(B, V, max_target_len))
+        if ctx.eager:
+            grad = _launch_backward(L, from_logits, gscale, log_probs, targets, tgt_off, in_len, tgt_len,
+                                    max_target_len, blank, zero_infinity, nll, ws, ws_bytes)
+            rc = L.ssak_ctc_loss_reduce(nll.data_ptr(), tgt_len.data_ptr(), B, red, int(zero_infinity),
+                                        loss.data_ptr(), None, stream)   # from the final likelihoods
+            _lib.check(rc, "ssak_ctc_loss_reduce")
+            ctx.save_for_backward(grad)
+            ctx.per_utterance = red == 0
+        elif save:
             ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale)
             ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes, from_logits)
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
+        if ctx.eager:
+            (grad,) = ctx.saved_tensors
+            return (_apply_upstream(ctx, grad, grad_loss, ctx.per_utterance),) + (None,) * 9
         log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale = ctx.saved_tensors
         max_target_len, blank, zero_infinity, ws_bytes, from_logits = ctx.meta
-        L = _lib.lib()
-        T, B, V = log_probs.shape
         g = (gscale * grad_loss.to(torch.float32)).contiguous()   # [B]: upstream x d loss / d nll_b
-        # same (dense) layout as log_probs: HF hands in a transposed [B,T,V] buffer and its
-        # log_softmax backward reads the gradient in that layout
-        grad = torch.empty_like(log_probs)
-        if grad.stride(2) != 1:
-            grad = torch.empty((T, B, V), dtype=torch.float32, device=log_probs.device)
-        with torch.cuda.device(log_probs.device):
-            stream = torch.cuda.current_stream().cuda_stream
-            bwd = L.ssak_ctc_logits_backward if from_logits else L.ssak_ctc_loss_backward
-            rc = bwd(g.data_ptr(), log_probs.data_ptr(), T, B, V, log_probs.stride(0),
-                     log_probs.stride(1), targets.data_ptr(), tgt_off.data_ptr(),
-                     in_len.data_ptr(), tgt_len.data_ptr(), max_target_len, blank,
-                     int(zero_infinity), nll.data_ptr(), grad.data_ptr(), grad.stride(0),
-                     grad.stride(1), ws.data_ptr(), ws_bytes, stream)
-        _lib.check(rc, "ssak_ctc_logits_backward" if from_logits else "ssak_ctc_loss_backward")
+        grad = _launch_backward(_lib.lib(), from_logits, g, log_probs, targets, tgt_off, in_len, tgt_len,
+                                max_target_len, blank, zero_infinity, nll, ws, ws_bytes)
         return grad, None, None, None, None, None, None, None, None, None
 
 
@@ -274,7 +318,9 @@ def _covers(log_probs, targets, target_lengths) -> bool:
 
 
 def _aten_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, zero_infinity=False):
-    """aten::_ctc_loss on CUDA -> (neg_log_likelihood[B], opaque workspace handed back as `log_alpha`)."""
+    """aten::_ctc_loss on CUDA -> (neg_log_likelihood[B], opaque tensor handed back as `log_alpha`): the workspace
+    (uint8), or -- where the forward likelihood is provisional until the backward call has run, see
+    _CTCLossFunction -- the gradient for a unit upstream gradient (fp32 [T,B,V]), computed right here."""
     lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, list(input_lengths), list(target_lengths),
                                                        blank)
     L = _lib.lib()
@@ -288,28 +334,29 @@ def _aten_ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, z
                                      tgt_off.data_ptr(), in_len.data_ptr(), tgt_len.data_ptr(), lmax, int(blank), 1,
                                      nll.data_ptr(), ws.data_ptr(), ws_bytes,
                                      torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "ssak_ctc_loss_forward")
+        _lib.check(rc, "ssak_ctc_loss_forward")
+        if L.ssak_ctc_loss_nll_is_provisional(B, V, lmax):
+            ones = torch.ones(B, dtype=torch.float32, device=lp.device)
+            ws = _launch_backward(L, False, ones, lp, tg, tgt_off, in_len, tgt_len, lmax, int(blank),
+                                  bool(zero_infinity), nll, ws, ws_bytes)
     return nll.to(log_probs.dtype), ws   # (fp64 callers get fp64 back: autograd checks the dtype)
 
 
 def _aten_ctc_loss_backward(grad, log_probs, targets, input_lengths, target_lengths, neg_log_likelihood, log_alpha,
                             blank, zero_infinity=False):
-    """aten::_ctc_loss_backward on CUDA; `log_alpha` is the workspace `_aten_ctc_loss` returned."""
+    """aten::_ctc_loss_backward on CUDA; `log_alpha` is what `_aten_ctc_loss` returned."""
+    if log_alpha.dtype == torch.float32:    # the unit gradient, already computed
+        B = log_alpha.shape[1]
+        return (log_alpha * grad.to(torch.float32).expand(B).view(1, B, 1)).to(log_probs.dtype).reshape(log_probs.shape)
     lp, tg, tgt_off, in_len, tgt_len, lmax = _prepare(log_probs, targets, list(input_lengths), list(target_lengths),
                                                        blank)
     L = _lib.lib()
     T, B, V = lp.shape
     g = grad.to(torch.float32).expand(B).contiguous()
     nll32 = neg_log_likelihood.to(torch.float32).contiguous()
-    out = torch.empty((T, B, V), dtype=torch.float32, device=lp.device)
-    with torch.cuda.device(lp.device):
-        rc = L.ssak_ctc_loss_backward(g.data_ptr(), lp.data_ptr(), T, B, V, lp.stride(0), lp.stride(1), tg.data_ptr(),
-                                      tgt_off.data_ptr(), in_len.data_ptr(), tgt_len.data_ptr(), lmax, int(blank),
-                                      int(zero_infinity), nll32.data_ptr(), out.data_ptr(),
-                                      out.stride(0), out.stride(1), log_alpha.data_ptr(), log_alpha.numel(),
-                                      torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "ssak_ctc_loss_backward")
-    return out.to(log_probs.dtype)
+    out = _launch_backward(L, False, g, lp, tg, tgt_off, in_len, tgt_len, lmax, int(blank), bool(zero_infinity),
+                           nll32, log_alpha, log_alpha.numel())
+    return out.to(log_probs.dtype).reshape(log_probs.shape)
 
 
 def install(mode: str = "functional") -> None:

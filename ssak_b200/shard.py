@@ -132,6 +132,23 @@ class _ShardedCTCFunction(torch.autograd.Function):
         _lib.check(rc, "ssak_ctc_shard_pack")
         distributed = dist.is_available() and dist.is_initialized()
         side = None
+        # Throughput kernels (batches that fill the GPU): the likelihood is provisional until the backward call has
+        # verified it (loss._CTCLossFunction), so the backward runs right here -- with the a-priori denominator for
+        # 'mean' / 'sum', 1 for 'mean_volume' -- and the local sums are packed again from the final likelihoods.
+        eager = bool(ctx.needs_input_grad[0]) and bool(L.ssak_ctc_loss_nll_is_provisional(B, V, max_target_len))
+        ctx.eager = eager
+        if eager:
+            from .loss import _launch_backward
+            inv0 = 1.0 / float(global_batch) if code == 1 else 1.0
+            g = torch.empty(B, dtype=torch.float32, device=dev)
+            rc = L.ssak_ctc_shard_grad_scale(gscale.data_ptr(), _device_scalar(1.0, dev).data_ptr(),
+                                             _device_scalar(inv0, dev).data_ptr(), B, g.data_ptr(), stream)
+            _lib.check(rc, "ssak_ctc_shard_grad_scale")
+            grad = _launch_backward(L, False, g, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank,
+                                    zero_infinity, nll, ws, ws_bytes)
+            rc = L.ssak_ctc_shard_pack(nll.data_ptr(), tgt_len.data_ptr(), B, code, int(zero_infinity),
+                                       packed.data_ptr(), gscale.data_ptr(), stream)
+            _lib.check(rc, "ssak_ctc_shard_pack")
         if distributed and overlap and code != 3 and ctx.needs_input_grad[0]:
             out.fill_(float("nan"))
             side = _side_stream(dev)
@@ -148,7 +165,10 @@ class _ShardedCTCFunction(torch.autograd.Function):
             rc = L.ssak_ctc_shard_finish(packed.data_ptr(), code, int(global_batch), out.data_ptr(),
                                          out.data_ptr() + 4, torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "ssak_ctc_shard_finish")
-        ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale, out)
+        if eager:
+            ctx.save_for_backward(grad, out)
+        else:
+            ctx.save_for_backward(log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale, out)
         ctx.meta = (max_target_len, blank, zero_infinity, ws_bytes, code, int(global_batch))
         ctx.side = side
         return out[0]
@@ -156,12 +176,25 @@ class _ShardedCTCFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         from . import _lib
-        log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale, out = ctx.saved_tensors
-        max_target_len, blank, zero_infinity, ws_bytes, code, global_batch = ctx.meta
         L = _lib.lib()
+        max_target_len, blank, zero_infinity, ws_bytes, code, global_batch = ctx.meta
+        gl = grad_loss if (grad_loss.dtype == torch.float32 and grad_loss.is_contiguous()) else grad_loss.float().contiguous()
+        if ctx.eager:
+            # apply autograd's upstream gradient (and, for 'mean_volume', the collective's 1/denominator); no memory
+            # traffic when the factor is 1.  (A second backward over a retained graph would scale twice: not supported.)
+            grad, out = ctx.saved_tensors
+            T, B, V = grad.shape
+            with torch.cuda.device(grad.device):
+                main = torch.cuda.current_stream()
+                if ctx.side is not None:
+                    main.wait_stream(ctx.side)
+                rc = L.ssak_ctc_grad_scale(grad.data_ptr(), T, B, V, grad.stride(0), grad.stride(1), None, gl.data_ptr(),
+                                           out.data_ptr() + 4 if code == 3 else None, main.cuda_stream)
+            _lib.check(rc, "ssak_ctc_grad_scale")
+            return (grad,) + (None,) * 11
+        log_probs, targets, tgt_off, in_len, tgt_len, nll, ws, gscale, out = ctx.saved_tensors
         T, B, V = log_probs.shape
         dev = log_probs.device
-        gl = grad_loss if (grad_loss.dtype == torch.float32 and grad_loss.is_contiguous()) else grad_loss.float().contiguous()
         g = torch.empty(B, dtype=torch.float32, device=dev)
         grad = torch.empty_like(log_probs)
         if grad.stride(2) != 1:

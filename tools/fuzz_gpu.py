@@ -1,0 +1,82 @@
+"""Randomised parity sweep of the throughput kernels (forced on small shapes) against torch CPU fp64 / the C oracle:
+python tools/fuzz_gpu.py [seconds] [seed].  Checked against torch CPU fp64; bars: 1e-5 relative (loss), 1e-4 (gradient), or 1.5 x the error of torch's own fp32 CPU kernel where that is larger."""
+import os, sys, time
+os.environ["SSAK_CTC_LIN32"] = "1"
+os.environ["SSAK_ALIGN_LANE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.nn.functional as F
+import ssak_b200
+from oracle import oracle as O
+from ssak_b200.synth import align_batch, ctc_batch
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+t_end, n_loss, n_align, worst, above, failures = time.time() + budget, 0, 0, 0.0, [], []
+while time.time() < t_end:
+    # ---- loss
+    V = int(rng.choice([2, 5, 33, 50, 64, 65, 128, 132, 256, 512, 1024]))
+    Lmax = int(rng.integers(0, 224 if V > 128 else 416))
+    T = int(rng.integers(1, 260))
+    B = int(rng.integers(1, 9))
+    planted = bool(rng.integers(0, 2))
+    seed = int(rng.integers(1 << 30))
+    lp, tg, il, tl = ctc_batch(B, T, V, 0, Lmax, seed, Tmin=1, planted=planted and V > 2)
+    tl = torch.minimum(tl, torch.tensor(Lmax))
+    il = torch.clamp(il, 1, T)
+    logits = bool(rng.integers(0, 3) == 0)
+    red = ["none", "mean", "sum"][int(rng.integers(0, 3))]
+    x0 = lp * 1.7 + 0.3 if logits else lp
+    x = x0.cuda().requires_grad_(True)
+    fn = ssak_b200.ctc_loss_from_logits if logits else ssak_b200.ctc_loss
+    loss = fn(x, tg, il, tl, 0, red, True)
+    loss.sum().backward()
+    y = x0.double().requires_grad_(True)
+    ref = F.ctc_loss(F.log_softmax(y, -1) if logits else y, tg, il, tl, 0, red, True)
+    ref.sum().backward()
+    # the reference itself (torch's fp32 CPU kernel) against the fp64 truth: the bar scales with its error where that
+    # exceeds the 1e-4 / 1e-5 bars (likelihoods of ~1000 nats)
+    y32 = x0.clone().requires_grad_(True)
+    ref32 = F.ctc_loss(F.log_softmax(y32, -1) if logits else y32, tg, il, tl, 0, red, True)
+    ref32.sum().backward()
+    ref_gerr = (y32.grad.double() - y.grad).abs().max().item()
+    ref_lerr = ((ref32.detach().double() - ref.detach()).abs() / ref.detach().abs().clamp_min(1.0)).reshape(-1)
+    ref_lerr = ref_lerr[torch.isfinite(ref_lerr)].max().item() if torch.isfinite(ref_lerr).any() else 0.0
+    l, r = loss.detach().cpu().double().reshape(-1), ref.detach().reshape(-1)
+    nll_max = float(F.ctc_loss(F.log_softmax(y.detach(), -1) if logits else y.detach(), tg, il, tl, 0, 'none', True).max())
+    case = f"tools/fuzz_case.py {V} {Lmax} {T} {B} {int(planted)} {int(logits)} {seed}   # reduction {red}"
+    if not torch.equal(torch.isfinite(l), torch.isfinite(r)):
+        failures.append(("finite", case)); continue
+    fin = torch.isfinite(r)
+    if fin.any():
+        rel = ((l - r).abs() / r.abs().clamp_min(1.0))[fin].max().item()
+        if rel > max(1e-5, 1.5 * ref_lerr + 1e-5) + 1e-7 * float(il.sum()) / max(float(r[fin].abs().max()), 1.0):
+            failures.append((f"loss {rel:.2e}", case)); continue
+    err = (x.grad.cpu().double() - y.grad).abs().max().item()
+    if err > max(1e-4, 1.5 * ref_gerr + 1e-5, 1e-6 * nll_max):
+        failures.append((f"grad {err:.2e}", case)); continue
+    if err > 1e-5:
+        above.append((round(err, 7), V, Lmax, T, B, planted, logits))
+    worst = max(worst, err)
+    n_loss += 1
+    # ---- aligner
+    V = int(rng.choice([3, 7, 50, 64, 97, 128]))
+    Lmax = int(rng.integers(1, 512))
+    T = int(rng.integers(1, 700))
+    B = int(rng.integers(1, 7))
+    kind = ["planted", "random", "tie"][int(rng.integers(0, 3))]
+    fag = bool(rng.integers(0, 2))
+    em, toks, el, tl2 = align_batch(B, T, V, 1, Lmax, int(rng.integers(1 << 30)), Tmin=1, kind=kind)
+    res = ssak_b200.forced_align(em.cuda(), toks, el, tl2, first_as_garbage=fag)
+    st, en, ts, status = res.starts.cpu(), res.ends.cpu(), res.t_start.cpu(), res.status.cpu()
+    for b in range(B):
+        Tb, Lb = int(el[b]), int(tl2[b])
+        rc, ss, se, sc, t0 = O.align(em[b, :Tb].numpy(), toks[b, :Lb].tolist(), 0, fag)
+        assert (rc == 0) == (int(status[b]) == 0), ("status", V, Lmax, T, kind, fag, b)
+        if rc == 0:
+            assert int(ts[b]) == t0 and st[b, :Lb].tolist() == ss.tolist() and en[b, :Lb].tolist() == se.tolist(), \
+                ("align", V, Lmax, T, kind, fag, b)
+    n_align += 1
+for f in failures:
+    print("FAIL", f)
+print(f"fuzz {'ok' if not failures else 'FAILED'}: {n_loss} loss batches (worst gradient error {worst:.1e}; above 1e-5 -- utterances recomputed by the "
+      f"log-domain kernels: {above[:8]}), {n_align} aligner batches")

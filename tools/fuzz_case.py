@@ -1,4 +1,5 @@
-"""Replay one loss case of the fuzz with per-utterance detail: python tools/fuzz_case.py V Lmax T B planted logits seed"""
+"""Replay one loss case of the fuzz with per-utterance detail:
+[SSAK_CTC_LIN32=.. SSAK_CTC_FWD_WAVE=.. ...] python tools/fuzz_case.py V Lmax T B planted logits seed"""
 import os, sys
 os.environ.setdefault("SSAK_CTC_LIN32", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,8 +1,6 @@
-"""Randomised parity sweep of the throughput kernels (forced on small shapes) against torch CPU fp64 / the C oracle:
+"""Randomised parity sweep of every kernel family (forced through the library's knobs on small shapes) against torch CPU fp64 / the C oracle:
 python tools/fuzz_gpu.py [seconds] [seed].  Checked against torch CPU fp64; bars: 1e-5 relative (loss), 1e-4 (gradient), or 1.5 x the error of torch's own fp32 CPU kernel where that is larger."""
 import os, sys, time
-os.environ["SSAK_CTC_LIN32"] = "1"
-os.environ["SSAK_ALIGN_LANE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.nn.functional as F
 import ssak_b200
@@ -12,12 +10,31 @@ from ssak_b200.synth import align_batch, ctc_batch
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 t_end, n_loss, n_align, worst, above, failures = time.time() + budget, 0, 0, 0.0, [], []
+KNOBS = ("SSAK_CTC_LIN32", "SSAK_CTC_FWD_WAVE", "SSAK_CTC_FEW", "SSAK_CTC_SPLIT", "SSAK_ALIGN_LANE", "SSAK_ALIGN_WAVE")
+
+
+def set_knobs(**kw):
+    """Kernel-family knobs of the library (read per call): None = the library's own choice."""
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    for k, v in kw.items():
+        if v is not None:
+            os.environ[k] = str(v)
+    return " ".join(f"{k}={v}" for k, v in kw.items() if v is not None)
+
+
 while time.time() < t_end:
-    # ---- loss
+    # ---- loss: throughput kernels forced (half of the cases), or the log-domain kernels in each of their variants
+    lin = int(rng.integers(0, 2))
+    knobs = set_knobs(SSAK_CTC_LIN32=lin,
+                      SSAK_CTC_FWD_WAVE=None if lin or rng.integers(0, 2) else 0,
+                      SSAK_CTC_FEW=None if lin or rng.integers(0, 2) else 0,
+                      SSAK_CTC_SPLIT=None if lin or rng.integers(0, 2) else 0)
     V = int(rng.choice([2, 5, 33, 50, 64, 65, 128, 132, 256, 512, 1024]))
-    Lmax = int(rng.integers(0, 224 if V > 128 else 416))
-    T = int(rng.integers(1, 260))
-    B = int(rng.integers(1, 9))
+    big = (not lin) and rng.integers(0, 6) == 0
+    Lmax = int(rng.integers(0, 224 if V > 128 else 416)) if not big else int(rng.integers(300, 1300))
+    T = int(rng.integers(1, 260)) if not big else int(rng.integers(300, 900))
+    B = int(rng.integers(1, 9)) if not big else int(rng.integers(1, 4))
     planted = bool(rng.integers(0, 2))
     seed = int(rng.integers(1 << 30))
     lp, tg, il, tl = ctc_batch(B, T, V, 0, Lmax, seed, Tmin=1, planted=planted and V > 2)
@@ -43,7 +60,7 @@ while time.time() < t_end:
     ref_lerr = ref_lerr[torch.isfinite(ref_lerr)].max().item() if torch.isfinite(ref_lerr).any() else 0.0
     l, r = loss.detach().cpu().double().reshape(-1), ref.detach().reshape(-1)
     nll_max = float(F.ctc_loss(F.log_softmax(y.detach(), -1) if logits else y.detach(), tg, il, tl, 0, 'none', True).max())
-    case = f"tools/fuzz_case.py {V} {Lmax} {T} {B} {int(planted)} {int(logits)} {seed}   # reduction {red}"
+    case = f"{knobs} python tools/fuzz_case.py {V} {Lmax} {T} {B} {int(planted)} {int(logits)} {seed}   # reduction {red}"
     if not torch.equal(torch.isfinite(l), torch.isfinite(r)):
         failures.append(("finite", case)); continue
     fin = torch.isfinite(r)
@@ -58,23 +75,30 @@ while time.time() < t_end:
         above.append((round(err, 7), V, Lmax, T, B, planted, logits))
     worst = max(worst, err)
     n_loss += 1
-    # ---- aligner
+    # ---- aligner: the throughput (one warp per utterance) kernel, the wavefront kernel, the barrier kernel
+    ak = int(rng.integers(0, 3))
+    aknobs = set_knobs(SSAK_ALIGN_LANE=1 if ak == 0 else 0, SSAK_ALIGN_WAVE=0 if ak == 2 else None)
     V = int(rng.choice([3, 7, 50, 64, 97, 128]))
     Lmax = int(rng.integers(1, 512))
     T = int(rng.integers(1, 700))
     B = int(rng.integers(1, 7))
     kind = ["planted", "random", "tie"][int(rng.integers(0, 3))]
     fag = bool(rng.integers(0, 2))
-    em, toks, el, tl2 = align_batch(B, T, V, 1, Lmax, int(rng.integers(1 << 30)), Tmin=1, kind=kind)
+    aseed = int(rng.integers(1 << 30))
+    em, toks, el, tl2 = align_batch(B, T, V, 1, Lmax, aseed, Tmin=1, kind=kind)
     res = ssak_b200.forced_align(em.cuda(), toks, el, tl2, first_as_garbage=fag)
     st, en, ts, status = res.starts.cpu(), res.ends.cpu(), res.t_start.cpu(), res.status.cpu()
     for b in range(B):
         Tb, Lb = int(el[b]), int(tl2[b])
+        if fag and Lb > 0 and np.isnan(O.garbage_col0(em[b, :Tb].numpy(), int(toks[b, 0]))).any():
+            continue   # an emission above 0 (the un-normalised "tie" rows): log(1 - exp(e)) is NaN, the result undefined
         rc, ss, se, sc, t0 = O.align(em[b, :Tb].numpy(), toks[b, :Lb].tolist(), 0, fag)
-        assert (rc == 0) == (int(status[b]) == 0), ("status", V, Lmax, T, kind, fag, b)
-        if rc == 0:
-            assert int(ts[b]) == t0 and st[b, :Lb].tolist() == ss.tolist() and en[b, :Lb].tolist() == se.tolist(), \
-                ("align", V, Lmax, T, kind, fag, b)
+        good = (rc == 0) == (int(status[b]) == 0)
+        if good and rc == 0:
+            good = int(ts[b]) == t0 and st[b, :Lb].tolist() == ss.tolist() and en[b, :Lb].tolist() == se.tolist()
+        if not good:
+            failures.append(("align", f"{aknobs} V={V} Lmax={Lmax} T={T} B={B} kind={kind} first_as_garbage={fag} seed={aseed} b={b}"))
+            break
     n_align += 1
 for f in failures:
     print("FAIL", f)

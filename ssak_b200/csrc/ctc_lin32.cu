@@ -270,14 +270,45 @@ struct Chain {
 __device__ __forceinline__ bool chain_of(const Params &p, Chain &c) {
     const int64_t id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (id >= 2 * p.B) return false;
-    c.dir = id >= p.B ? 1 : 0;
-    c.b = (int)(id - (int64_t)c.dir * p.B);
+    if (p.order) {   // longest utterances first (see lin32_order_kernel)
+        c.dir = (int)(id & 1);
+        c.b = p.order[id >> 1];
+    } else {
+        c.dir = id >= p.B ? 1 : 0;
+        c.b = (int)(id - (int64_t)c.dir * p.B);
+    }
     int Tb = p.in_len[c.b];
     c.Tb = Tb < 0 ? 0 : (Tb > (int)p.T ? (int)p.T : Tb);
     int L = p.tgt_len[c.b];
     c.L = L < 0 ? 0 : (L > p.Lmax ? p.Lmax : L);
     c.m = c.Tb >> 1;
     return true;
+}
+
+// Launch order.  The block scheduler hands out one-warp CTAs in blockIdx order and an SM holds 12 (backward) chains:
+// B = 1024 is 2048 chains on 1776 places, and the 272 chains of the partial second wave start when the first ones
+// finish.  With the utterances in order of decreasing T_b the second wave holds the SHORTEST chains (and they run on
+// nearly empty SMs): longest-processing-time-first.  order[rank of b] = b, rank = number of utterances with a larger
+// T_b (ties by index): B^2 / 2 comparisons, nothing next to the recursion for the batch sizes this is used for.
+constexpr int ORDER_MAX_B = 8192;
+__global__ void __launch_bounds__(256) lin32_order_kernel(const Params p) {
+    __shared__ int tile[256];
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    const int B = (int)p.B;
+    auto len_of = [&](int i) {
+        const int t = p.in_len[i];
+        return t < 0 ? 0 : (t > (int)p.T ? (int)p.T : t);
+    };
+    const int mine = b < B ? len_of(b) : 0;
+    int rank = 0;
+    for (int b0 = 0; b0 < B; b0 += 256) {
+        __syncthreads();
+        tile[threadIdx.x] = b0 + threadIdx.x < B ? len_of(b0 + threadIdx.x) : -1;
+        __syncthreads();
+        const int n = B - b0 < 256 ? B - b0 : 256;
+        for (int i = 0; i < n; ++i) rank += (tile[i] > mine || (tile[i] == mine && b0 + i < b)) ? 1 : 0;
+    }
+    if (b < B) p.order[rank] = b;
 }
 
 // Emission staging: the warp converts its own rows.  Raw rows travel global -> shared with cp.async (LDGSTS: no
@@ -764,6 +795,8 @@ namespace ssak {
 namespace lin32 {
 
 // ------------------------------------------------------------------------------------------------ host side
+bool ordered(int64_t B) { return B <= ORDER_MAX_B; }
+
 int lanes_k(int64_t Lmax, int64_t V) {
     if (V > MAXV) {   // large vocabularies: the gather kernels of ctc_lin32_lv.cuh
         if (V > LV_MAXV || Lmax + 1 > 32 * LV_MAXK) return 0;
@@ -826,6 +859,11 @@ static int launch(const Params &p, cudaStream_t s) {
 }
 
 int launch_forward(const Params &p, cudaStream_t s) {
+    if (p.order) {
+        lin32_order_kernel<<<(unsigned)((p.B + 255) / 256), 256, 0, s>>>(p);
+        int rc0 = check_launch();
+        if (rc0 != SSAK_OK) return rc0;
+    }
     int rc = launch<false>(p, s);
     if (rc != SSAK_OK) return rc;
     lin32_join_kernel<<<(unsigned)p.B, 128, 0, s>>>(p);

@@ -36,6 +36,8 @@ struct Params {
                                 //     CTA pair per row block)
     int *slot_counter;
     int n_slots;
+    int *order;                 // [B] utterances by decreasing T_b (chains 2r, 2r+1 belong to utterance order[r]: the
+                                //     longest chains start first, the partial last wave holds the shortest), or nullptr
     const float *grad_out;
     float *grad;
     int64_t gst, gsb;
@@ -47,6 +49,7 @@ struct Params {
 
 // positions per lane for targets up to Lmax labels, 0 when the kernels do not cover the shape
 int lanes_k(int64_t Lmax, int64_t V);
+bool ordered(int64_t B);        // the launches take the utterances by decreasing T_b (Params::order is used)
 inline int ck_row_elems(int K) { return 64 * K + 32; }
 inline int n_checkpoints(int64_t T) { return (int)((T / 2 + 1) / C) + 2; }
 

@@ -1644,7 +1644,7 @@ static inline int rows_aligned(const float *lp, int64_t st, int64_t sb, int64_t 
 // ctc_lin32.cu): every utterance of a small batch, 1/8 of a large one (beyond: NaN likelihood / gradient, loud)
 static inline int64_t lin_slots(int64_t B) { return B <= 32 ? B : std::max<int64_t>(32, B / 8); }
 
-struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, lin_fr, lin_ck, rows, total; };
+struct WsLayout { size_t nll2, abort_word, finals, zl, tabs, lin_fr, lin_ck, lin_order, rows, total; };
 static inline int tab_slots(int64_t T) { return (int)((T + 7) / 8) + 2; }  // >= chunks of T/2 frames (chunk >= 4) + 1
 // V < 0: the vocabulary is not known (ssak_ctc_loss_workspace_bytes); aligned < 0 with V > 128: the alignment of the
 // rows is not known (ssak_ctc_loss_workspace_bytes_v) -- in both cases room for either kernel family
@@ -1657,12 +1657,13 @@ static WsLayout ws_layout(int64_t T, int64_t B, int64_t V, int64_t Lmax, int row
     // abort word (+ the slot counter of the throughput mode at +4), then nan_flag[B], then the throughput kernels'
     // flags[B], slot[B] and slot_b[n_slots <= B]: one memset
     w.abort_word = o; o += 256 + 4 * align_up((size_t)B * sizeof(int), 256);
-    w.lin_fr = w.lin_ck = o;
+    w.lin_fr = w.lin_ck = w.lin_order = o;
     if (K > 0) {
         const size_t ck_row = (size_t)lin32::ck_row_elems(K);
         w.lin_fr = o; o += align_up((size_t)B * 2 * ck_row * sizeof(float), 256);
         w.lin_ck = o;
         if (saved) o += align_up((size_t)B * 2 * lin32::n_checkpoints(T) * ck_row * sizeof(float), 256);
+        w.lin_order = o; o += align_up((size_t)B * sizeof(int), 256);
     }
     w.finals = o; o += align_up((size_t)B * 2 * row_elems * sizeof(float), 256);
     w.zl = o;     o += align_up((size_t)B * (size_t)T * sizeof(float), 256);   // row normalisers (logits entry points)
@@ -1752,6 +1753,7 @@ static bool lin_params(const CtcParams &p, void *workspace, bool saved, lin32::P
     q->slot = reinterpret_cast<int *>(ws + w.abort_word + 256 + 2 * align_up((size_t)p.B * sizeof(int), 256));
     q->slot_b = reinterpret_cast<int *>(ws + w.abort_word + 256 + 3 * align_up((size_t)p.B * sizeof(int), 256));
     q->slot_counter = reinterpret_cast<int *>(ws + w.abort_word + 4);
+    q->order = lin32::ordered(p.B) ? reinterpret_cast<int *>(ws + w.lin_order) : nullptr;
     q->n_slots = saved ? (int)lin_slots(p.B) : (int)p.B;   // (no rows are stored without save_for_backward)
     q->grad_out = p.grad_out; q->grad = p.grad; q->gst = p.gst; q->gsb = p.gsb; q->zero_inf = p.zero_inf;
     q->save = saved ? 1 : 0;
@@ -1792,9 +1794,9 @@ extern "C" int ssak_ctc_loss_path_flags(const void *workspace, int64_t T, int64_
 
 // kernels of ours per forward + backward call pair (what bench.py reports as gpu_launches)
 extern "C" int ssak_ctc_loss_launches(int64_t B, int64_t V, int64_t max_target_len, int32_t logits) {
-    // throughput mode: memset excluded; forward: [row lse] lin32 fwd + lin32 join + masked log-domain fwd + join;
-    // backward: lin32 bwd + masked log-domain fwd + join + bwd.  Log-domain mode: fwd + join, bwd.
-    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B, 1, true) > 0 ? 9 : 3);
+    // throughput mode: memset excluded; forward: [row lse] [order] lin32 fwd + lin32 join + masked log-domain fwd +
+    // join; backward: lin32 bwd + masked log-domain fwd + join + bwd + orphans.  Log-domain mode: fwd + join, bwd.
+    return (logits ? 1 : 0) + (lin_k(max_target_len, V, B, 1, true) > 0 ? 9 + (lin32::ordered(B) ? 1 : 0) : 3);
 }
 
 static int forward_impl(const float *x, int64_t T, int64_t B, int64_t V, int64_t st, int64_t sb,

@@ -107,3 +107,25 @@ def test_eager_upstream_gradient(monkeypatch):
         ((ref * w.double()).sum() if red == "none" else ref * 3.0).backward()
         assert (g1.cpu().double() - y.grad).abs().max() <= 2e-5
         assert (x.grad.cpu().double() - y.grad).abs().max() <= 2e-5
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum", "mean_volume"])
+def test_sharded_wrapper_eager(reduction, monkeypatch):
+    """The sharded loss (world size 1) on the throughput kernels: both calls inside forward, the upstream gradient
+    (and 'mean_volume's denominator) applied in backward; one utterance of the batch is a tight one whose
+    provisional likelihood is revised."""
+    from ssak_b200.shard import sharded_ctc_loss
+    monkeypatch.setenv("SSAK_CTC_LIN32", "1")
+    x0, tg, il, tl, logits = _inputs("50 349 195 3 1 0 508654026")
+    x = x0.cuda().requires_grad_(True)
+    loss = sharded_ctc_loss(x, tg.cuda(), il.cuda(), tl.cuda(), 0, reduction, True, global_batch=3)
+    loss.backward(torch.tensor(0.5, device="cuda"))
+    y = x0.double().requires_grad_(True)
+    if reduction == "mean_volume":
+        nll = F.ctc_loss(y, tg, il, tl, 0, "none", True)
+        ref = nll.sum() / tl.sum()
+    else:
+        ref = F.ctc_loss(y, tg, il, tl, 0, reduction, True)
+    (0.5 * ref).backward()
+    assert abs(loss.item() - ref.item()) <= 2e-5 * max(abs(ref.item()), 1.0)
+    assert (x.grad.cpu().double() - y.grad).abs().max().item() <= 1e-4

@@ -211,10 +211,13 @@ def test_loss_full_size_c2(planted):
         assert (grad[int(il[b]):, b] == 0).all()
 
 
-def test_loss_aten_level_install():
-    """install(mode="aten"): torch's own F.ctc_loss (ATen composite + autograd) runs on the sm_100a kernels.
-    Runs last in this file: the registration cannot be undone within the process."""
-    import subprocess, sys, textwrap
+@pytest.mark.parametrize("lin32", ["0", "1"])
+def test_loss_aten_level_install(lin32):
+    """install(mode="aten"): torch's own F.ctc_loss (ATen composite + autograd) runs on the sm_100a kernels
+    (lin32 = 1: the throughput kernels forced, whose likelihood is final only after the backward call -- the
+    registration then runs both calls inside aten::_ctc_loss and hands the unit gradient on as `log_alpha`).
+    In a subprocess: the registration cannot be undone within the process."""
+    import os, subprocess, sys, textwrap
     code = textwrap.dedent("""
         import torch, torch.nn.functional as F, sys
         sys.path.insert(0, %r)
@@ -233,7 +236,8 @@ def test_loss_aten_level_install():
             assert (x.grad.cpu().double() - y.grad).abs().max() <= 1e-4, red
         print("aten ok")
     """ % __import__("conftest").ROOT)
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, SSAK_CTC_LIN32=lin32))
     assert out.returncode == 0 and "aten ok" in out.stdout, out.stdout + out.stderr
 
 

@@ -129,3 +129,31 @@ def test_sharded_wrapper_eager(reduction, monkeypatch):
     (0.5 * ref).backward()
     assert abs(loss.item() - ref.item()) <= 2e-5 * max(abs(ref.item()), 1.0)
     assert (x.grad.cpu().double() - y.grad).abs().max().item() <= 1e-4
+
+
+def test_default_dispatch_batch_with_tight_utterances():
+    """B = 256 through the DEFAULT dispatch (throughput kernels from B = 222 on): 240 ordinary utterances and 16
+    tight ones (170 .. 199 labels on 200 frames, planted peaks 1.7 x sharper) that end up on the log-domain kernels'
+    row blocks -- some already in forward (likelihood 0 in fp32 block floating point), some in backward."""
+    import ssak_b200
+    from ssak_b200.synth import ctc_batch
+    from test_gpu_lin32 import _path_flags
+    T, V = 200, 33
+    lp1, tg1, il1, tl1 = ctc_batch(240, T, V, 5, 60, 4242, Tmin=80)
+    lp2, tg2, il2, tl2 = ctc_batch(16, T, V, 170, 199, 4243, Tmin=T)
+    tg = torch.zeros(256, 199, dtype=tg1.dtype)
+    tg[:240, :tg1.shape[1]] = tg1
+    tg[240:, :tg2.shape[1]] = tg2
+    x0 = torch.cat([lp1, (lp2 * 1.7).log_softmax(-1)], 1)
+    il, tl = torch.cat([il1, il2]), torch.cat([tl1, tl2])
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(5))
+    x0, tg, il, tl = x0[:, perm].contiguous(), tg[perm], il[perm], tl[perm]
+    assert ssak_b200.lib().ssak_ctc_loss_nll_is_provisional(256, V, int(tl.max())) == 1
+    x = x0.cuda().requires_grad_(True)
+    loss = ssak_b200.ctc_loss(x, tg, il, tl, 0, "none", True)
+    loss.sum().backward()
+    _compare(loss, x.grad, x0, tg, il, tl, False)
+    fl, _, _ = _path_flags(x0, tg, il, tl)
+    tight = (tl >= 170)
+    assert (fl[~tight] == 0).all() and (fl & 4).sum() == 0
+    print("path flags of the tight utterances:", fl[tight].tolist())

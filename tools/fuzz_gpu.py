@@ -65,8 +65,13 @@ while time.time() < t_end:
         failures.append(("finite", case)); continue
     fin = torch.isfinite(r)
     if fin.any():
-        rel = ((l - r).abs() / r.abs().clamp_min(1.0))[fin].max().item()
-        if rel > max(1e-5, 1.5 * ref_lerr + 1e-5) + 1e-7 * float(il.sum()) / max(float(r[fin].abs().max()), 1.0):
+        # 1e-5 relative (absolute below 1), or 1.5 x the reference's own error, + one fp32 rounding of an O(1) term per
+        # frame (the row normalisers of the logits path, the emissions)
+        frames = float(il.max()) if red == "none" else float(il.sum())
+        tol = max(1e-5, 1.5 * ref_lerr + 1e-5) * r[fin].abs().clamp_min(1.0) + 2e-7 * frames
+        bad = ((l - r).abs()[fin] > tol)
+        if bad.any():
+            rel = ((l - r).abs() / r.abs().clamp_min(1.0))[fin].max().item()
             failures.append((f"loss {rel:.2e}", case)); continue
     err = (x.grad.cpu().double() - y.grad).abs().max().item()
     if err > max(1e-4, 1.5 * ref_gerr + 1e-5, 1e-6 * nll_max):

@@ -9,7 +9,7 @@ from ssak_b200.synth import align_batch, ctc_batch
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-t_end, n_loss, n_align, worst, above, failures = time.time() + budget, 0, 0, 0.0, [], []
+t_end, n_loss, n_align, n_greedy, worst, above, failures = time.time() + budget, 0, 0, 0, 0.0, [], []
 KNOBS = ("SSAK_CTC_LIN32", "SSAK_CTC_FWD_WAVE", "SSAK_CTC_FEW", "SSAK_CTC_SPLIT", "SSAK_ALIGN_LANE", "SSAK_ALIGN_WAVE")
 
 
@@ -35,6 +35,8 @@ while time.time() < t_end:
     Lmax = int(rng.integers(0, 224 if V > 128 else 416)) if not big else int(rng.integers(300, 1300))
     T = int(rng.integers(1, 260)) if not big else int(rng.integers(300, 900))
     B = int(rng.integers(1, 9)) if not big else int(rng.integers(1, 4))
+    if lin and rng.integers(0, 8) == 0:      # many chains at once: launch order, more hand-backs than a small batch
+        B, T = int(rng.integers(20, 33)), min(T, 120)   # (<= 32: a row block for every utterance, see lin_slots)
     planted = bool(rng.integers(0, 2))
     seed = int(rng.integers(1 << 30))
     lp, tg, il, tl = ctc_batch(B, T, V, 0, Lmax, seed, Tmin=1, planted=planted and V > 2)
@@ -105,7 +107,24 @@ while time.time() < t_end:
             failures.append(("align", f"{aknobs} V={V} Lmax={Lmax} T={T} B={B} kind={kind} first_as_garbage={fag} seed={aseed} b={b}"))
             break
     n_align += 1
+    # ---- greedy: argmax (first maximum) + collapse, rows with exact ties
+    if n_align % 4 == 0:
+        import itertools
+        V, T, B = int(rng.choice([1, 3, 33, 50, 257, 1024])), int(rng.integers(1, 90)), int(rng.integers(1, 6))
+        gseed = int(rng.integers(1 << 30))
+        gg = torch.Generator().manual_seed(gseed)
+        pr = torch.round(torch.randn(B, T, V, generator=gg) * 2) / 2
+        nfr = torch.randint(0, T + 1, (B,), generator=gg)
+        blank = int(rng.integers(0, V))
+        ids, out, lens = ssak_b200.greedy_ids(pr.cuda(), nfr, blank)
+        good = torch.equal(ids.cpu().long(), torch.argmax(pr, -1))
+        for b in range(B):
+            exp = [k for k, _ in itertools.groupby(torch.argmax(pr[b, : int(nfr[b])], -1).tolist()) if k != blank]
+            good = good and out[b, : int(lens[b])].cpu().tolist() == exp
+        if not good:
+            failures.append(("greedy", f"V={V} T={T} B={B} blank={blank} seed={gseed}"))
+        n_greedy += 1
 for f in failures:
     print("FAIL", f)
 print(f"fuzz {'ok' if not failures else 'FAILED'}: {n_loss} loss batches (worst gradient error {worst:.1e}; above 1e-5 -- utterances recomputed by the "
-      f"log-domain kernels: {above[:8]}), {n_align} aligner batches")
+      f"log-domain kernels: {above[:8]}), {n_align} aligner batches, {n_greedy} greedy batches")

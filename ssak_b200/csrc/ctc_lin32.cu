@@ -55,7 +55,14 @@ constexpr int ZDROP = 500;          // checkpoints drop lanes this many bits bel
 constexpr int WIN = 12;             // hysteresis of the re-scaling: lane maxima stay within [2^(TOP-WIN), 2^(TOP+4))
 constexpr int DMAX = 16;            // a lane's exponent is at most DMAX below its upstream neighbour's
 constexpr int EZERO = -(1 << 24);   // exponent wish of a lane that holds only zeros
-constexpr int MC = 4;               // copies of the posterior-mass vector (lanes 8c .. 8c+7 add into copy c)
+// Copies of the posterior-mass vector (the lanes of a warp add into copy lane / (32 / copies)).  INTERLEAVED layout,
+// mass[label][copy]: copy c only ever touches the banks = c (mod copies), so lanes of different copies never meet
+// in a bank, the 32 / copies lanes of one copy spread over 32 / copies banks, and the frame's reduction reads the
+// copies of a column as one or two 16-byte words.  8 copies for V <= 64, 4 beyond (shared memory per warp).
+#ifndef SSAK_MASS_IL
+#define SSAK_MASS_IL 1              // 0: the layout before (4 copies, mass[copy][label]) -- A/B builds
+#endif
+__host__ __device__ inline int mc_of(int V) { return SSAK_MASS_IL ? (V <= 64 ? 8 : 4) : 4; }
 constexpr int FIX = 30;             // posteriors are accumulated in 2^-FIX fixed point (integer adds: order-independent)
 constexpr int GMIN = -120;          // smallest exponent of the tile scale 2^(E_live + E_other - E_P)
 constexpr int GMAX = 127 - (TOP + DMAX + 2 * C + 2);   // largest exponent of tile scale x 2^FIX: tile entries stay finite
@@ -77,7 +84,7 @@ __host__ __device__ inline WarpSmem smem_map(int K, int V, bool grad) {
     int o = 0;
     m.ring = o;  o += (grad ? BWD_DEPTH : FWD_DEPTH) * C * (32 * nv_of(V) + 4) * 4;
     m.tile = o;  if (grad) o += C * 2 * K * 32 * 4;
-    m.mass = o;  if (grad) o += (MC * (V + 1) * 4 + 15) & ~15;
+    m.mass = o;  if (grad) o += (mc_of(V) * (V + 1) * 4 + 15) & ~15;
     m.total = (o + 127) & ~127;
     return m;
 }
@@ -124,7 +131,7 @@ __device__ __forceinline__ void make_skip(int q0, int L, int V, const int32_t *t
 //   state (as a; the consumer multiplies the blank sum by ebp once) and the label state the other direction pairs it
 //   with, which is exactly the carry.  MODE 2 (live direction): posteriors = (state before its emission) x tile
 //   entry, label posteriors added to mass[label] in fixed point.
-template <int K, int D, int MODE>
+template <int K, int D, int MODE, int MSH = 0>
 __device__ __forceinline__ void step(float (&a)[K], float (&l)[K], const float ebp, const unsigned char *yrow,
                                      const int (&labs)[K + 1], const float (&sk)[K], const float cin, float *tl,
                                      unsigned *mass, float &sbl) {
@@ -141,7 +148,7 @@ __device__ __forceinline__ void step(float (&a)[K], float (&l)[K], const float e
         }
         if (MODE == 2) {
             sbl = fmaf(A, tl[k * 32], sbl);
-            atomicAdd(reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(mass) + labs[k + 1 - D]),
+            atomicAdd(reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(mass) + (labs[k + 1 - D] << MSH)),
                       __float2uint_rn(t * tl[(K + k) * 32]));
         }
         carry = l[k];
@@ -592,7 +599,9 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
     // [MC][V + 1] label posterior mass of the frame in fixed point (integer adds: the sum does not depend on their
     // order); MC copies so that the ~L/V states of a label rarely meet in one shared-memory atomic (9 -> ~3 passes)
     unsigned *mass = reinterpret_cast<unsigned *>(mine + sm.mass);
-    unsigned *mass_mine = mass + (lane / (32 / MC)) * (V + 1);
+    constexpr int MC = SSAK_MASS_IL ? (NV == 2 ? 8 : 4) : 4;      // (= mc_of(V): NV == 2 <=> V <= 64)
+    constexpr int MSH = SSAK_MASS_IL ? (MC == 8 ? 3 : 2) : 0;     // label byte offset -> byte offset of its copies
+    unsigned *mass_mine = SSAK_MASS_IL ? mass + lane / (32 / MC) : mass + (lane / (32 / MC)) * (V + 1);
     const int q0 = lane * K;
     const bool live = q0 <= L;
     for (int cc = lane; cc < MC * (V + 1); cc += 32) mass[cc] = 0u;
@@ -716,7 +725,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                 const unsigned char *yrow = reinterpret_cast<const unsigned char *>(yrowf);
                 const float eb = *reinterpret_cast<const float *>(yrow + eoff_blank);
                 float sbl = 0.f;
-                step<K, DL, 2>(la, ll, ebpL, yrow, labs, sk, carry_in<K, DL>(ll, fL), tl + i * 2 * K * 32, mass_mine, sbl);
+                step<K, DL, 2, MSH>(la, ll, ebpL, yrow, labs, sk, carry_in<K, DL>(ll, fL), tl + i * 2 * K * 32, mass_mine, sbl);
                 ebpL = eb;
                 sbl *= i == 0 ? 1.f : eb;                       // (slot 0: the checkpoint's true blank states)
                 bad = bad || !(sbl <= 3.0e38f);                 // inf / NaN
@@ -732,11 +741,21 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                     mi[jj] = 0u;
                     if (cc < V) {
                         unsigned msum = cc == p.blank ? blank_mass : 0u;
+#if SSAK_MASS_IL
+                        uint4 *mp = reinterpret_cast<uint4 *>(mass + cc * MC);
+#pragma unroll
+                        for (int c2 = 0; c2 < MC / 4; ++c2) {
+                            const uint4 v4 = mp[c2];
+                            msum += (v4.x + v4.y) + (v4.z + v4.w);
+                            mp[c2] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+#else
 #pragma unroll
                         for (int c2 = 0; c2 < MC; ++c2) {
                             msum += mass[c2 * (V + 1) + cc];
                             mass[c2 * (V + 1) + cc] = 0u;
                         }
+#endif
                         mi[jj] = msum;
                     }
                     tot += mi[jj];

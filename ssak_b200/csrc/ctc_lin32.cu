@@ -62,7 +62,10 @@ constexpr int EZERO = -(1 << 24);   // exponent wish of a lane that holds only z
 #ifndef SSAK_MASS_IL
 #define SSAK_MASS_IL 1              // 0: the layout before (4 copies, mass[copy][label]) -- A/B builds
 #endif
-__host__ __device__ inline int mc_of(int V) { return SSAK_MASS_IL ? (V <= 64 ? 8 : 4) : 4; }
+#ifndef SSAK_MASS_MC
+#define SSAK_MASS_MC 8
+#endif
+__host__ __device__ inline int mc_of(int V) { return SSAK_MASS_IL ? (V <= 64 ? SSAK_MASS_MC : 4) : 4; }
 constexpr int FIX = 30;             // posteriors are accumulated in 2^-FIX fixed point (integer adds: order-independent)
 constexpr int GMIN = -120;          // smallest exponent of the tile scale 2^(E_live + E_other - E_P)
 constexpr int GMAX = 127 - (TOP + DMAX + 2 * C + 2);   // largest exponent of tile scale x 2^FIX: tile entries stay finite
@@ -599,8 +602,8 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
     // [MC][V + 1] label posterior mass of the frame in fixed point (integer adds: the sum does not depend on their
     // order); MC copies so that the ~L/V states of a label rarely meet in one shared-memory atomic (9 -> ~3 passes)
     unsigned *mass = reinterpret_cast<unsigned *>(mine + sm.mass);
-    constexpr int MC = SSAK_MASS_IL ? (NV == 2 ? 8 : 4) : 4;      // (= mc_of(V): NV == 2 <=> V <= 64)
-    constexpr int MSH = SSAK_MASS_IL ? (MC == 8 ? 3 : 2) : 0;     // label byte offset -> byte offset of its copies
+    constexpr int MC = SSAK_MASS_IL ? (NV == 2 ? SSAK_MASS_MC : 4) : 4;      // (= mc_of(V): NV == 2 <=> V <= 64)
+    constexpr int MSH = SSAK_MASS_IL ? (MC == 16 ? 4 : MC == 8 ? 3 : 2) : 0;   // label byte offset -> byte offset of its copies
     unsigned *mass_mine = SSAK_MASS_IL ? mass + lane / (32 / MC) : mass + (lane / (32 / MC)) * (V + 1);
     const int q0 = lane * K;
     const bool live = q0 <= L;
@@ -647,6 +650,9 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
         const bool logits = zl_b != nullptr;
         bool bad = false;
         float xmax = -1.f;
+        unsigned seen[NV];                                      // running sum of my columns' mass copies (see below)
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) seen[jj] = 0u;
         auto issue = [&](int n) {                               // tile n into ring stage n % DEPTH (empty group beyond the end)
             int j, row0, i0, nr;
             geometry(n, j, row0, i0, nr);
@@ -742,13 +748,17 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
                     if (cc < V) {
                         unsigned msum = cc == p.blank ? blank_mass : 0u;
 #if SSAK_MASS_IL
-                        uint4 *mp = reinterpret_cast<uint4 *>(mass + cc * MC);
+                        // the copies are never cleared: they run on (mod 2^32, like their sum) and the frame's mass
+                        // is the difference to the sum the last frame saw
+                        const uint4 *mp = reinterpret_cast<const uint4 *>(mass + cc * MC);
+                        unsigned run = 0u;
 #pragma unroll
                         for (int c2 = 0; c2 < MC / 4; ++c2) {
                             const uint4 v4 = mp[c2];
-                            msum += (v4.x + v4.y) + (v4.z + v4.w);
-                            mp[c2] = make_uint4(0u, 0u, 0u, 0u);
+                            run += (v4.x + v4.y) + (v4.z + v4.w);
                         }
+                        msum += run - seen[jj];
+                        seen[jj] = run;
 #else
 #pragma unroll
                         for (int c2 = 0; c2 < MC; ++c2) {

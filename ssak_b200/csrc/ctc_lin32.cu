@@ -299,26 +299,24 @@ __device__ __forceinline__ bool chain_of(const Params &p, Chain &c) {
 // B = 1024 is 2048 chains on 1776 places, and the 272 chains of the partial second wave start when the first ones
 // finish.  With the utterances in order of decreasing T_b the second wave holds the SHORTEST chains (and they run on
 // nearly empty SMs): longest-processing-time-first.  order[rank of b] = b, rank = number of utterances with a larger
-// T_b (ties by index): B^2 / 2 comparisons, nothing next to the recursion for the batch sizes this is used for.
+// T_b (ties by index): B^2 comparisons, one warp per utterance (3 us at B = 1024), B <= 8192.
 constexpr int ORDER_MAX_B = 8192;
-__global__ void __launch_bounds__(256) lin32_order_kernel(const Params p) {
-    __shared__ int tile[256];
-    const int b = blockIdx.x * 256 + threadIdx.x;
+__global__ void __launch_bounds__(256) lin32_order_kernel(const Params p) {   // one warp per utterance
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int B = (int)p.B;
+    if (b >= B) return;
     auto len_of = [&](int i) {
         const int t = p.in_len[i];
         return t < 0 ? 0 : (t > (int)p.T ? (int)p.T : t);
     };
-    const int mine = b < B ? len_of(b) : 0;
+    const int mine = len_of(b);
     int rank = 0;
-    for (int b0 = 0; b0 < B; b0 += 256) {
-        __syncthreads();
-        tile[threadIdx.x] = b0 + threadIdx.x < B ? len_of(b0 + threadIdx.x) : -1;
-        __syncthreads();
-        const int n = B - b0 < 256 ? B - b0 : 256;
-        for (int i = 0; i < n; ++i) rank += (tile[i] > mine || (tile[i] == mine && b0 + i < b)) ? 1 : 0;
+    for (int i = lane; i < B; i += 32) {
+        const int t = len_of(i);
+        rank += (t > mine || (t == mine && i < b)) ? 1 : 0;
     }
-    if (b < B) p.order[rank] = b;
+    rank = __reduce_add_sync(FULL, rank);
+    if (lane == 0) p.order[rank] = b;
 }
 
 // Emission staging: the warp converts its own rows.  Raw rows travel global -> shared with cp.async (LDGSTS: no
@@ -889,7 +887,7 @@ static int launch(const Params &p, cudaStream_t s) {
 
 int launch_forward(const Params &p, cudaStream_t s) {
     if (p.order) {
-        lin32_order_kernel<<<(unsigned)((p.B + 255) / 256), 256, 0, s>>>(p);
+        lin32_order_kernel<<<(unsigned)((p.B + 7) / 8), 256, 0, s>>>(p);
         int rc0 = check_launch();
         if (rc0 != SSAK_OK) return rc0;
     }

@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(32, BWD_WARPS) lin32_backward_kernel(const Par
     const WarpSmem sm = smem_map(K, V, true);
     unsigned char *mine = smem + (size_t)warp * sm.total;
     float *tile = reinterpret_cast<float *>(mine + sm.tile);       // [C][2K][32]
-    // [MC][V + 1] label posterior mass of the frame in fixed point (integer adds: the sum does not depend on their
-    // order); MC copies so that the ~L/V states of a label rarely meet in one shared-memory atomic (9 -> ~3 passes)
+    // [V + 1][MC] label posterior mass in fixed point (integer adds: the sum does not depend on their order); MC
+    // copies so that the ~L/V states of a label rarely meet in one shared-memory atomic (layout: see mc_of)
     unsigned *mass = reinterpret_cast<unsigned *>(mine + sm.mass);
     constexpr int MC = SSAK_MASS_IL ? (NV == 2 ? SSAK_MASS_MC : 4) : 4;      // (= mc_of(V): NV == 2 <=> V <= 64)
     constexpr int MSH = SSAK_MASS_IL ? (MC == 16 ? 4 : MC == 8 ? 3 : 2) : 0;   // label byte offset -> byte offset of its copies

@@ -440,8 +440,13 @@ def run_ours(args, rank, world, local_rank):
 
 
 def launches_per_step(lib, B, V, Lmax):
-    """Kernels of ours per loss call (forward group + backward group + the reduction), as the library reports them."""
-    return int(lib.ssak_ctc_loss_launches(B, V, Lmax, 0)) + 1
+    """Kernels of ours per loss call (forward group + backward group + the reduction), as the library reports them;
+    where the likelihood is final only after the backward call (throughput kernels) the wrapper reduces twice and
+    launches the upstream-gradient kernel."""
+    n = int(lib.ssak_ctc_loss_launches(B, V, Lmax, 0)) + 1
+    if lib.ssak_ctc_loss_nll_is_provisional(B, V, Lmax):
+        n += 2
+    return n
 
 
 def _timed_ms(fn, flush, n=7, warm=3):

@@ -112,3 +112,30 @@ def test_ctc_oracle_argument_errors():
         O.ctc_loss(lp, [[1]], [5], [1])           # input_length > T
     with pytest.raises(RuntimeError):
         O.ctc_loss(lp, [[1]], [4], [1], blank=3)   # blank outside the vocabulary
+
+
+def test_ctc_oracle_tight_alignments():
+    """The shapes the GPU fuzz found the kernels wrong on (tests/test_gpu_tight.py): targets nearly as long as the
+    input under peaky emissions that disagree with them, likelihoods of hundreds of nats.  The checker itself must
+    be right there: C restatement in fp64 against torch's CPU kernel in fp64, and in fp32 as close to the fp64
+    truth as torch's own fp32 kernel is."""
+    from ssak_b200.synth import ctc_batch
+    for case in ("33 121 122 8 1 0 971909417", "50 205 186 3 1 0 29280320", "33 256 147 3 1 0 224398287"):
+        V, Lmax, T, B, planted, _, seed = (int(v) for v in case.split())
+        lp, tg, il, tl = ctc_batch(B, T, V, 0, Lmax, seed, Tmin=1, planted=bool(planted))
+        tl = torch.minimum(tl, torch.tensor(Lmax))
+        il = torch.clamp(il, 1, T)
+        x = lp.double().requires_grad_(True)
+        ref = F.ctc_loss(x, tg, il, tl, 0, "none", True)
+        ref.sum().backward()
+        assert float(ref.detach().max()) > 100.0             # (the case is what it claims to be)
+        _, nll, g = O.ctc_loss(lp.numpy(), tg.numpy(), il.numpy(), tl.numpy(), 0, "sum", True, dtype=np.float64)
+        fin = np.isfinite(nll)
+        np.testing.assert_allclose(np.where(fin, nll, 0.0), ref.detach().numpy(), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(g, x.grad.numpy(), atol=1e-11)
+        x32 = lp.clone().requires_grad_(True)
+        F.ctc_loss(x32, tg, il, tl, 0, "sum", True).backward()
+        _, _, g32 = O.ctc_loss(lp.numpy(), tg.numpy(), il.numpy(), tl.numpy(), 0, "sum", True, dtype=np.float32)
+        err_o = np.abs(g32.astype(np.float64) - x.grad.numpy()).max()
+        err_t = (x32.grad.double() - x.grad).abs().max().item()
+        assert err_o <= max(1e-4, 2.0 * err_t + 1e-5), (err_o, err_t)

@@ -102,7 +102,12 @@ class _ShardedCTCFunction(torch.autograd.Function):
     kernels and are joined to the caller's stream at the end of backward().  Until then the returned loss is
     ordered on the side stream only (it is pre-filled with NaN on the caller's stream, so a premature read is loud,
     never a stale number); without gradients, and for 'mean_volume' (whose denominator IS the collective's result),
-    the join happens before forward returns."""
+    the join happens before forward returns.
+
+    Where the throughput kernels run (ssak_ctc_loss_nll_is_provisional) the likelihoods are final only after the
+    backward call, so forward() runs it too -- with the a-priori denominator -- packs the local sums from the final
+    likelihoods and only then starts the collective; backward() applies autograd's upstream gradient (a launch
+    without memory traffic when it is 1) and joins the side stream."""
 
     @staticmethod
     def forward(ctx, log_probs, targets, tgt_off, in_len, tgt_len, max_target_len, blank, zero_infinity,

@@ -1,5 +1,15 @@
-"""Randomised parity sweep of every kernel family (forced through the library's knobs on small shapes) against torch CPU fp64 / the C oracle:
-python tools/fuzz_gpu.py [seconds] [seed].  Checked against torch CPU fp64; bars: 1e-5 relative (loss), 1e-4 (gradient), or 1.5 x the error of torch's own fp32 CPU kernel where that is larger."""
+"""Randomised parity sweep of every kernel family on small shapes: python tools/fuzz_gpu.py [seconds] [seed]
+
+Loss: the library's knobs force the throughput kernels (SSAK_CTC_LIN32=1) or one of the log-domain variants
+(wavefront / barrier forward, few / many CTAs, posterior warps on / off) on shapes the default dispatch would not give
+them -- T <= 260, targets up to 415 labels (also longer than the input), V from 2 to 1024, log-probabilities or raw
+logits, every reduction; occasionally T <= 900 with targets up to 1300 labels -- against torch's CPU kernel in fp64.
+Bars: loss 1e-5 relative (absolute below 1) + one fp32 rounding per frame, gradient 1e-4; both widened to 1.5 x the
+error of torch's own fp32 CPU kernel on the same batch, the gradient also to 1e-6 x the largest likelihood (nats),
+where those are larger.  Aligner: lane / wavefront / barrier kernels, planted / random / exact-tie emissions, with and
+without first_as_garbage, bit-exact against the C oracle.  Greedy: argmax with exact ties + collapse.
+A failing loss case is replayed with tools/fuzz_case.py / tools/fuzz_diag.py, an aligner case with
+tools/fuzz_align_case.py; the cases found so far are pinned in tests/test_gpu_tight.py."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.nn.functional as F
